@@ -1,0 +1,172 @@
+"""Pins the CPU oracle to the reference's own known-answer tests."""
+import math
+import numpy as np
+import pytest
+
+from oracle.psp_hgh import PspHgh
+from oracle.basis import (Element, Model, PlaneWaveBasis, compute_fft_size, reducible_kcoords,
+                          index_G_vectors, Kpoint)
+from oracle.terms import (Terms, energy_hamiltonian, energy_ewald, energy_psp_correction,
+                          guess_density)
+from oracle import scf
+from silicon import LATTICE, POSITIONS, KCOORDS, KWEIGHTS
+
+
+def test_psp_hgh_values():
+    # reference: test/PspHgh.jl:41-84
+    psp = PspHgh.from_table("Si", "lda")
+    nrm = lambda v: np.array([np.linalg.norm(v)])
+    for v, ref in [([0.1, 0, 0], -400.395448865164), ([0.1, 0.2, 0], -80.39317320182417),
+                   ([0.1, 0.2, -0.3], -28.95951714682582), ([1.0, -2.0, 3.0], -0.275673388844235),
+                   ([10.0, 0, 0], -5.1468909215285576e-5)]:
+        assert psp.eval_local_fourier(nrm(v))[0] == pytest.approx(ref * 4 * math.pi, rel=1e-10)
+    pn = np.sqrt([0, 0.01, 0.1, 0.3, 1, 10])
+    np.testing.assert_allclose(psp.eval_projector_fourier(1, 0, pn),
+                               [6.503085484692629, 6.497277328372439, 6.445236803354619,
+                                6.331078654802208, 5.947214691896995, 2.661098803299718], rtol=1e-10)
+    np.testing.assert_allclose(psp.eval_projector_fourier(2, 0, pn),
+                               [10.074536712471094, 10.059542796942894, 9.925438587886482,
+                                9.632787375976731, 8.664551612201326, 1.666783598475508], rtol=1e-10)
+    np.testing.assert_allclose(psp.eval_projector_fourier(1, 1, pn) * pn,
+                               [0.0, 0.3149163627204332, 0.9853983576555614,
+                                1.667197861646941, 2.8039993470553535, 3.0863036233824626], rtol=1e-10)
+    np.testing.assert_allclose(psp.eval_projector_fourier(3, 1, pn) * pn,
+                               [0.0, 0.7482799478933317, 2.321676914155303,
+                                3.8541542745249706, 6.053770711942623, 1.6078748819430986], rtol=1e-10)
+
+
+def test_psp_parser_roundtrip():
+    # reference format: data/psp/hgh/lda/si-q4.hgh, parser src/pseudo/PspHgh.jl:25-93
+    text = ("Si GTH-PADE-q4 GTH-LDA-q4\n    2    2\n     0.44000000    1    -7.33610297\n    2\n"
+            "     0.42273813    2     5.90692831    -1.26189397\n"
+            "                                        3.25819622\n     0.48427842    1     2.72701346\n")
+    p, q = PspHgh.parse(text), PspHgh.from_table("Si", "lda")
+    assert p.Zion == q.Zion == 4 and p.rloc == q.rloc and p.lmax == 1
+    np.testing.assert_array_equal(p.cloc, q.cloc)
+    for a, b in zip(p.h, q.h):
+        np.testing.assert_array_equal(a, b)
+    assert p.rp == q.rp
+
+
+def test_compute_fft_size():
+    # reference: test/compute_fft_size.jl:6-12
+    for E, n in [(3, 15), (4, 15), (5, 18), (15, 27), (25, 36), (30, 40)]:
+        assert compute_fft_size(LATTICE, E) == (n, n, n)
+    assert compute_fft_size(LATTICE, 30, supersampling=1.8) == (36, 36, 36)
+
+
+def test_energy_nuclear():
+    # reference: test/energy_nuclear.jl:31,48 (ABINIT)
+    assert energy_ewald(LATTICE, [4, 4], POSITIONS) == pytest.approx(-8.39789357839024, abs=1e-10)
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, symmetries=False)
+    assert energy_psp_correction(m) == pytest.approx(-0.294622067023269, abs=1e-10)
+
+
+def test_G_index():
+    # reference: test/PlaneWaveBasis.jl:92-96 -- index of G=[-2,-3,-1] at k=[1/3,1/3,0], fft (7,9,11), Ecut 3
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, symmetries=False)
+    kpt = Kpoint(0, [1 / 3, 1 / 3, 0], m.recip_lattice, (7, 9, 11), 3)
+    lin = index_G_vectors((7, 9, 11), np.array([-2, -3, -1]))
+    pos = int(np.nonzero(kpt.mapping == lin)[0][0]) + 1
+    assert pos == 62
+
+
+def test_fft_roundtrip_and_dft_matrix():
+    # reference: test/fourier_transforms.jl:1-47
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, symmetries=False)
+    b = PlaneWaveBasis(m, 4, fft_size=(8, 9, 10), kcoords=[[0.1, 0.2, 0.3]], kweights=[1.0])
+    rng = np.random.default_rng(0)
+    f = rng.standard_normal(b.N) + 1j * rng.standard_normal(b.N)
+    np.testing.assert_allclose(b.fft_cube(b.ifft_cube(f)), f, atol=1e-12)
+    kpt = b.kpoints[0]
+    c = rng.standard_normal(kpt.n_G) + 1j * rng.standard_normal(kpt.n_G)
+    np.testing.assert_allclose(b.fft_kpt(kpt, b.ifft_kpt(kpt, c)), c, atol=1e-12)
+    # explicit DFT: f(r) = sum_G c_G e^{i2π G·r}/sqrt(Ω)
+    nx, ny, nz = b.fft_size
+    r = np.stack(np.meshgrid(np.arange(nz) / nz, np.arange(ny) / ny, np.arange(nx) / nx, indexing="ij"), -1)
+    r = r.reshape(-1, 3)[:, ::-1]
+    ph = np.exp(2j * math.pi * (r @ kpt.G_vectors.T))
+    np.testing.assert_allclose(b.ifft_kpt(kpt, c), ph @ c / math.sqrt(m.unit_cell_volume), atol=1e-12)
+
+
+def test_energies_guess_density():
+    # reference: test/energies_guess_density.jl:8-36 -- every energy term to 5e-8
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, functionals=("lda_x", "lda_c_vwn"), symmetries=False)
+    kc = reducible_kcoords((1, 2, 3), (0, 0.5, 0))
+    b = PlaneWaveBasis(m, 15, fft_size=(27, 27, 27), kcoords=kc, kweights=[1 / 6] * 6)
+    terms = Terms(b)
+    rho0 = guess_density(b)
+    E, H = energy_hamiltonian(b, terms, None, None, rho0)
+    assert E["Hartree"] == pytest.approx(0.3527293727197568, abs=5e-8)
+    assert E["Xc"] == pytest.approx(-2.3033165870558165, abs=5e-8)
+    res = scf.diagonalize_all_kblocks(H, 8, tol=1e-9)
+    assert res["converged"]
+    occ = [np.array([2., 2, 2, 2, 0, 0, 0, 0]) for _ in b.kpoints]
+    rho = scf.compute_density(b, res["X"], occ)
+    E, _ = energy_hamiltonian(b, terms, res["X"], occ, rho)
+    ref = dict(Kinetic=3.3824289861522194, AtomicLocal=-2.4178712046759157,
+               AtomicNonlocal=1.664289455206788, Hartree=0.6712993199211524,
+               Xc=-2.4489960475309056, Ewald=-8.397893578467201, PspCorrection=-0.294622067031369)
+    for k, v in ref.items():
+        assert E[k] == pytest.approx(v, abs=5e-8), k
+
+
+def test_lobpcg_free_electron():
+    # reference: test/lobpcg.jl:1-48
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, terms=("Kinetic",), symmetries=False)
+    b = PlaneWaveBasis(m, 5, fft_size=(15, 15, 15), kcoords=KCOORDS, kweights=KWEIGHTS)
+    _, H = energy_hamiltonian(b, Terms(b), None, None, np.zeros((1, b.N)))
+    ref = [[0.00000000000, 0.56219939834, 0.56219939834, 0.56219939834, 0.56219939834,
+            0.56219939834, 0.56219939834, 0.56219939834, 0.56219939834, 0.74959919778],
+           [0.06246659981, 0.24986639926, 0.49973279852, 0.49973279852, 0.49973279852,
+            0.56219939834, 0.56219939834, 0.56219939834, 0.74959919778, 0.74959919778],
+           [0.08328879975, 0.33315519901, 0.39562179883, 0.39562179883, 0.39562179883,
+            0.39562179883, 0.83288799753, 0.83288799754, 0.83288799754, 0.83288799754],
+           [0.16657759951, 0.22904419932, 0.22904419932, 0.41644399877, 0.41644399877,
+            0.66631039803, 0.72877699784, 0.72877699784, 0.72877699784, 0.72877699784]]
+    res = scf.diagonalize_all_kblocks(H, 10, tol=1e-8)
+    assert res["converged"]
+    for ik in range(4):
+        np.testing.assert_allclose(res["λ"][ik], ref[ik], atol=1e-8)
+        assert res["n_iter"][ik] < 50
+    res = scf.diagonalize_all_kblocks(H, 10, tol=1e-4, prec=False, maxiter=200)
+    for ik in range(4):
+        np.testing.assert_allclose(res["λ"][ik], ref[ik], atol=1e-4)
+
+
+@pytest.mark.slow
+def test_lobpcg_kinetic_local():
+    # reference: test/lobpcg.jl:50-75 (atol 5e-7)
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, terms=("Kinetic", "AtomicLocal"), symmetries=False)
+    b = PlaneWaveBasis(m, 25, fft_size=(33, 33, 33), kcoords=KCOORDS, kweights=KWEIGHTS)
+    _, H = energy_hamiltonian(b, Terms(b), None, None, np.zeros((1, b.N)))
+    res = scf.diagonalize_all_kblocks(H, 6, tol=1e-8)
+    ref = [[-4.087198659513310, -4.085326314828677, -0.506869382308294, -0.506869382280876, -0.506869381798614],
+           [-4.085824585443292, -4.085418874576503, -0.509716820984169, -0.509716820267449, -0.508545832298541],
+           [-4.086645155119840, -4.085209948598607, -0.514320642233337, -0.514320641863231, -0.499373272772206],
+           [-4.085991608422304, -4.085039856878318, -0.517299903754010, -0.513805498246478, -0.497036479690380]]
+    for ik in range(4):
+        np.testing.assert_allclose(res["λ"][ik][:5], ref[ik], atol=5e-7)
+
+
+def test_silicon_lda_scf_vs_abinit():
+    # reference: test/silicon_lda.jl:10-20,47-51 (Ecut 25, fft 33, eigenvalues 1e-5, Etot 1e-5)
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, functionals=("lda_x", "lda_c_vwn"))
+    assert len(m.symmetries) == 48
+    b = PlaneWaveBasis(m, 25, fft_size=(33, 33, 33), kcoords=KCOORDS, kweights=KWEIGHTS)
+    ref = [[-0.178566465714968, 0.261882541175914, 0.261882541178847, 0.261882541181782,
+            0.354070367072414, 0.354070367076363, 0.354070367080310, 0.376871160884678],
+           [-0.127794342370963, 0.064395861472044, 0.224958824747686, 0.224958824750934,
+            0.321313617512188, 0.388442495007398, 0.388442495010722, 0.542078732298094],
+           [-0.108449612789883, 0.077125812982728, 0.172380374761464, 0.172380374766260,
+            0.283802499666810, 0.329872296009131, 0.525606867582028, 0.525606867585921],
+           [-0.058089253154566, 0.012364292440522, 0.097350168867990, 0.183765652148129,
+            0.314593174568090, 0.470869435132365, 0.496966579772700, 0.517009645871194]]
+
+    def conv(info):
+        h = info["history_Etot"]
+        return len(h) > 1 and abs(h[-1] - h[-2]) < 1e-7
+    res = scf.self_consistent_field(b, nbandsalg=scf.AdaptiveBands(m, n_bands_converge=8), is_converged=conv)
+    assert res["energies"]["total"] == pytest.approx(-7.911817522631488, abs=1e-5)
+    for ik in range(4):
+        np.testing.assert_allclose(res["eigenvalues"][ik][:8], ref[ik], atol=1e-5)
