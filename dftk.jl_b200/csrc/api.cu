@@ -1,0 +1,485 @@
+// extern "C" entry points of libdftk_b200 (see include/dftk_b200.h for the contract).
+#include <mutex>
+#include "structs.cuh"
+
+using namespace dftk;
+
+static std::string g_last_error;
+static std::mutex g_err_mutex;
+
+static int record(dftk_b200_ctx* ctx, int code, const std::string& msg) {
+  {
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_error = msg;
+  }
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+#define API_BEGIN try {
+#define API_END(ctx)                                                        \
+  }                                                                         \
+  catch (const dftk::Error& e) { return record((ctx), e.code, e.what()); }  \
+  catch (const std::exception& e) { return record((ctx), DFTK_B200_EINVAL, e.what()); } \
+  return DFTK_B200_OK;
+
+// Stage a (possibly host) input buffer onto the device.  Returns a device pointer.
+static const void* stage_in(dftk_b200_ctx* ctx, const void* p, size_t bytes, DevBuf<char>& buf) {
+  if (is_device_ptr(p)) return p;
+  buf.ensure(bytes);
+  CUDA_CHECK(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return buf.p;
+}
+
+// Runs `fn(dev_in, dev_out)` with psi-like input/outputs that may live on the host.
+template <class F>
+static void with_staging(dftk_b200_ctx* ctx, const void* in, size_t in_bytes, void* out, size_t out_bytes,
+                         bool out_is_inout, F fn) {
+  const void* din = stage_in(ctx, in, in_bytes, ctx->stage_in);
+  if (is_device_ptr(out)) {
+    fn(din, out);
+    return;
+  }
+  ctx->stage_out.ensure(out_bytes);
+  if (out_is_inout) CUDA_CHECK(cudaMemcpyAsync(ctx->stage_out.p, out, out_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  fn(din, (void*)ctx->stage_out.p);
+  CUDA_CHECK(cudaMemcpyAsync(out, ctx->stage_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+extern "C" {
+
+const char* dftk_b200_last_error(dftk_b200_ctx* ctx) {
+  if (ctx) return ctx->last_error.c_str();
+  return g_last_error.c_str();
+}
+
+static int ctx_create_common(int device, dftk_b200_ctx** out) {
+  REQUIRE(out != nullptr, "ctx_create: out is NULL");
+  int ndev = 0;
+  CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  REQUIRE(device >= 0 && device < ndev, "ctx_create: no such CUDA device (the product path has no CPU fallback)");
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  REQUIRE(prop.major >= 10, "libdftk_b200 is built for sm_100a (Blackwell) only");
+  dftk_b200_ctx* c = new dftk_b200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->stream = 0;  // legacy default stream: ordered with the caller's default-stream work
+  CUBLAS_CHECK(cublasCreate(&c->cublas));
+  CUBLAS_CHECK(cublasSetStream(c->cublas, c->stream));
+  CUSOLVER_CHECK(cusolverDnCreate(&c->cusolver));
+  CUSOLVER_CHECK(cusolverDnSetStream(c->cusolver, c->stream));
+  fft_set_attributes();
+  blas_set_attributes();
+  *out = c;
+  return 0;
+}
+
+int dftk_b200_ctx_create(int device, dftk_b200_ctx** out) {
+  API_BEGIN
+  ctx_create_common(device, out);
+  API_END(nullptr)
+}
+
+int dftk_b200_nccl_unique_id(void* out128) {
+  API_BEGIN
+  REQUIRE(out128 != nullptr, "nccl_unique_id: out is NULL");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_CHECK(ncclGetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  API_END(nullptr)
+}
+
+int dftk_b200_ctx_create_dist(int device, const void* nccl_unique_id, int rank, int nranks,
+                              dftk_b200_ctx** out) {
+  API_BEGIN
+  REQUIRE(nccl_unique_id != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "ctx_create_dist: bad arguments");
+  ctx_create_common(device, out);
+  ncclUniqueId id;
+  memcpy(&id, nccl_unique_id, 128);
+  (*out)->rank = rank;
+  (*out)->nranks = nranks;
+  NCCL_CHECK(ncclCommInitRank(&(*out)->nccl, nranks, id, rank));
+  API_END(nullptr)
+}
+
+int dftk_b200_ctx_destroy(dftk_b200_ctx* ctx) {
+  if (!ctx) return DFTK_B200_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->nccl) ncclCommDestroy(ctx->nccl);
+  if (ctx->cublas) cublasDestroy(ctx->cublas);
+  if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
+  delete ctx;
+  return DFTK_B200_OK;
+}
+
+int dftk_b200_sync(dftk_b200_ctx* ctx) {
+  API_BEGIN
+  REQUIRE(ctx, "sync: ctx is NULL");
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+int dftk_b200_mem_info(dftk_b200_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes) {
+  API_BEGIN
+  size_t f = 0, t = 0;
+  CUDA_CHECK(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = (int64_t)f;
+  if (total_bytes) *total_bytes = (int64_t)t;
+  API_END(ctx)
+}
+
+int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset) {
+  if (!ctx) return -1;
+  int64_t v = ctx->launches;
+  if (reset) ctx->launches = 0;
+  return v;
+}
+
+int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
+  API_BEGIN
+  REQUIRE(ctx && name, "set_option: NULL argument");
+  std::string n(name);
+  if (n == "gemm_backend") ctx->gemm_backend = (int)value;
+  else if (n == "band_chunk") ctx->band_chunk = (int)value;
+  else throw Error(DFTK_B200_EINVAL, "set_option: unknown option " + n);
+  API_END(ctx)
+}
+
+// ------------------------------------------------------------------ grid
+int dftk_b200_grid_create(dftk_b200_ctx* ctx, int nx, int ny, int nz, double unit_cell_volume,
+                          dftk_b200_grid** out) {
+  API_BEGIN
+  REQUIRE(ctx && out, "grid_create: NULL argument");
+  REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && unit_cell_volume > 0, "grid_create: bad size / volume");
+  REQUIRE(ny <= 65535 && nz <= 65535, "grid_create: axis too long");
+  dftk_b200_grid* g = new dftk_b200_grid();
+  g->ctx = ctx;
+  g->nx = nx;
+  g->ny = ny;
+  g->nz = nz;
+  g->N = (int64_t)nx * ny * nz;
+  g->omega = unit_cell_volume;
+  g->ifft_norm = 1.0 / std::sqrt(unit_cell_volume);          // src/fft.jl:87
+  g->fft_norm = std::sqrt(unit_cell_volume) / (double)g->N;  // src/fft.jl:88
+  try {
+    g->px = make_plan(nx);
+    g->py = make_plan(ny);
+    g->pz = make_plan(nz);
+    g->Lx = choose_lines(nx);
+    g->Ly = choose_lines(ny);
+    g->Lz = choose_lines(nz);
+    auto tx = make_twiddles(nx), ty = make_twiddles(ny), tz = make_twiddles(nz);
+    g->twx.upload(tx.data(), tx.size(), ctx->stream);
+    g->twy.upload(ty.data(), ty.size(), ctx->stream);
+    g->twz.upload(tz.data(), tz.size(), ctx->stream);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  } catch (...) {
+    delete g;
+    throw;
+  }
+  *out = g;
+  API_END(ctx)
+}
+
+int dftk_b200_grid_destroy(dftk_b200_grid* grid) {
+  delete grid;
+  return DFTK_B200_OK;
+}
+
+int dftk_b200_fft_cube(dftk_b200_grid* grid, void* data, int direction, int64_t batch) {
+  dftk_b200_ctx* ctx = grid ? grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(grid && data, "fft_cube: NULL argument");
+  REQUIRE(direction == 1 || direction == -1, "fft_cube: direction must be +1 (backward) or -1 (forward)");
+  size_t bytes = (size_t)grid->N * batch * sizeof(cplx);
+  if (is_device_ptr(data)) {
+    fft_cube_inplace(grid, (cplx*)data, direction, batch);
+  } else {
+    cplx* d = (cplx*)stage_in(ctx, data, bytes, ctx->stage_in);
+    fft_cube_inplace(grid, d, direction, batch);
+    CUDA_CHECK(cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  API_END(ctx)
+}
+
+// ------------------------------------------------------------------ k-block
+int dftk_b200_kblock_create(dftk_b200_grid* grid, int64_t n_pw, const int64_t* mapping,
+                            const double* kin, int64_t n_proj, const void* P, const double* D, int spin,
+                            double kweight, dftk_b200_kblock** out) {
+  dftk_b200_ctx* ctx = grid ? grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(grid && mapping && out, "kblock_create: NULL argument");
+  REQUIRE(n_pw >= 1 && n_pw <= grid->N, "kblock_create: n_pw out of range");
+  REQUIRE(n_proj >= 0 && (n_proj == 0 || (P && D)), "kblock_create: projectors missing");
+  std::vector<int64_t> map_h(n_pw);
+  CUDA_CHECK(cudaMemcpy(map_h.data(), mapping, n_pw * sizeof(int64_t), cudaMemcpyDefault));
+  dftk_b200_kblock* kb = new dftk_b200_kblock();
+  try {
+    kb->grid = grid;
+    kb->n_pw = n_pw;
+    kb->n_proj = n_proj;
+    kb->spin = spin;
+    kb->kweight = kweight;
+    kb->Th = build_sphere_tables(grid->nx, grid->ny, grid->nz, n_pw, map_h.data());
+    const SphereTablesHost& H = kb->Th;
+    cudaStream_t s = ctx->stream;
+    kb->d_col_start.upload(H.col_start.data(), H.col_start.size(), s);
+    kb->d_col_cnt.upload(H.col_cnt.data(), H.col_cnt.size(), s);
+    kb->d_slot_ix.upload(H.slot_ix.data(), H.slot_ix.size(), s);
+    kb->d_slot_src.upload(H.slot_src.data(), H.slot_src.size(), s);
+    kb->d_zlist.upload(H.zlist.data(), H.zlist.size(), s);
+    kb->d_colmap.upload(H.colmap.data(), H.colmap.size(), s);
+    SphereTables& T = kb->T;
+    T.nx = H.nx; T.ny = H.ny; T.nz = H.nz; T.n_pw = n_pw; T.n_cols = H.n_cols; T.cnt_max = H.cnt_max;
+    T.n_zc = H.n_zc; T.col_start = kb->d_col_start.p; T.col_cnt = kb->d_col_cnt.p;
+    T.slot_ix = kb->d_slot_ix.p; T.slot_src = kb->d_slot_src.p; T.zlist = kb->d_zlist.p;
+    T.colmap = kb->d_colmap.p;
+    if (kin) {
+      kb->kin.ensure(n_pw);
+      CUDA_CHECK(cudaMemcpyAsync(kb->kin.p, kin, n_pw * sizeof(double), cudaMemcpyDefault, s));
+      kb->has_kin = true;
+    }
+    if (n_proj > 0) {
+      kb->P.ensure((size_t)n_pw * n_proj);
+      CUDA_CHECK(cudaMemcpyAsync(kb->P.p, P, (size_t)n_pw * n_proj * sizeof(cplx), cudaMemcpyDefault, s));
+      kb->D_host.resize((size_t)n_proj * n_proj);
+      CUDA_CHECK(cudaMemcpy(kb->D_host.data(), D, (size_t)n_proj * n_proj * sizeof(double), cudaMemcpyDefault));
+      std::vector<double> dc(2 * (size_t)n_proj * n_proj, 0.0);
+      for (size_t i = 0; i < (size_t)n_proj * n_proj; ++i) dc[2 * i] = kb->D_host[i];
+      kb->Dc.ensure((size_t)n_proj * n_proj);
+      CUDA_CHECK(cudaMemcpyAsync(kb->Dc.p, dc.data(), dc.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  } catch (...) {
+    delete kb;
+    throw;
+  }
+  *out = kb;
+  API_END(ctx)
+}
+
+int dftk_b200_kblock_destroy(dftk_b200_kblock* kb) {
+  delete kb;
+  return DFTK_B200_OK;
+}
+
+__global__ void k_scale_copy(double* dst, const double* src, double f, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * f;
+}
+
+int dftk_b200_kblock_set_potential(dftk_b200_kblock* kb, const double* V) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb, "set_potential: kblock is NULL");
+  if (!V) {
+    kb->has_V = false;
+    return DFTK_B200_OK;
+  }
+  const int64_t N = kb->grid->N;
+  const double* d = (const double*)stage_in(ctx, V, N * sizeof(double), ctx->stage_in);
+  kb->V.ensure(N);
+  // pre-scale by fft_normalization * ifft_normalization = 1/N (src/terms/Hamiltonian.jl:152-153)
+  LAUNCH(ctx, k_scale_copy, (unsigned)((N + 255) / 256), 256, 0, kb->V.p, d, kb->grid->fft_norm * kb->grid->ifft_norm, N);
+  kb->has_V = true;
+  API_END(ctx)
+}
+
+int dftk_b200_fft_sphere_to_real(dftk_b200_kblock* kb, const void* psi, void* out_real, int64_t n_bands,
+                                 int normalize) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && psi && out_real && n_bands >= 0, "fft_sphere_to_real: bad argument");
+  with_staging(ctx, psi, (size_t)kb->n_pw * n_bands * sizeof(cplx), out_real,
+               (size_t)kb->grid->N * n_bands * sizeof(cplx), false, [&](const void* i, void* o) {
+                 kb_sphere_to_real(kb, (const cplx*)i, (cplx*)o, n_bands, normalize ? kb->grid->ifft_norm : 1.0);
+               });
+  API_END(ctx)
+}
+
+int dftk_b200_fft_real_to_sphere(dftk_b200_kblock* kb, const void* in_real, void* out, int64_t n_bands,
+                                 int normalize) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && in_real && out && n_bands >= 0, "fft_real_to_sphere: bad argument");
+  with_staging(ctx, in_real, (size_t)kb->grid->N * n_bands * sizeof(cplx), out,
+               (size_t)kb->n_pw * n_bands * sizeof(cplx), false, [&](const void* i, void* o) {
+                 kb_real_to_sphere(kb, (const cplx*)i, (cplx*)o, n_bands, normalize ? kb->grid->fft_norm : 1.0);
+               });
+  API_END(ctx)
+}
+
+int dftk_b200_apply_terms(dftk_b200_kblock* kb, const void* psi, void* hpsi, int64_t n_bands, int parts,
+                          int accumulate) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && psi && hpsi && n_bands >= 0, "apply: bad argument");
+  REQUIRE(psi != hpsi, "apply: psi and hpsi must not alias");
+  const bool loc = parts & 1, kinp = parts & 2, nl = parts & 4;
+  REQUIRE(!kinp || kb->has_kin, "apply: kinetic energies were not given to kblock_create");
+  size_t bytes = (size_t)kb->n_pw * n_bands * sizeof(cplx);
+  with_staging(ctx, psi, bytes, hpsi, bytes, accumulate != 0, [&](const void* i, void* o) {
+    if (loc || kinp) kb_apply_local_kinetic(kb, (const cplx*)i, (cplx*)o, n_bands, loc, kinp, accumulate != 0);
+    else if (!accumulate) CUDA_CHECK(cudaMemsetAsync(o, 0, bytes, ctx->stream));
+    if (nl) kb_apply_nonlocal(kb, (const cplx*)i, (cplx*)o, n_bands);
+  });
+  API_END(ctx)
+}
+
+int dftk_b200_apply_h(dftk_b200_kblock* kb, const void* psi, void* hpsi, int64_t n_bands) {
+  if (!kb) return record(nullptr, DFTK_B200_EINVAL, "apply_h: kblock is NULL");
+  int parts = (kb->has_V ? 1 : 0) | (kb->has_kin ? 2 : 0) | (kb->n_proj > 0 ? 4 : 0);
+  return dftk_b200_apply_terms(kb, psi, hpsi, n_bands, parts, 0);
+}
+
+__global__ void k_nonlocal_band_energy(const cplx* proj, const cplx* dproj, int64_t np, int64_t nb,
+                                       double* out) {
+  // one thread per band: sum_i real(conj(proj) * dproj)
+  int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  double s = 0.0;
+  for (int64_t i = 0; i < np; ++i) {
+    cplx a = proj[i + np * b], d = dproj[i + np * b];
+    s += a.x * d.x + a.y * d.y;
+  }
+  out[b] = s;
+}
+
+int dftk_b200_band_energies(dftk_b200_kblock* kb, const void* psi, int64_t n_bands, double* ekin_host,
+                            double* enl_host) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && psi && n_bands >= 0, "band_energies: bad argument");
+  if (n_bands == 0) return DFTK_B200_OK;
+  const cplx* d = (const cplx*)stage_in(ctx, psi, (size_t)kb->n_pw * n_bands * sizeof(cplx), ctx->stage_in);
+  double* sc = ctx->scal.ensure(2 * n_bands + 8);
+  if (ekin_host) {
+    REQUIRE(kb->has_kin, "band_energies: no kinetic term");
+    kin_dots(ctx, d, kb->n_pw, kb->kin.p, kb->n_pw, n_bands, sc);
+    CUDA_CHECK(cudaMemcpyAsync(ekin_host, sc, n_bands * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (enl_host) {
+    if (kb->n_proj == 0) {
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      for (int64_t i = 0; i < n_bands; ++i) enl_host[i] = 0.0;
+    } else {
+      const int64_t np = kb->n_proj;
+      cplx* proj = kb->proj.ensure((size_t)2 * np * n_bands);
+      cplx* dproj = proj + (size_t)np * n_bands;
+      const cplx one = make_double2(1, 0), zero = make_double2(0, 0);
+      zgemm(ctx, 2, np, n_bands, kb->n_pw, one, kb->P.p, kb->n_pw, d, kb->n_pw, zero, proj, np);
+      zgemm(ctx, 0, np, n_bands, np, one, kb->Dc.p, np, proj, np, zero, dproj, np);
+      LAUNCH(ctx, k_nonlocal_band_energy, (unsigned)((n_bands + 63) / 64), 64, 0, (const cplx*)proj,
+             (const cplx*)dproj, np, n_bands, sc + n_bands);
+      CUDA_CHECK(cudaMemcpyAsync(enl_host, sc + n_bands, n_bands * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+int dftk_b200_lobpcg(dftk_b200_kblock* kb, void* X, int64_t n_bands, double tol, int miniter, int maxiter,
+                     int64_t n_conv_check, int use_tpa_preconditioner, double* lambda_host,
+                     double* resid_host, int* n_iter, int64_t* n_matvec, int* converged) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && X && lambda_host && resid_host && n_iter && n_matvec && converged, "lobpcg: NULL argument");
+  REQUIRE(maxiter >= 0 && miniter >= 0, "lobpcg: bad iteration limits");
+  size_t bytes = (size_t)kb->n_pw * n_bands * sizeof(cplx);
+  if (is_device_ptr(X)) {
+    lobpcg_run(kb, (cplx*)X, n_bands, tol, miniter, maxiter, n_conv_check, use_tpa_preconditioner != 0,
+               lambda_host, resid_host, n_iter, n_matvec, converged);
+  } else {
+    ctx->stage_out.ensure(bytes);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->stage_out.p, X, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    lobpcg_run(kb, (cplx*)ctx->stage_out.p, n_bands, tol, miniter, maxiter, n_conv_check,
+               use_tpa_preconditioner != 0, lambda_host, resid_host, n_iter, n_matvec, converged);
+    CUDA_CHECK(cudaMemcpyAsync(X, ctx->stage_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  API_END(ctx)
+}
+
+int dftk_b200_density_accumulate(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host,
+                                 int64_t n_bands, double* rho) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && psi && occ_w_host && rho && n_bands >= 0, "density_accumulate: bad argument");
+  const cplx* d = (const cplx*)stage_in(ctx, psi, (size_t)kb->n_pw * n_bands * sizeof(cplx), ctx->stage_in);
+  if (is_device_ptr(rho)) {
+    kb_density_accumulate(kb, d, occ_w_host, n_bands, rho);
+  } else {
+    size_t bytes = (size_t)kb->grid->N * sizeof(double);
+    ctx->stage_out.ensure(bytes);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->stage_out.p, rho, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    kb_density_accumulate(kb, d, occ_w_host, n_bands, (double*)ctx->stage_out.p);
+    CUDA_CHECK(cudaMemcpyAsync(rho, ctx->stage_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  API_END(ctx)
+}
+
+// ------------------------------------------------------------------ collectives
+static ncclDataType_t nccl_type(int dtype) {
+  if (dtype == DFTK_B200_F64) return ncclFloat64;
+  if (dtype == DFTK_B200_I64) return ncclInt64;
+  throw Error(DFTK_B200_EINVAL, "collective: unknown dtype");
+}
+
+int dftk_b200_allreduce(dftk_b200_ctx* ctx, void* buf, int64_t count, int dtype, int op) {
+  API_BEGIN
+  REQUIRE(ctx && buf && count >= 0, "allreduce: bad argument");
+  if (ctx->nranks == 1) return DFTK_B200_OK;
+  REQUIRE(ctx->nccl, "allreduce: context has no communicator (use ctx_create_dist)");
+  REQUIRE(is_device_ptr(buf), "allreduce: buffer must be device memory");
+  ncclRedOp_t o = op == 0 ? ncclSum : (op == 1 ? ncclMin : ncclMax);
+  NCCL_CHECK(ncclAllReduce(buf, buf, (size_t)count, nccl_type(dtype), o, ctx->nccl, ctx->stream));
+  ctx->launches++;
+  API_END(ctx)
+}
+
+int dftk_b200_allgather(dftk_b200_ctx* ctx, const void* send, void* recv, int64_t count_per_rank, int dtype) {
+  API_BEGIN
+  REQUIRE(ctx && send && recv && count_per_rank >= 0, "allgather: bad argument");
+  if (ctx->nranks == 1) {
+    if (send != recv)
+      CUDA_CHECK(cudaMemcpyAsync(recv, send, (size_t)count_per_rank * 8, cudaMemcpyDefault, ctx->stream));
+    return DFTK_B200_OK;
+  }
+  REQUIRE(ctx->nccl, "allgather: context has no communicator (use ctx_create_dist)");
+  NCCL_CHECK(ncclAllGather(send, recv, (size_t)count_per_rank, nccl_type(dtype), ctx->nccl, ctx->stream));
+  ctx->launches++;
+  API_END(ctx)
+}
+
+// ------------------------------------------------------------------ dense helpers
+int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,
+                              int64_t n_cols, void* out_host) {
+  API_BEGIN
+  REQUIRE(ctx && A && B && out_host, "columnwise_dots: NULL argument");
+  REQUIRE(is_device_ptr(A) && is_device_ptr(B), "columnwise_dots: inputs must be device memory");
+  cplx* o = (cplx*)ctx->scal.ensure(2 * n_cols + 8);
+  columnwise_dots(ctx, (const cplx*)A, n_rows, (const cplx*)B, n_rows, n_rows, n_cols, o);
+  CUDA_CHECK(cudaMemcpyAsync(out_host, o, n_cols * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+int dftk_b200_zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, const double* alpha2,
+                    const void* A, int64_t lda, const void* B, int64_t ldb, const double* beta2, void* C,
+                    int64_t ldc) {
+  API_BEGIN
+  REQUIRE(ctx && A && B && C && alpha2 && beta2, "zgemm: NULL argument");
+  REQUIRE(is_device_ptr(A) && is_device_ptr(B) && is_device_ptr(C), "zgemm: operands must be device memory");
+  zgemm(ctx, transA, m, n, k, make_double2(alpha2[0], alpha2[1]), (const cplx*)A, lda, (const cplx*)B, ldb,
+        make_double2(beta2[0], beta2[1]), (cplx*)C, ldc);
+  API_END(ctx)
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Common infrastructure of libdftk_b200: context, error handling, device buffers, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/dftk_b200.h"
+#include "fft_core.cuh"
+
+namespace dftk {
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      throw ::dftk::Error(DFTK_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) +  \
+                                               " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+#define CUBLAS_CHECK(expr)                                                                       \
+  do {                                                                                           \
+    cublasStatus_t _s = (expr);                                                                  \
+    if (_s != CUBLAS_STATUS_SUCCESS)                                                             \
+      throw ::dftk::Error(DFTK_B200_ECUDA, std::string(#expr) + ": cublas status " + std::to_string((int)_s)); \
+  } while (0)
+#define CUSOLVER_CHECK(expr)                                                                     \
+  do {                                                                                           \
+    cusolverStatus_t _s = (expr);                                                                \
+    if (_s != CUSOLVER_STATUS_SUCCESS)                                                           \
+      throw ::dftk::Error(DFTK_B200_ECUDA, std::string(#expr) + ": cusolver status " + std::to_string((int)_s)); \
+  } while (0)
+#define NCCL_CHECK(expr)                                                                         \
+  do {                                                                                           \
+    ncclResult_t _r = (expr);                                                                    \
+    if (_r != ncclSuccess)                                                                       \
+      throw ::dftk::Error(DFTK_B200_ENCCL, std::string(#expr) + ": " + ncclGetErrorString(_r));  \
+  } while (0)
+#define REQUIRE(cond, msg)                                              \
+  do {                                                                  \
+    if (!(cond)) throw ::dftk::Error(DFTK_B200_EINVAL, std::string(msg)); \
+  } while (0)
+
+// Growable device buffer (the library's scratch arena is a handful of these; they only ever grow).
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  T* ensure(size_t n) {
+    if (n > cap) {
+      release();
+      CUDA_CHECK(cudaMalloc((void**)&p, n * sizeof(T)));
+      cap = n;
+    }
+    return p;
+  }
+  void upload(const T* host, size_t n, cudaStream_t s) {
+    ensure(n);
+    if (n) CUDA_CHECK(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyDefault, s));
+  }
+};
+
+}  // namespace dftk
+
+struct dftk_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = 0;
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  ncclComm_t nccl = nullptr;
+  int rank = 0, nranks = 1;
+  int64_t launches = 0;
+  int gemm_backend = 0;   // 0 = own DMMA kernels, 1 = cuBLAS (A/B comparison only)
+  int band_chunk = 0;     // 0 = auto
+  int sm_count = 148;
+  std::string last_error;
+  dftk::DevBuf<char> solver_work;
+  dftk::DevBuf<int> dev_info;
+  dftk::DevBuf<double> scal;     // small scalar scratch
+  dftk::DevBuf<char> gemm_ws;    // split-K partials
+  dftk::DevBuf<char> stage_in, stage_out;  // host<->device staging for host-buffer calls
+};
+
+namespace dftk {
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                     \
+  do {                                                                  \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+    (ctx)->launches++;                                                  \
+    CUDA_CHECK(cudaGetLastError());                                     \
+  } while (0)
+
+inline bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+}  // namespace dftk

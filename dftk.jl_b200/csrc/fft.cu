@@ -1,0 +1,241 @@
+// CUDA kernels (thin __global__ wrappers over the stage bodies of fft_core.cuh) and host drivers of
+// the batched, pruned sphere<->cube FFT pipeline.  Reference semantics: src/fft.jl:106-172 (ifft!/fft!
+// with Gvec_mapping) and the "local" part of mul!(::DftHamiltonianBlock), src/terms/Hamiltonian.jl:152-163.
+#include "structs.cuh"
+
+namespace dftk {
+
+#define FFT_THREADS 256
+extern __shared__ __align__(16) unsigned char dyn_smem[];
+
+__global__ void __launch_bounds__(FFT_THREADS)
+k_sphere_to_x(SphereTables T, FftPlan px, const cplx* twx, const cplx* psi, int64_t ldpsi, cplx* W1,
+              int L, int Lp) {
+  stage_sphere_to_x(T, px, twx, psi, ldpsi, W1, L, Lp, (cplx*)dyn_smem,
+                    Dim3i{(int)blockIdx.x, (int)blockIdx.y, 0});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_y_backward(SphereTables T, FftPlan py, const cplx* twy, const cplx* W1, cplx* W2, int L, int Lp) {
+  stage_y_backward(T, py, twy, W1, W2, L, Lp, (cplx*)dyn_smem,
+                   Dim3i{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_z_apply_potential(SphereTables T, FftPlan pz, const cplx* twz, cplx* W2, const double* V, int L,
+                    int Lp) {
+  stage_z_apply_potential(T, pz, twz, W2, V, L, Lp, (cplx*)dyn_smem,
+                          Dim3i{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_z_to_cube(SphereTables T, FftPlan pz, const cplx* twz, const cplx* W2, cplx* cube, double scale,
+            int L, int Lp) {
+  stage_z_to_cube(T, pz, twz, W2, cube, scale, L, Lp, (cplx*)dyn_smem,
+                  Dim3i{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_z_from_cube(SphereTables T, FftPlan pz, const cplx* twz, const cplx* cube, cplx* W2, int L, int Lp) {
+  stage_z_from_cube(T, pz, twz, cube, W2, L, Lp, (cplx*)dyn_smem,
+                    Dim3i{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_z_density(SphereTables T, FftPlan pz, const cplx* twz, const cplx* W2, const double* wts, int nb,
+            double* rho, int L, int Lp) {
+  stage_z_density(T, pz, twz, W2, wts, nb, rho, L, Lp, (cplx*)dyn_smem,
+                  Dim3i{(int)blockIdx.x, (int)blockIdx.y, 0});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_y_forward(SphereTables T, FftPlan py, const cplx* twy, const cplx* W2, cplx* W1, int L, int Lp) {
+  stage_y_forward(T, py, twy, W2, W1, L, Lp, (cplx*)dyn_smem,
+                  Dim3i{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_x_to_sphere(SphereTables T, FftPlan px, const cplx* twx, const cplx* W1, cplx* out, int64_t ldout,
+              double scale, const double* kin, const cplx* psi, int64_t ldpsi, int accumulate, int L,
+              int Lp) {
+  stage_x_to_sphere(T, px, twx, W1, out, ldout, scale, kin, psi, ldpsi, accumulate, L, Lp,
+                    (cplx*)dyn_smem, Dim3i{(int)blockIdx.x, (int)blockIdx.y, 0});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_cube_pass_x(cplx* data, int nx, int64_t n_lines, FftPlan px, const cplx* twx, int sign, int L, int Lp) {
+  cube_pass_x(data, nx, n_lines, px, twx, sign, L, Lp, (cplx*)dyn_smem,
+              Dim3i{(int)blockIdx.x, (int)blockIdx.y, 0});
+}
+__global__ void __launch_bounds__(FFT_THREADS)
+k_cube_pass_strided(cplx* data, int nx, int n, int64_t stride_line, int64_t stride_outer,
+                    int64_t cube_size, FftPlan p, const cplx* tw, int sign, int L, int Lp) {
+  cube_pass_strided(data, nx, n, stride_line, stride_outer, cube_size, p, tw, sign, L, Lp,
+                    (cplx*)dyn_smem, Dim3i{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z});
+}
+
+static const int kMaxSmem = 200 * 1024;
+
+void fft_set_attributes() {
+#define SETATTR(k) CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem))
+  SETATTR(k_sphere_to_x);
+  SETATTR(k_y_backward);
+  SETATTR(k_z_apply_potential);
+  SETATTR(k_z_to_cube);
+  SETATTR(k_z_from_cube);
+  SETATTR(k_z_density);
+  SETATTR(k_y_forward);
+  SETATTR(k_x_to_sphere);
+  SETATTR(k_cube_pass_x);
+  SETATTR(k_cube_pass_strided);
+#undef SETATTR
+}
+
+static inline size_t smem_for(int n, int L) { return 2 * (size_t)n * (L | 1) * sizeof(cplx); }
+static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// CUDA limits gridDim.y/z to 65535: fine for every axis length the engine supports.
+void fft_cube_inplace(dftk_b200_grid* g, cplx* data, int sign, int64_t batch) {
+  dftk_b200_ctx* ctx = g->ctx;
+  const int nx = g->nx, ny = g->ny, nz = g->nz;
+  REQUIRE(batch <= 65535, "fft_cube: batch too large");
+  {
+    int L = g->Lx, Lp = L | 1;
+    int64_t nl = (int64_t)ny * nz;
+    LAUNCH(ctx, k_cube_pass_x, dim3(cdiv(nl, L), (unsigned)batch), FFT_THREADS, smem_for(nx, L),
+           data, nx, nl, g->px, (const cplx*)g->twx.p, sign, L, Lp);
+  }
+  if (ny > 1) {
+    int L = g->Ly, Lp = L | 1;
+    LAUNCH(ctx, k_cube_pass_strided, dim3(cdiv(nx, L), nz, (unsigned)batch), FFT_THREADS,
+           smem_for(ny, L), data, nx, ny, (int64_t)nx, (int64_t)nx * ny, g->N, g->py,
+           (const cplx*)g->twy.p, sign, L, Lp);
+  }
+  if (nz > 1) {
+    int L = g->Lz, Lp = L | 1;
+    LAUNCH(ctx, k_cube_pass_strided, dim3(cdiv(nx, L), ny, (unsigned)batch), FFT_THREADS,
+           smem_for(nz, L), data, nx, nz, (int64_t)nx * ny, (int64_t)nx, g->N, g->pz,
+           (const cplx*)g->twz.p, sign, L, Lp);
+  }
+}
+
+int band_chunk_for(dftk_b200_kblock* kb, int64_t n_bands) {
+  dftk_b200_grid* g = kb->grid;
+  int64_t chunk = g->ctx->band_chunk;
+  if (chunk <= 0) {
+    // enough CTAs to fill the machine several times over, bounded scratch (<= ~4 GiB)
+    size_t per_band = ((size_t)kb->Th.n_cols * g->nx + (size_t)kb->Th.n_zc * g->ny * g->nx) * sizeof(cplx);
+    chunk = (int64_t)((size_t)4 << 30) / (int64_t)(per_band ? per_band : 1);
+    if (chunk > 64) chunk = 64;
+    if (chunk < 1) chunk = 1;
+  }
+  if (chunk > n_bands) chunk = n_bands;
+  if (chunk > 65535) chunk = 65535;
+  return (int)chunk;
+}
+
+static void ensure_scratch(dftk_b200_kblock* kb, int nb) {
+  dftk_b200_grid* g = kb->grid;
+  kb->W1.ensure((size_t)nb * kb->Th.n_cols * g->nx);
+  kb->W2.ensure((size_t)nb * kb->Th.n_zc * g->ny * g->nx);
+}
+
+void kb_sphere_to_planes(dftk_b200_kblock* kb, const cplx* psi, int64_t ldpsi, int nb) {
+  dftk_b200_grid* g = kb->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  ensure_scratch(kb, nb);
+  {
+    int L = g->Lx, Lp = L | 1;
+    LAUNCH(ctx, k_sphere_to_x, dim3(cdiv(kb->T.n_cols, L), nb), FFT_THREADS, smem_for(g->nx, L), kb->T,
+           g->px, (const cplx*)g->twx.p, psi, ldpsi, kb->W1.p, L, Lp);
+  }
+  {
+    int L = g->Ly, Lp = L | 1;
+    LAUNCH(ctx, k_y_backward, dim3(cdiv(g->nx, L), kb->T.n_zc, nb), FFT_THREADS, smem_for(g->ny, L),
+           kb->T, g->py, (const cplx*)g->twy.p, (const cplx*)kb->W1.p, kb->W2.p, L, Lp);
+  }
+}
+
+void kb_planes_to_sphere(dftk_b200_kblock* kb, cplx* out, int64_t ldout, int nb, double scale,
+                         const double* kin, const cplx* psi, int64_t ldpsi, int accumulate) {
+  dftk_b200_grid* g = kb->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  {
+    int L = g->Ly, Lp = L | 1;
+    LAUNCH(ctx, k_y_forward, dim3(cdiv(g->nx, L), kb->T.n_zc, nb), FFT_THREADS, smem_for(g->ny, L),
+           kb->T, g->py, (const cplx*)g->twy.p, (const cplx*)kb->W2.p, kb->W1.p, L, Lp);
+  }
+  {
+    int L = g->Lx, Lp = L | 1;
+    LAUNCH(ctx, k_x_to_sphere, dim3(cdiv(kb->T.n_cols, L), nb), FFT_THREADS, smem_for(g->nx, L), kb->T,
+           g->px, (const cplx*)g->twx.p, (const cplx*)kb->W1.p, out, ldout, scale, kin, psi, ldpsi,
+           accumulate, L, Lp);
+  }
+}
+
+// hpsi (+)= FFT[V IFFT psi] (+ kin psi), batched over bands in chunks.
+void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_t n_bands,
+                            bool with_local, bool with_kin, bool accumulate) {
+  dftk_b200_grid* g = kb->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  if (n_bands == 0) return;
+  if (!with_local) {
+    scale_kin_add(ctx, psi, hpsi, with_kin ? kb->kin.p : nullptr, kb->n_pw, n_bands, accumulate);
+    return;
+  }
+  REQUIRE(kb->has_V, "apply_h: local potential not set (dftk_b200_kblock_set_potential)");
+  const int chunk = band_chunk_for(kb, n_bands);
+  for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
+    int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
+    const cplx* p = psi + b0 * kb->n_pw;
+    kb_sphere_to_planes(kb, p, kb->n_pw, nb);
+    int L = g->Lz, Lp = L | 1;
+    LAUNCH(ctx, k_z_apply_potential, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L),
+           kb->T, g->pz, (const cplx*)g->twz.p, kb->W2.p, (const double*)kb->V.p, L, Lp);
+    kb_planes_to_sphere(kb, hpsi + b0 * kb->n_pw, kb->n_pw, nb, 1.0, with_kin ? kb->kin.p : nullptr, p,
+                        kb->n_pw, accumulate ? 1 : 0);
+  }
+}
+
+void kb_sphere_to_real(dftk_b200_kblock* kb, const cplx* psi, cplx* cube, int64_t n_bands, double scale) {
+  dftk_b200_grid* g = kb->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  const int chunk = band_chunk_for(kb, n_bands);
+  for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
+    int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
+    kb_sphere_to_planes(kb, psi + b0 * kb->n_pw, kb->n_pw, nb);
+    int L = g->Lz, Lp = L | 1;
+    LAUNCH(ctx, k_z_to_cube, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L), kb->T,
+           g->pz, (const cplx*)g->twz.p, (const cplx*)kb->W2.p, cube + b0 * g->N, scale, L, Lp);
+  }
+}
+
+void kb_real_to_sphere(dftk_b200_kblock* kb, const cplx* cube, cplx* out, int64_t n_bands, double scale) {
+  dftk_b200_grid* g = kb->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  const int chunk = band_chunk_for(kb, n_bands);
+  for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
+    int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
+    ensure_scratch(kb, nb);
+    int L = g->Lz, Lp = L | 1;
+    LAUNCH(ctx, k_z_from_cube, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L), kb->T,
+           g->pz, (const cplx*)g->twz.p, cube + b0 * g->N, kb->W2.p, L, Lp);
+    kb_planes_to_sphere(kb, out + b0 * kb->n_pw, kb->n_pw, nb, scale, nullptr, nullptr, 0, 0);
+  }
+}
+
+// rho += sum_n occ_w[n] |IFFT psi_n|^2 * ifft_norm^2      (src/densities.jl:38-41)
+void kb_density_accumulate(dftk_b200_kblock* kb, const cplx* psi, const double* occ_w_host,
+                           int64_t n_bands, double* rho) {
+  dftk_b200_grid* g = kb->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  if (n_bands == 0) return;
+  std::vector<double> w(n_bands);
+  for (int64_t i = 0; i < n_bands; ++i) w[i] = occ_w_host[i] * g->ifft_norm * g->ifft_norm;
+  kb->wts.upload(w.data(), n_bands, ctx->stream);
+  const int chunk = band_chunk_for(kb, n_bands);
+  for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
+    int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
+    kb_sphere_to_planes(kb, psi + b0 * kb->n_pw, kb->n_pw, nb);
+    int L = g->Lz, Lp = L | 1;
+    size_t sm = smem_for(g->nz, L) + (size_t)g->nz * L * sizeof(double);
+    LAUNCH(ctx, k_z_density, dim3(cdiv(g->nx, L), g->ny), FFT_THREADS, sm, kb->T, g->pz,
+           (const cplx*)g->twz.p, (const cplx*)kb->W2.p, (const double*)(kb->wts.p + b0), nb, rho, L, Lp);
+  }
+  // the host weight vector must outlive the async upload
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace dftk

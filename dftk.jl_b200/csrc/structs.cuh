@@ -1,0 +1,69 @@
+// Grid / k-block handle definitions shared by the translation units of libdftk_b200.
+#pragma once
+#include "common.cuh"
+#include "fft_plan.h"
+
+struct dftk_b200_grid {
+  dftk_b200_ctx* ctx;
+  int nx, ny, nz;
+  int64_t N;
+  double omega;
+  double ifft_norm, fft_norm;  // src/fft.jl:87-88
+  dftk::FftPlan px, py, pz;
+  dftk::DevBuf<double> twx, twy, twz;
+  int Lx, Ly, Lz;
+};
+
+struct dftk_b200_kblock {
+  dftk_b200_grid* grid;
+  int64_t n_pw, n_proj;
+  int spin;
+  double kweight;
+  dftk::SphereTablesHost Th;
+  dftk::SphereTables T;  // device view
+  dftk::DevBuf<int> d_col_start, d_col_cnt, d_slot_ix, d_slot_src, d_zlist, d_colmap;
+  dftk::DevBuf<double> kin;       // n_pw (may be empty)
+  bool has_kin = false;
+  dftk::DevBuf<dftk::cplx> P;     // n_pw x n_proj
+  std::vector<double> D_host;     // n_proj x n_proj
+  dftk::DevBuf<dftk::cplx> Dc;    // complex copy of D on the device (n_proj x n_proj)
+  dftk::DevBuf<double> V;         // N, pre-scaled by 1/N (fft_norm*ifft_norm)
+  bool has_V = false;
+  // scratch
+  dftk::DevBuf<dftk::cplx> W1, W2;    // pruned intermediates for a chunk of bands
+  dftk::DevBuf<dftk::cplx> proj;      // n_proj x n_bands (+ D*proj)
+  dftk::DevBuf<dftk::cplx> lobpcg_ws; // big LOBPCG workspace
+  dftk::DevBuf<dftk::cplx> small_ws;  // small dense LOBPCG workspace
+  dftk::DevBuf<double> wts;
+};
+
+namespace dftk {
+// fft.cu
+int band_chunk_for(dftk_b200_kblock* kb, int64_t n_bands);
+void fft_cube_inplace(dftk_b200_grid* g, cplx* data, int sign, int64_t batch);
+void kb_sphere_to_planes(dftk_b200_kblock* kb, const cplx* psi, int64_t ldpsi, int nb);
+void kb_planes_to_sphere(dftk_b200_kblock* kb, cplx* out, int64_t ldout, int nb, double scale,
+                         const double* kin, const cplx* psi, int64_t ldpsi, int accumulate);
+void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_t n_bands,
+                            bool with_local, bool with_kin, bool accumulate);
+void kb_sphere_to_real(dftk_b200_kblock* kb, const cplx* psi, cplx* cube, int64_t n_bands, double scale);
+void kb_real_to_sphere(dftk_b200_kblock* kb, const cplx* cube, cplx* out, int64_t n_bands, double scale);
+void kb_density_accumulate(dftk_b200_kblock* kb, const cplx* psi, const double* occ_w_host,
+                           int64_t n_bands, double* rho);
+void fft_set_attributes();
+// blas.cu
+void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx alpha, const cplx* A,
+           int64_t lda, const cplx* B, int64_t ldb, cplx beta, cplx* C, int64_t ldc);
+void blas_set_attributes();
+void kb_apply_nonlocal(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_t n_bands);
+void columnwise_dots(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                     int64_t n_rows, int64_t n_cols, cplx* out_dev);
+void kin_dots(dftk_b200_ctx* ctx, const cplx* X, int64_t ldx, const double* kin, int64_t n_rows,
+              int64_t n_cols, double* out_dev);
+void scale_kin_add(dftk_b200_ctx* ctx, const cplx* psi, cplx* hpsi, const double* kin, int64_t n_rows,
+                   int64_t n_cols, int accumulate);
+// lobpcg.cu
+int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter, int maxiter,
+               int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host,
+               int* n_iter, int64_t* n_matvec, int* converged);
+}  // namespace dftk

@@ -1,0 +1,205 @@
+"""Thin object layer over the C ABI: Context / FFTGrid / KBlock handles holding torch CUDA tensors.
+
+PyTorch is used only for device memory management and (optionally) torch.distributed plumbing; every
+kernel on the hot path is launched by libdftk_b200.
+"""
+import ctypes
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, c_vp, c_i64, c_int
+
+
+def _ptr(t):
+    """Raw pointer of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.is_contiguous()
+        return ctypes.c_void_p(t.data_ptr())
+    if isinstance(t, np.ndarray):
+        assert t.flags["C_CONTIGUOUS"] or t.flags["F_CONTIGUOUS"]
+        return t.ctypes.data_as(ctypes.c_void_p)
+    raise TypeError(type(t))
+
+
+class Context:
+    """One per GPU / rank (dftk_b200_ctx)."""
+
+    def __init__(self, device=0, nccl_id=None, rank=0, nranks=1):
+        self.L = _lib.lib()
+        if not torch.cuda.is_available():
+            raise RuntimeError("dftk_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        torch.cuda.set_device(device)
+        torch.zeros(1, device=f"cuda:{device}")  # make sure the primary context exists
+        h = c_vp()
+        if nranks > 1:
+            buf = (ctypes.c_char * 128).from_buffer_copy(nccl_id)
+            check(self.L.dftk_b200_ctx_create_dist(device, buf, rank, nranks, ctypes.byref(h)))
+        else:
+            check(self.L.dftk_b200_ctx_create(device, ctypes.byref(h)))
+        self.h = h
+        self.device = torch.device(f"cuda:{device}")
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def nccl_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        check(_lib.lib().dftk_b200_nccl_unique_id(buf))
+        return buf.raw
+
+    def sync(self):
+        check(self.L.dftk_b200_sync(self.h), self.h)
+
+    def launch_count(self, reset=False):
+        return int(self.L.dftk_b200_launch_count(self.h, 1 if reset else 0))
+
+    def set_option(self, name, value):
+        check(self.L.dftk_b200_set_option(self.h, name.encode(), int(value)), self.h)
+
+    def mem_info(self):
+        f, t = c_i64(), c_i64()
+        check(self.L.dftk_b200_mem_info(self.h, ctypes.byref(f), ctypes.byref(t)), self.h)
+        return f.value, t.value
+
+    def allreduce(self, t, op="sum"):
+        dt = 0 if t.dtype == torch.float64 else 1
+        check(self.L.dftk_b200_allreduce(self.h, _ptr(t), t.numel(), dt, {"sum": 0, "min": 1, "max": 2}[op]), self.h)
+        return t
+
+    def allgather(self, send, recv):
+        dt = 0 if send.dtype == torch.float64 else 1
+        check(self.L.dftk_b200_allgather(self.h, _ptr(send), _ptr(recv), send.numel(), dt), self.h)
+        return recv
+
+    def zgemm(self, transA, A, B, C, alpha=1.0, beta=0.0):
+        """C = alpha op(A) B + beta C on column-major data: tensors are (cols, rows) C-contiguous."""
+        al = np.array([np.real(alpha), np.imag(alpha)], dtype=np.float64)
+        be = np.array([np.real(beta), np.imag(beta)], dtype=np.float64)
+        if transA == "C":
+            k, m = A.shape[1], A.shape[0]
+            n = B.shape[0]
+            check(self.L.dftk_b200_zgemm(self.h, 2, m, n, k, _ptr(al), _ptr(A), k, _ptr(B), k, _ptr(be), _ptr(C), m), self.h)
+        else:
+            m, k = A.shape[1], A.shape[0]
+            n = B.shape[0]
+            check(self.L.dftk_b200_zgemm(self.h, 0, m, n, k, _ptr(al), _ptr(A), m, _ptr(B), k, _ptr(be), _ptr(C), m), self.h)
+        return C
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.L.dftk_b200_ctx_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class FFTGrid:
+    """dftk_b200_grid (FFTGrid of src/fft.jl:57-98)."""
+
+    def __init__(self, ctx, fft_size, unit_cell_volume):
+        self.ctx = ctx
+        self.fft_size = tuple(int(n) for n in fft_size)
+        self.N = int(np.prod(self.fft_size))
+        h = c_vp()
+        check(ctx.L.dftk_b200_grid_create(ctx.h, *self.fft_size, float(unit_cell_volume), ctypes.byref(h)), ctx.h)
+        self.h = h
+
+    def fft_cube(self, data, direction):
+        """In-place unnormalised transform of (batch, N) complex data; -1 forward, +1 backward."""
+        batch = data.numel() // self.N
+        check(self.ctx.L.dftk_b200_fft_cube(self.h, _ptr(data), direction, batch), self.ctx.h)
+        return data
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.ctx.L.dftk_b200_grid_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class KBlock:
+    """dftk_b200_kblock: one (k-point, spin) Hamiltonian block resident on the device.
+
+    Orbitals are stored as torch tensors of shape (n_bands, n_pw) complex128 (= column-major n_pw×n_bands).
+    """
+
+    def __init__(self, grid, mapping, kin=None, P=None, D=None, spin=0, kweight=1.0):
+        self.grid, self.ctx = grid, grid.ctx
+        self.n_pw = int(len(mapping))
+        self.n_proj = 0 if P is None else int(P.shape[0])
+        self.spin, self.kweight = spin, kweight
+        mapping = np.ascontiguousarray(mapping, dtype=np.int64)
+        h = c_vp()
+        if D is not None:
+            D = np.asfortranarray(D, dtype=np.float64)
+        if kin is not None and isinstance(kin, np.ndarray):
+            kin = np.ascontiguousarray(kin, dtype=np.float64)
+        check(self.ctx.L.dftk_b200_kblock_create(grid.h, self.n_pw, _ptr(mapping), _ptr(kin), self.n_proj,
+                                                 _ptr(P), _ptr(D), spin, float(kweight), ctypes.byref(h)),
+              self.ctx.h)
+        self.h = h
+
+    def set_potential(self, V):
+        check(self.ctx.L.dftk_b200_kblock_set_potential(self.h, _ptr(V)), self.ctx.h)
+
+    def _new(self, nb):
+        return torch.empty((nb, self.n_pw), dtype=torch.complex128, device=self.ctx.device)
+
+    def apply_h(self, psi, out=None):
+        out = self._new(psi.shape[0]) if out is None else out
+        check(self.ctx.L.dftk_b200_apply_h(self.h, _ptr(psi), _ptr(out), psi.shape[0]), self.ctx.h)
+        return out
+
+    def apply_terms(self, psi, parts, out=None, accumulate=False):
+        out = self._new(psi.shape[0]) if out is None else out
+        check(self.ctx.L.dftk_b200_apply_terms(self.h, _ptr(psi), _ptr(out), psi.shape[0], parts,
+                                               1 if accumulate else 0), self.ctx.h)
+        return out
+
+    def sphere_to_real(self, psi, normalize=True):
+        nb = psi.shape[0]
+        out = torch.empty((nb, self.grid.N), dtype=torch.complex128, device=self.ctx.device)
+        check(self.ctx.L.dftk_b200_fft_sphere_to_real(self.h, _ptr(psi), _ptr(out), nb, int(normalize)), self.ctx.h)
+        return out
+
+    def real_to_sphere(self, f_real, normalize=True):
+        nb = f_real.shape[0]
+        out = self._new(nb)
+        check(self.ctx.L.dftk_b200_fft_real_to_sphere(self.h, _ptr(f_real), _ptr(out), nb, int(normalize)), self.ctx.h)
+        return out
+
+    def band_energies(self, psi):
+        nb = psi.shape[0]
+        ek, en = np.zeros(nb), np.zeros(nb)
+        check(self.ctx.L.dftk_b200_band_energies(self.h, _ptr(psi), nb, _ptr(ek), _ptr(en)), self.ctx.h)
+        return ek, en
+
+    def lobpcg(self, X, tol=1e-6, miniter=1, maxiter=100, n_conv_check=None, prec=True):
+        nb = X.shape[0]
+        lam, res = np.zeros(nb), np.zeros(nb)
+        nit, conv, nmv = c_int(), c_int(), c_i64()
+        check(self.ctx.L.dftk_b200_lobpcg(self.h, _ptr(X), nb, float(tol), miniter, maxiter,
+                                          nb if n_conv_check is None else int(n_conv_check), int(prec),
+                                          _ptr(lam), _ptr(res), ctypes.byref(nit), ctypes.byref(nmv),
+                                          ctypes.byref(conv)), self.ctx.h)
+        return dict(λ=lam, X=X, residual_norms=res, n_iter=nit.value, n_matvec=nmv.value,
+                    converged=bool(conv.value))
+
+    def density_accumulate(self, psi, occ_w, rho):
+        occ_w = np.ascontiguousarray(occ_w, dtype=np.float64)
+        check(self.ctx.L.dftk_b200_density_accumulate(self.h, _ptr(psi), _ptr(occ_w), psi.shape[0], _ptr(rho)),
+              self.ctx.h)
+        return rho
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.ctx.L.dftk_b200_kblock_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass

@@ -1,0 +1,129 @@
+/*
+ * libdftk_b200 -- C ABI of the B200-native plane-wave Kohn-Sham hot path.
+ *
+ * Drop-in boundary for the seam where DFTK.jl's ext/DFTKCUDAExt.jl + src/architecture.jl plug in
+ * today (reference paths relative to the DFTK.jl tree).  Each entry point names the reference
+ * function it replaces.  Conventions:
+ *   - all functions return 0 on success, a negative DFTK_B200_E* code on failure; the message of the
+ *     last failure on a context is available from dftk_b200_last_error(); nothing throws.
+ *   - column-major arrays, complex = interleaved double[2], indices 0-based (Julia glue subtracts 1
+ *     once when it passes `kpt.mapping`).
+ *   - "dev/host" pointers may be device or host memory (resolved through UVA); hot-path buffers
+ *     (psi, hpsi, X, rho) are expected on the device -- host buffers are staged through H2D/D2H copies
+ *     inside the call (this is what the end-to-end benchmark measures).
+ *   - handles are opaque and not thread-safe; one context per GPU / rank; the caller owns psi/rho/V
+ *     buffers, the library owns plans, scratch and its copies of mapping/kin/P/D.
+ */
+#ifndef DFTK_B200_H
+#define DFTK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dftk_b200_ctx dftk_b200_ctx;
+typedef struct dftk_b200_grid dftk_b200_grid;
+typedef struct dftk_b200_kblock dftk_b200_kblock;
+
+#define DFTK_B200_OK 0
+#define DFTK_B200_EINVAL (-1)   /* bad argument */
+#define DFTK_B200_ECUDA (-2)    /* CUDA runtime / library failure */
+#define DFTK_B200_ENUM (-3)     /* numerical failure (e.g. LOBPCG cannot keep vectors normalised) */
+#define DFTK_B200_ENCCL (-4)    /* NCCL failure / communicator missing */
+
+#define DFTK_B200_F64 0
+#define DFTK_B200_I64 1
+
+/* ---- context (replaces the `architecture=GPU(CuArray)` selection, src/architecture.jl:4-53;
+ *      synchronize_device / memory_usage, ext/DFTKCUDAExt.jl:11-15) ---- */
+int dftk_b200_ctx_create(int device, dftk_b200_ctx** out);
+/* distributed variant: `nccl_unique_id` = 128 bytes from dftk_b200_nccl_unique_id on rank 0 */
+int dftk_b200_ctx_create_dist(int device, const void* nccl_unique_id, int rank, int nranks,
+                              dftk_b200_ctx** out);
+int dftk_b200_nccl_unique_id(void* out128);
+int dftk_b200_ctx_destroy(dftk_b200_ctx* ctx);
+const char* dftk_b200_last_error(dftk_b200_ctx* ctx); /* ctx may be NULL: last global error */
+int dftk_b200_sync(dftk_b200_ctx* ctx);
+int dftk_b200_mem_info(dftk_b200_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
+/* number of kernel launches issued by this library on the context since creation / last reset */
+int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset);
+/* tuning knobs: "gemm_backend" (0 = own DMMA kernels, 1 = cuBLAS for A/B comparison),
+ * "band_chunk" (bands per batched-FFT launch) */
+int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value);
+
+/* ---- FFT grid (FFTGrid + build_fft_plans!, src/fft.jl:57-98,343-362) ---- */
+int dftk_b200_grid_create(dftk_b200_ctx* ctx, int nx, int ny, int nz, double unit_cell_volume,
+                          dftk_b200_grid** out);
+int dftk_b200_grid_destroy(dftk_b200_grid* grid);
+/* in-place unnormalised 3D C2C transform of `batch` cubes; direction -1 = forward (e^{-iGr}),
+ * +1 = backward (ipFFT / ipBFFT of src/fft.jl:107,119,159,166) */
+int dftk_b200_fft_cube(dftk_b200_grid* grid, void* data /*dev: complex[N*batch]*/, int direction,
+                       int64_t batch);
+
+/* ---- k-block = Kpoint + DftHamiltonianBlock data (src/Kpoint.jl:6-41,
+ *      src/terms/Hamiltonian.jl:22-57, kinetic.jl:24-35, nonlocal.jl:9-28) ----
+ * mapping: n_pw int64, 0-based linear cube index of each sphere coefficient (kpt.mapping - 1)
+ * kin:     n_pw doubles, ½|k+G|² (FourierMultiplication multiplier); may be NULL (no kinetic term)
+ * P:       n_pw × n_proj complex, column-major (NonlocalOperator.P); n_proj may be 0
+ * D:       n_proj × n_proj real, column-major (NonlocalOperator.D, block diagonal) */
+int dftk_b200_kblock_create(dftk_b200_grid* grid, int64_t n_pw, const int64_t* mapping,
+                            const double* kin, int64_t n_proj, const void* P, const double* D,
+                            int spin, double kweight, dftk_b200_kblock** out);
+int dftk_b200_kblock_destroy(dftk_b200_kblock* kb);
+/* total local potential on the real-space grid for this block's spin (sum of all
+ * RealSpaceMultiplication operators, src/terms/operators.jl:213-222); N_fft doubles.  NULL = none */
+int dftk_b200_kblock_set_potential(dftk_b200_kblock* kb, const double* V);
+
+/* ---- sphere <-> real-space transforms (ifft!/fft! with Gvec_mapping, src/fft.jl:110-122,162-172) */
+int dftk_b200_fft_sphere_to_real(dftk_b200_kblock* kb, const void* psi /*n_pw×n_bands*/,
+                                 void* out_real /*N_fft×n_bands complex*/, int64_t n_bands,
+                                 int normalize);
+int dftk_b200_fft_real_to_sphere(dftk_b200_kblock* kb, const void* in_real /*N_fft×n_bands*/,
+                                 void* out /*n_pw×n_bands*/, int64_t n_bands, int normalize);
+
+/* ---- Hψ (LinearAlgebra.mul!(Hψ, ::DftHamiltonianBlock, ψ), src/terms/Hamiltonian.jl:137-192) ----
+ * hpsi = FFT[V·IFFT[psi]] + kin·psi + P (D (P' psi)), all bands of the block in one batched pass. */
+int dftk_b200_apply_h(dftk_b200_kblock* kb, const void* psi, void* hpsi, int64_t n_bands);
+/* individual operators, `apply!(out, op, in)` semantics of src/terms/operators.jl (ACCUMULATE into hpsi
+ * when accumulate != 0): parts bitmask 1 = local (RealSpaceMultiplication :71-78),
+ * 2 = kinetic (FourierMultiplication :104-112), 4 = nonlocal (NonlocalOperator :119-129) */
+int dftk_b200_apply_terms(dftk_b200_kblock* kb, const void* psi, void* hpsi, int64_t n_bands,
+                          int parts, int accumulate);
+/* per-band <psi|kin|psi> and <psi|P D P'|psi> (ene_ops, kinetic.jl:40-57, nonlocal.jl:31-47); host out */
+int dftk_b200_band_energies(dftk_b200_kblock* kb, const void* psi, int64_t n_bands,
+                            double* ekin_host, double* enl_host);
+
+/* ---- LOBPCG (lobpcg_hyper, src/eigen/diag_lobpcg_hyper.jl:5-18 -> LOBPCG,
+ *      src/eigen/lobpcg_hyper_impl.jl:354-582, PreconditionerTPA src/eigen/preconditioners.jl:27-78) ----
+ * X: n_pw × n_bands, in: guess, out: eigenvectors (device).  lambda/resid: host, n_bands each. */
+int dftk_b200_lobpcg(dftk_b200_kblock* kb, void* X, int64_t n_bands, double tol, int miniter,
+                     int maxiter, int64_t n_conv_check, int use_tpa_preconditioner,
+                     double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec,
+                     int* converged);
+
+/* ---- density (compute_density inner loop, src/densities.jl:32-44):
+ *      rho[:,:,:] += sum_n occ_w[n] |IFFT psi_n|² / Ω   with occ_w[n] = occupation·kweight (host) ---- */
+int dftk_b200_density_accumulate(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host,
+                                 int64_t n_bands, double* rho /*dev: N_fft doubles of this spin*/);
+
+/* ---- collectives (mpi_sum!/mpi_min/mpi_max over basis.comm_kpts, src/common/mpi.jl:19-31) ---- */
+int dftk_b200_allreduce(dftk_b200_ctx* ctx, void* buf /*dev*/, int64_t count, int dtype,
+                        int op /*0 sum, 1 min, 2 max*/);
+int dftk_b200_allgather(dftk_b200_ctx* ctx, const void* send /*dev*/, void* recv /*dev*/,
+                        int64_t count_per_rank, int dtype);
+
+/* ---- small dense helpers used by the host driver (columnwise_dots, src/common/linalg.jl:2-15) ---- */
+int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,
+                              int64_t n_cols, void* out_host /*complex[n_cols]*/);
+/* C = alpha * op(A) * B + beta * C on complex128 column-major device arrays (own DMMA kernels);
+ * transA: 0 = N, 2 = C (conjugate transpose) */
+int dftk_b200_zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k,
+                    const double* alpha2, const void* A, int64_t lda, const void* B, int64_t ldb,
+                    const double* beta2, void* C, int64_t ldc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,105 @@
+// Host emulation of the FFT pipeline kernel bodies (TEST INFRASTRUCTURE ONLY, never loaded by the
+// product).  Runs the same __host__ __device__ stage bodies as the CUDA kernels, block by block and
+// "thread" by "thread", so the index logic can be validated against NumPy without a GPU.
+#include <vector>
+#include <cstring>
+#include "../../dftk.jl_b200/csrc/fft_plan.h"
+using namespace dftk;
+
+static SphereTables view(const SphereTablesHost& H) {
+  SphereTables T;
+  T.nx = H.nx; T.ny = H.ny; T.nz = H.nz; T.n_pw = H.n_pw; T.n_cols = H.n_cols; T.cnt_max = H.cnt_max;
+  T.n_zc = H.n_zc; T.col_start = H.col_start.data(); T.col_cnt = H.col_cnt.data();
+  T.slot_ix = H.slot_ix.data(); T.slot_src = H.slot_src.data(); T.zlist = H.zlist.data();
+  T.colmap = H.colmap.data();
+  return T;
+}
+struct Emu {
+  SphereTablesHost H; SphereTables T; FftPlan px, py, pz; std::vector<double> twx, twy, twz;
+  int Lx, Ly, Lz; std::vector<cplx> W1, W2, sm;
+  Emu(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, int nb) {
+    H = build_sphere_tables(nx, ny, nz, n_pw, mapping); T = view(H);
+    px = make_plan(nx); py = make_plan(ny); pz = make_plan(nz);
+    twx = make_twiddles(nx); twy = make_twiddles(ny); twz = make_twiddles(nz);
+    Lx = choose_lines(nx); Ly = choose_lines(ny); Lz = choose_lines(nz);
+    W1.resize((size_t)nb * H.n_cols * nx); W2.resize((size_t)nb * H.n_zc * ny * nx);
+    size_t m = std::max(std::max(nx, ny), nz);
+    sm.resize(3 * m * 17 + 64);
+  }
+  const cplx* tx() { return (const cplx*)twx.data(); }
+  const cplx* ty() { return (const cplx*)twy.data(); }
+  const cplx* tz() { return (const cplx*)twz.data(); }
+  void to_planes(const cplx* psi, int nb) {
+    int L = Lx, Lp = L | 1;
+    for (int b = 0; b < nb; ++b) for (int bx = 0; bx < (T.n_cols + L - 1) / L; ++bx)
+      stage_sphere_to_x(T, px, tx(), psi, T.n_pw, W1.data(), L, Lp, sm.data(), Dim3i{bx, b, 0});
+    L = Ly; Lp = L | 1;
+    for (int b = 0; b < nb; ++b) for (int z = 0; z < T.n_zc; ++z) for (int bx = 0; bx < (T.nx + L - 1) / L; ++bx)
+      stage_y_backward(T, py, ty(), W1.data(), W2.data(), L, Lp, sm.data(), Dim3i{bx, z, b});
+  }
+  void from_planes(cplx* out, int nb, double scale, const double* kin, const cplx* psi, int acc) {
+    int L = Ly, Lp = L | 1;
+    for (int b = 0; b < nb; ++b) for (int z = 0; z < T.n_zc; ++z) for (int bx = 0; bx < (T.nx + L - 1) / L; ++bx)
+      stage_y_forward(T, py, ty(), W2.data(), W1.data(), L, Lp, sm.data(), Dim3i{bx, z, b});
+    L = Lx; Lp = L | 1;
+    for (int b = 0; b < nb; ++b) for (int bx = 0; bx < (T.n_cols + L - 1) / L; ++bx)
+      stage_x_to_sphere(T, px, tx(), W1.data(), out, T.n_pw, scale, kin, psi, T.n_pw, acc, L, Lp, sm.data(), Dim3i{bx, b, 0});
+  }
+};
+
+extern "C" {
+int emu_apply_local(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* psi,
+                    int nb, const double* Vscaled, const double* kin, double* out) {
+  Emu e(nx, ny, nz, n_pw, mapping, nb);
+  e.to_planes((const cplx*)psi, nb);
+  int L = e.Lz, Lp = L | 1;
+  for (int b = 0; b < nb; ++b) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx)
+    stage_z_apply_potential(e.T, e.pz, e.tz(), e.W2.data(), Vscaled, L, Lp, e.sm.data(), Dim3i{bx, y, b});
+  e.from_planes((cplx*)out, nb, 1.0, kin, (const cplx*)psi, 0);
+  return 0;
+}
+int emu_sphere_to_real(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* psi,
+                       int nb, double scale, double* cube) {
+  Emu e(nx, ny, nz, n_pw, mapping, nb);
+  e.to_planes((const cplx*)psi, nb);
+  int L = e.Lz, Lp = L | 1;
+  for (int b = 0; b < nb; ++b) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx)
+    stage_z_to_cube(e.T, e.pz, e.tz(), e.W2.data(), (cplx*)cube, scale, L, Lp, e.sm.data(), Dim3i{bx, y, b});
+  return 0;
+}
+int emu_real_to_sphere(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* cube,
+                       int nb, double scale, double* out) {
+  Emu e(nx, ny, nz, n_pw, mapping, nb);
+  int L = e.Lz, Lp = L | 1;
+  for (int b = 0; b < nb; ++b) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx)
+    stage_z_from_cube(e.T, e.pz, e.tz(), (const cplx*)cube, e.W2.data(), L, Lp, e.sm.data(), Dim3i{bx, y, b});
+  e.from_planes((cplx*)out, nb, scale, nullptr, nullptr, 0);
+  return 0;
+}
+int emu_density(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* psi,
+                int nb, const double* wts, double* rho) {
+  Emu e(nx, ny, nz, n_pw, mapping, nb);
+  e.to_planes((const cplx*)psi, nb);
+  int L = e.Lz, Lp = L | 1;
+  for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx)
+    stage_z_density(e.T, e.pz, e.tz(), e.W2.data(), wts, nb, rho, L, Lp, e.sm.data(), Dim3i{bx, y, 0});
+  return 0;
+}
+int emu_fft_cube(int nx, int ny, int nz, double* data, int sign, int batch) {
+  FftPlan px = make_plan(nx), py = make_plan(ny), pz = make_plan(nz);
+  auto twx = make_twiddles(nx), twy = make_twiddles(ny), twz = make_twiddles(nz);
+  size_t m = std::max(std::max(nx, ny), nz);
+  std::vector<cplx> sm(2 * m * 17 + 64);
+  int L = choose_lines(nx), Lp = L | 1;
+  int64_t nl = (int64_t)ny * nz;
+  for (int b = 0; b < batch; ++b) for (int bx = 0; bx < (nl + L - 1) / L; ++bx)
+    cube_pass_x((cplx*)data, nx, nl, px, (const cplx*)twx.data(), sign, L, Lp, sm.data(), Dim3i{bx, b, 0});
+  L = choose_lines(ny); Lp = L | 1;
+  for (int b = 0; b < batch; ++b) for (int z = 0; z < nz; ++z) for (int bx = 0; bx < (nx + L - 1) / L; ++bx)
+    cube_pass_strided((cplx*)data, nx, ny, nx, (int64_t)nx * ny, (int64_t)nx * ny * nz, py, (const cplx*)twy.data(), sign, L, Lp, sm.data(), Dim3i{bx, z, b});
+  L = choose_lines(nz); Lp = L | 1;
+  for (int b = 0; b < batch; ++b) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx)
+    cube_pass_strided((cplx*)data, nx, nz, (int64_t)nx * ny, nx, (int64_t)nx * ny * nz, pz, (const cplx*)twz.data(), sign, L, Lp, sm.data(), Dim3i{bx, y, b});
+  return 0;
+}
+}

@@ -1,0 +1,149 @@
+"""GPU parity tests of every kernel family against the CPU oracle (run on the B200 box: -m gpu).
+All calls go through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def si():
+    from gpu_common import silicon_setup, device_blocks
+    m, b, t, rho, ham = silicon_setup()
+    grid, blocks = device_blocks(b, ham)
+    return dict(m=m, b=b, t=t, rho=rho, ham=ham, grid=grid, kb=blocks[0], blk=ham[0])
+
+
+@pytest.mark.parametrize("fft_size", [(8, 9, 10), (27, 27, 27), (40, 40, 40), (33, 20, 17), (48, 45, 32)])
+def test_fft_cube(fft_size):
+    import dftk_b200
+    from gpu_common import ctx, to_dev
+    nx, ny, nz = fft_size
+    grid = dftk_b200.FFTGrid(ctx(), fft_size, 10.0)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, nz, ny, nx)) + 1j * rng.standard_normal((2, nz, ny, nx))
+    for sign in (-1, 1):
+        d = to_dev(x.reshape(2, -1))
+        grid.fft_cube(d, sign)
+        ref = np.fft.fftn(x, axes=(1, 2, 3)) if sign < 0 else np.fft.ifftn(x, axes=(1, 2, 3)) * (nx * ny * nz)
+        np.testing.assert_allclose(d.cpu().numpy().reshape(x.shape), ref, atol=1e-12 * np.abs(ref).max())
+
+
+def test_sphere_transforms(si):
+    from gpu_common import to_dev, rand_psi
+    b, kb, kpt = si["b"], si["kb"], si["blk"].kpt
+    psi = rand_psi(kpt.n_G, 5)
+    out = kb.sphere_to_real(to_dev(psi), normalize=True).cpu().numpy()
+    ref = np.stack([b.ifft_kpt(kpt, p) for p in psi])
+    np.testing.assert_allclose(out, ref, atol=1e-12 * np.abs(ref).max())
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal((3, b.N)) + 1j * rng.standard_normal((3, b.N))
+    back = kb.real_to_sphere(to_dev(f), normalize=True).cpu().numpy()
+    refb = np.stack([b.fft_kpt(kpt, x) for x in f])
+    np.testing.assert_allclose(back, refb, atol=1e-12 * np.abs(refb).max())
+    # round trip (test/fourier_transforms.jl:1-47)
+    rt = kb.real_to_sphere(kb.sphere_to_real(to_dev(psi))).cpu().numpy()
+    np.testing.assert_allclose(rt, psi, atol=1e-12)
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+def test_apply_h_terms(si, backend):
+    from gpu_common import to_dev, rand_psi, ctx
+    ctx().set_option("gemm_backend", backend)
+    try:
+        blk, kb = si["blk"], si["kb"]
+        psi = rand_psi(blk.kpt.n_G, 7, seed=1)
+        d = to_dev(psi)
+        P, D = blk.PD
+        ref_loc = blk.local_apply(psi.T).T
+        ref_kin = blk.kin[None, :] * psi
+        ref_nl = (P @ (D @ (P.conj().T @ psi.T))).T
+        scale = np.abs(ref_loc + ref_kin + ref_nl).max()
+        np.testing.assert_allclose(kb.apply_terms(d, 1).cpu().numpy(), ref_loc, atol=1e-12 * scale)
+        np.testing.assert_allclose(kb.apply_terms(d, 2).cpu().numpy(), ref_kin, atol=1e-12 * scale)
+        np.testing.assert_allclose(kb.apply_terms(d, 4).cpu().numpy(), ref_nl, atol=1e-12 * scale)
+        np.testing.assert_allclose(kb.apply_h(d).cpu().numpy(), blk.matmul(psi.T).T, atol=1e-12 * scale)
+        # accumulate semantics of apply! (src/terms/operators.jl:6-8)
+        acc = to_dev(psi.copy())
+        kb.apply_terms(d, 7, out=acc, accumulate=True)
+        np.testing.assert_allclose(acc.cpu().numpy(), psi + blk.matmul(psi.T).T, atol=1e-12 * scale)
+        # host buffers through the same C ABI call (end-to-end path)
+        hout = np.zeros_like(psi)
+        from dftk_b200._lib import check
+        from dftk_b200.device import _ptr
+        check(kb.ctx.L.dftk_b200_apply_h(kb.h, _ptr(psi), _ptr(hout), psi.shape[0]), kb.ctx.h)
+        np.testing.assert_allclose(hout, blk.matmul(psi.T).T, atol=1e-12 * scale)
+    finally:
+        ctx().set_option("gemm_backend", 0)
+
+
+@pytest.mark.parametrize("shape", [(1000, 7, 5), (4099, 70, 33), (129, 64, 32), (20000, 130, 1), (515, 3, 97)])
+def test_zgemm_own_kernels(shape):
+    from gpu_common import ctx
+    K, m, n = shape
+    c = ctx()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    A = torch.randn(m, K, 2, generator=g, dtype=torch.float64)
+    B = torch.randn(n, K, 2, generator=g, dtype=torch.float64)
+    A = torch.view_as_complex(A).to(c.device)
+    B = torch.view_as_complex(B).to(c.device)
+    C0 = torch.view_as_complex(torch.randn(n, m, 2, generator=g, dtype=torch.float64)).to(c.device)
+    alpha, beta = 0.7 - 0.2j, -0.3 + 1.1j
+    # Gram: C(m x n) = A^H B ; tensors are stored (cols, rows)
+    C = C0.clone()
+    c.zgemm("C", A, B, C, alpha, beta)
+    ref = alpha * (B @ A.conj().T) + beta * C0      # (n, m) = column-major m x n
+    assert (C - ref).abs().max().item() < 1e-11 * ref.abs().max().item()
+    # update: X(K x n) = A(K x m) * S(m x n)
+    S = torch.view_as_complex(torch.randn(n, m, 2, generator=g, dtype=torch.float64)).to(c.device)
+    X0 = torch.view_as_complex(torch.randn(n, K, 2, generator=g, dtype=torch.float64)).to(c.device)
+    X = X0.clone()
+    c.zgemm("N", A, S, X, alpha, beta)
+    refx = alpha * (S @ A) + beta * X0
+    assert (X - refx).abs().max().item() < 1e-11 * refx.abs().max().item()
+
+
+def test_band_energies_and_density(si):
+    from gpu_common import to_dev, rand_psi, ctx
+    b, blk, kb = si["b"], si["blk"], si["kb"]
+    psi = rand_psi(blk.kpt.n_G, 6, seed=4)
+    ek, en = kb.band_energies(to_dev(psi))
+    P, D = blk.PD
+    Pp = P.conj().T @ psi.T
+    np.testing.assert_allclose(ek, np.real(np.sum(np.conj(psi) * blk.kin[None, :] * psi, axis=1)), rtol=1e-12)
+    np.testing.assert_allclose(en, np.sum(np.real(np.conj(Pp) * (D @ Pp)), axis=0), rtol=1e-11)
+    w = np.array([2.0, 2.0, 1.5, 0.3, 0.0, 1.0])
+    rho = torch.zeros(b.N, dtype=torch.float64, device=ctx().device)
+    kb.density_accumulate(to_dev(psi), w, rho)
+    ref = sum(w[i] * b.ifft_normalization ** 2 * np.abs(b.ifft_kpt(blk.kpt, psi[i], False)) ** 2 for i in range(6))
+    np.testing.assert_allclose(rho.cpu().numpy(), ref, atol=1e-12 * ref.max())
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+def test_lobpcg_matches_oracle(si, backend):
+    from gpu_common import to_dev, ctx
+    from oracle import lobpcg as olob
+    ctx().set_option("gemm_backend", backend)
+    try:
+        blk, kb = si["blk"], si["kb"]
+        rng = np.random.default_rng(5)
+        X0 = rng.standard_normal((blk.kpt.n_G, 8)) + 1j * rng.standard_normal((blk.kpt.n_G, 8))
+        ref = olob.lobpcg(blk, X0.copy(), olob.PreconditionerTPA(blk.kin), tol=1e-9, maxiter=200)
+        X = to_dev(X0.T)
+        res = kb.lobpcg(X, tol=1e-9, maxiter=200)
+        assert res["converged"] and ref["converged"]
+        np.testing.assert_allclose(res["λ"], ref["λ"], atol=1e-8)
+        assert abs(res["n_iter"] - ref["n_iter"]) <= max(3, ref["n_iter"] // 5)
+        # residual check with the device operator itself
+        HX = kb.apply_h(X)
+        r = HX - torch.from_numpy(res["λ"]).to(X.device)[:, None] * X
+        assert r.norm(dim=1).max().item() < 1e-8
+        G = X.conj() @ X.T
+        assert (G - torch.eye(8, dtype=G.dtype, device=G.device)).abs().max().item() < 1e-12
+        # partial convergence / locking path: only 4 of 7 bands must converge (AdaptiveBands usage)
+        X = to_dev(X0.T[:7])
+        res2 = kb.lobpcg(X, tol=1e-7, maxiter=100, n_conv_check=4)
+        np.testing.assert_allclose(res2["λ"][:4], ref["λ"][:4], atol=1e-6)
+    finally:
+        ctx().set_option("gemm_backend", 0)

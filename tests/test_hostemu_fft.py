@@ -1,0 +1,93 @@
+"""Index-logic test of the FFT pipeline kernel bodies, executed on the host (tests/hostemu/emu.cu
+compiles the same __host__ __device__ stage functions the CUDA kernels run).  Checker: the oracle."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+import pytest
+
+from oracle.basis import Element, Model, PlaneWaveBasis
+from silicon import LATTICE, POSITIONS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "hostemu", "libhostemu.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(HERE, "hostemu", "emu.cu")
+    csrc = os.path.join(HERE, "..", "dftk.jl_b200", "csrc")
+    deps = [src, os.path.join(csrc, "fft_core.cuh"), os.path.join(csrc, "fft_plan.h")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                               "-Wno-deprecated-gpu-targets", "-o", SO, src])
+    return ctypes.CDLL(SO)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _basis(fft_size, Ecut, k):
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, symmetries=False)
+    return PlaneWaveBasis(m, Ecut, fft_size=fft_size, kcoords=[k], kweights=[1.0])
+
+
+@pytest.mark.parametrize("fft_size,Ecut", [((15, 15, 15), 5), ((12, 15, 18), 4), ((17, 20, 21), 6),
+                                           ((27, 27, 27), 15), ((24, 24, 24), 9)])
+def test_emulated_pipeline(emu, fft_size, Ecut):
+    b = _basis(fft_size, Ecut, [0.1, -0.2, 0.3])
+    kpt = b.kpoints[0]
+    nx, ny, nz = fft_size
+    rng = np.random.default_rng(1)
+    nb = 3
+    npw = ctypes.c_int64(kpt.n_G)
+    psi = rng.standard_normal((nb, kpt.n_G)) + 1j * rng.standard_normal((nb, kpt.n_G))
+    V = rng.standard_normal(b.N)
+    kin = rng.random(kpt.n_G)
+    mapping = np.ascontiguousarray(kpt.mapping, dtype=np.int64)
+    Vs = np.ascontiguousarray(V / b.N)
+    # H psi local + kinetic
+    out = np.zeros_like(psi)
+    emu.emu_apply_local(nx, ny, nz, npw, _p(mapping), _p(psi), nb, _p(Vs), _p(kin), _p(out))
+    ref = np.stack([b.fft_kpt(kpt, b.ifft_kpt(kpt, psi[i], False) * V / b.N, False) + kin * psi[i]
+                    for i in range(nb)])
+    np.testing.assert_allclose(out, ref, atol=1e-11 * np.abs(ref).max())
+    # sphere -> real
+    cube = np.zeros((nb, b.N), dtype=complex)
+    emu.emu_sphere_to_real(nx, ny, nz, npw, _p(mapping), _p(psi), nb,
+                           ctypes.c_double(b.ifft_normalization), _p(cube))
+    refc = np.stack([b.ifft_kpt(kpt, psi[i]) for i in range(nb)])
+    np.testing.assert_allclose(cube, refc, atol=1e-12 * np.abs(refc).max())
+    # real -> sphere
+    f = rng.standard_normal((nb, b.N)) + 1j * rng.standard_normal((nb, b.N))
+    back = np.zeros_like(psi)
+    emu.emu_real_to_sphere(nx, ny, nz, npw, _p(mapping), _p(f), nb,
+                           ctypes.c_double(b.fft_normalization), _p(back))
+    refb = np.stack([b.fft_kpt(kpt, f[i]) for i in range(nb)])
+    np.testing.assert_allclose(back, refb, atol=1e-12 * np.abs(refb).max())
+    # density
+    w = rng.random(nb)
+    rho = np.zeros(b.N)
+    emu.emu_density(nx, ny, nz, npw, _p(mapping), _p(psi), nb, _p(w), _p(rho))
+    refr = sum(w[i] * np.abs(b.ifft_kpt(kpt, psi[i], False)) ** 2 for i in range(nb))
+    np.testing.assert_allclose(rho, refr, atol=1e-11 * refr.max())
+    # unsorted mapping (construct_from_equivalent_kpt, src/Kpoint.jl:44-56)
+    perm = rng.permutation(kpt.n_G)
+    out2 = np.zeros_like(psi)
+    emu.emu_apply_local(nx, ny, nz, npw, _p(np.ascontiguousarray(mapping[perm])),
+                        _p(np.ascontiguousarray(psi[:, perm])), nb, _p(Vs),
+                        _p(np.ascontiguousarray(kin[perm])), _p(out2))
+    np.testing.assert_allclose(out2, ref[:, perm], atol=1e-11 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("fft_size", [(8, 9, 10), (15, 15, 15), (33, 5, 7), (40, 3, 16), (1, 4, 25)])
+def test_emulated_cube_fft(emu, fft_size):
+    nx, ny, nz = fft_size
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((2, nz, ny, nx)) + 1j * rng.standard_normal((2, nz, ny, nx))
+    for sign in (-1, 1):
+        d = x.copy()
+        emu.emu_fft_cube(nx, ny, nz, _p(d), sign, 2)
+        ref = np.fft.fftn(x, axes=(1, 2, 3)) if sign < 0 else np.fft.ifftn(x, axes=(1, 2, 3)) * (nx * ny * nz)
+        np.testing.assert_allclose(d, ref, atol=1e-12 * np.abs(ref).max())
