@@ -1,0 +1,246 @@
+"""self_consistent_field and friends (host-side mirror of src/scf/self_consistent_field.jl:80-289,
+scf_solvers.jl:76-102, anderson.jl, mixing.jl:38-103, nbands_algorithm.jl, scf_callbacks.jl:191-230).
+
+Host orchestration only: the density, potentials, orbitals and Anderson history stay on the device;
+every orbital-sized operation is a libdftk_b200 call."""
+import math
+import time
+import numpy as np
+import torch
+
+from .hamiltonian import energy_hamiltonian, energy
+from .eigen import lobpcg_hyper, diagonalize_all_kblocks
+from .occupation import compute_occupation
+from .densities import compute_density
+from .terms import guess_density
+
+
+class AdaptiveBands:
+    """nbands_algorithm.jl:57-109."""
+
+    def __init__(self, model, *, n_bands_converge=None, occupation_threshold=1e-6, gap_min=1e-2,
+                 temperature_factor_converge=1.05, temperature_factor_compute=1.20):
+        def default_n_bands(factor):
+            mn = -(-model.n_electrons // (model.n_spin_components * model.filled_occupation))
+            return int(math.ceil(mn * (1.0 if model.temperature == 0 else factor)))
+        self.n_bands_converge = default_n_bands(temperature_factor_converge) if n_bands_converge is None else n_bands_converge
+        self.n_bands_compute = max(3 + self.n_bands_converge, default_n_bands(temperature_factor_compute))
+        self.occupation_threshold, self.gap_min = occupation_threshold, gap_min
+
+    def determine_n_bands(self, occupation, eigenvalues, psi):
+        if occupation is None:
+            ncomp = self.n_bands_compute if psi is None else max(self.n_bands_compute, max(p.shape[0] for p in psi))
+            return (self.n_bands_converge + self.n_bands_compute) // 2, ncomp
+
+        def findlast(pred, arr):
+            idx = [i for i, a in enumerate(arr) if pred(a)]
+            return idx[-1] + 1 if idx else len(arr) + 1
+        n_occ = max(findlast(lambda f: abs(f) >= self.occupation_threshold, o) for o in occupation)
+        nconv = max(self.n_bands_converge, n_occ)
+        ncomp_e = 0
+        if eigenvalues is not None:
+            ncomp_e = max(len(ek) + 1 if nconv > len(ek) else
+                          findlast(lambda e, ek=ek: e <= ek[nconv - 1] + self.gap_min, ek) for ek in eigenvalues)
+        ncomp = max(self.n_bands_compute, ncomp_e, nconv + 3)
+        if psi is not None:
+            ncomp = max(ncomp, max(p.shape[0] for p in psi))
+        return nconv, ncomp
+
+
+class FixedBands:
+    def __init__(self, n_bands_converge, n_bands_compute=None, occupation_threshold=1e-6):
+        self.n_bands_converge = n_bands_converge
+        self.n_bands_compute = n_bands_compute if n_bands_compute is not None else n_bands_converge + 3
+        self.occupation_threshold = occupation_threshold
+
+    def determine_n_bands(self, occupation, eigenvalues, psi):
+        return self.n_bands_converge, self.n_bands_compute
+
+
+class AdaptiveDiagtol:
+    """scf_callbacks.jl:191-212."""
+
+    def __init__(self, ratio_rhodiff=0.2, diagtol_min=None, diagtol_max=0.005, diagtol_first=None):
+        self.ratio, self.dmin, self.dmax = ratio_rhodiff, diagtol_min, diagtol_max
+        self.dfirst = 6 * diagtol_max if diagtol_first is None else diagtol_first
+
+    def determine_diagtol(self, info):
+        if info["n_iter"] <= 1:
+            return min(self.dfirst, 5 * self.dmax)
+        d = min(info["history_drho"]) * self.ratio
+        dmin = 100 * np.finfo(float).eps if self.dmin is None else self.dmin
+        return min(max(d, dmin), self.dmax)
+
+
+class ScfConvergenceDensity:
+    def __init__(self, tol):
+        self.tol = tol
+
+    def __call__(self, info):
+        return info["history_drho"][-1] < self.tol
+
+
+class ScfConvergenceEnergy:
+    def __init__(self, tol):
+        self.tol = tol
+
+    def __call__(self, info):
+        h = info["history_Etot"]
+        return len(h) > 1 and abs(h[-1] - h[-2]) < self.tol
+
+
+class SimpleMixing:
+    def mix_density(self, basis, dF, **kw):
+        return dF
+
+
+class KerkerMixing:
+    """mixing.jl:61-103 (ΔDOS_Ω = 0)."""
+
+    def __init__(self, kTF=0.8):
+        self.kTF = kTF
+
+    def mix_density(self, basis, dF, **kw):
+        G2 = (basis.G_vectors_cart ** 2).sum(dim=1)
+        tot = dF.sum(dim=0)
+        tf = basis.fft(tot).reshape(-1) * G2 / (self.kTF ** 2 + G2)
+        dtot = basis.irfft(basis.enforce_real(tf)).reshape(-1)
+        dtot = dtot + (tot.mean() - dtot.mean())
+        if dF.shape[0] == 1:
+            return dtot[None, :]
+        spin = dF[0] - dF[1]
+        return torch.stack([(dtot + spin) / 2, (dtot - spin) / 2])
+
+
+class AndersonAcceleration:
+    """anderson.jl:42-130, history kept on the device."""
+
+    def __init__(self, m=10, maxcond=1e6, errorfactor=1e5):
+        self.m, self.maxcond, self.errorfactor = m, maxcond, errorfactor
+        self.xs, self.rs, self.errs = [], [], []
+
+    def _push(self, x, r):
+        self.xs.append(x.clone()); self.rs.append(r.clone()); self.errs.append(float(r.norm()))
+        if len(self.xs) > self.m:
+            self.xs.pop(0); self.rs.pop(0); self.errs.pop(0)
+
+    def __call__(self, x, alpha, Pf):
+        shape = x.shape
+        x, Pf = x.reshape(-1), Pf.reshape(-1)
+        if self.m == 0 or self.errorfactor <= 1 or self.maxcond <= 1:
+            return (x + alpha * Pf).reshape(shape)
+        if not self.xs:
+            self._push(x, Pf)
+            return (x + alpha * Pf).reshape(shape)
+        min_err = min(min(self.errs), float(Pf.norm()))
+        keep = [i for i in range(len(self.errs)) if i == len(self.errs) - 1 or not self.errs[i] > self.errorfactor * min_err]
+        self.xs, self.rs, self.errs = ([l[i] for i in keep] for l in (self.xs, self.rs, self.errs))
+        M = torch.stack(self.rs, dim=1) - Pf[:, None]
+        while True:
+            Q, R = torch.linalg.qr(M)
+            if M.shape[1] > 1 and float(torch.linalg.cond(R)) > self.maxcond:
+                idrop = int(np.argmax(self.errs[:-1]))
+                for l in (self.xs, self.rs, self.errs):
+                    l.pop(idrop)
+                M = M[:, [c for c in range(M.shape[1]) if c != idrop]]
+                continue
+            break
+        betas = -torch.linalg.solve_triangular(R, (Q.T @ Pf)[:, None], upper=True).reshape(-1)
+        xn = x + alpha * Pf
+        for ib, b in enumerate(betas.cpu().tolist()):
+            xn = xn + b * (self.xs[ib] - x + alpha * (self.rs[ib] - Pf))
+        self._push(x, Pf)
+        return xn.reshape(shape)
+
+
+def next_density(ham, nbandsalg, *, eigensolver=lobpcg_hyper, psi=None, eigenvalues=None, occupation=None,
+                 tol=1e-6, miniter=1, maxiter=100, generator=None):
+    """self_consistent_field.jl:80-129."""
+    basis = ham.basis
+    nconv, ncomp = nbandsalg.determine_n_bands(occupation, eigenvalues, psi)
+    if psi is not None:
+        ncomp = max(ncomp, max(p.shape[0] for p in psi))
+    ncomp = int(basis.comm_kpts.max(ncomp))
+    eig = diagonalize_all_kblocks(eigensolver, ham, ncomp, psiguess=psi, n_conv_check=nconv, tol=tol,
+                                  miniter=miniter, maxiter=maxiter, generator=generator)
+    if not eig["converged"]:
+        import warnings
+        warnings.warn(f"Eigensolver not converged, n_iter={eig['n_iter']}")
+    occ, eF = compute_occupation(basis, eig["λ"], tol_n_elec=nbandsalg.occupation_threshold)
+    rho = compute_density(basis, eig["X"], occ, occupation_threshold=nbandsalg.occupation_threshold)
+    return dict(psi=eig["X"], eigenvalues=eig["λ"], occupation=occ, eF=eF, rho=rho, diagonalization=eig,
+                n_bands_converge=nconv, n_matvec=int(basis.comm_kpts.sum(eig["n_matvec"])))
+
+
+def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=None, maxiter=100,
+                          mixing=None, damping=0.8, eigensolver=lobpcg_hyper, diagtolalg=None, nbandsalg=None,
+                          callback=None, compute_consistent_energies=True, seed=None, anderson_m=10):
+    model = basis.model
+    start = time.time()
+    rho = guess_density(basis) if rho is None else rho
+    mixing = mixing or SimpleMixing()      # reference default LdosMixing degenerates to SimpleMixing at T = 0
+    nbandsalg = nbandsalg or AdaptiveBands(model)
+    diagtolalg = diagtolalg or AdaptiveDiagtol()
+    is_converged = is_converged or ScfConvergenceDensity(tol)
+    gen = torch.Generator(device=basis.architecture.device)
+    gen.manual_seed(int(basis.comm_kpts.bcast_object(seed if seed is not None else 0)) + 7919 * basis.comm_kpts.rank)
+    info = dict(basis=basis, rho=rho, psi=psi, occupation=None, eigenvalues=None, eF=None, n_iter=0, n_matvec=0,
+                converged=False, history_Etot=[], history_drho=[], stage="iterate", algorithm="SCF")
+    acc = AndersonAcceleration(m=anderson_m)
+
+    def fixpoint_map(rho_in):
+        info["n_iter"] += 1
+        t0 = time.time()
+        _, ham = energy_hamiltonian(basis, info["psi"], info["occupation"], rho=rho_in,
+                                    eigenvalues=info["eigenvalues"], eF=info["eF"])
+        nxt = next_density(ham, nbandsalg, eigensolver=eigensolver, psi=info["psi"], eigenvalues=info["eigenvalues"],
+                           occupation=info["occupation"], miniter=1, tol=diagtolalg.determine_diagtol(info),
+                           generator=gen)
+        info.update(ham=ham, rho_in=rho_in, psi=nxt["psi"], eigenvalues=nxt["eigenvalues"], occupation=nxt["occupation"],
+                    eF=nxt["eF"], rho_out=nxt["rho"], diagonalization=nxt["diagonalization"],
+                    n_bands_converge=nxt["n_bands_converge"], n_matvec=info["n_matvec"] + nxt["n_matvec"])
+        if compute_consistent_energies:
+            energies = energy(basis, nxt["psi"], nxt["occupation"], rho=nxt["rho"], eigenvalues=nxt["eigenvalues"],
+                              eF=nxt["eF"])
+        else:
+            energies = _
+        drho = nxt["rho"] - rho_in
+        info["energies"] = energies
+        info["history_Etot"].append(energies.total)
+        info["history_drho"].append(float(drho.norm()) * math.sqrt(basis.dvol))
+        nxt_rho = rho_in + mixing.mix_density(basis, drho)
+        info["converged"] = bool(basis.comm_kpts.bcast_object(is_converged(info)))
+        info["time_step"] = time.time() - t0
+        if callback:
+            callback(info)
+        return nxt_rho
+
+    x = rho
+    for _ in range(maxiter):
+        fx = fixpoint_map(x)
+        if info["converged"]:
+            break
+        x = acc(x, damping, fx - x)
+    rho_f = info["rho_out"]
+    energies, ham = energy_hamiltonian(basis, info["psi"], info["occupation"], rho=rho_f,
+                                       eigenvalues=info["eigenvalues"], eF=info["eF"])
+    return dict(ham=ham, basis=basis, energies=energies, converged=info["converged"], rho=rho_f,
+                eigenvalues=info["eigenvalues"], occupation=info["occupation"], eF=info["eF"], psi=info["psi"],
+                n_iter=info["n_iter"], n_matvec=info["n_matvec"], history_Etot=info["history_Etot"],
+                history_drho=info["history_drho"], diagonalization=info["diagonalization"],
+                n_bands_converge=info["n_bands_converge"], runtime_s=time.time() - start, stage="finalize",
+                algorithm="SCF")
+
+
+def ScfDefaultCallback():
+    """scf_callbacks.jl:30-124: the convergence table."""
+    def cb(info):
+        if info["n_iter"] == 1:
+            print("n     Energy            log10(ΔE)   log10(Δρ)   Diag   Δtime")
+            print("---   ---------------   ---------   ---------   ----   ------")
+        h = info["history_Etot"]
+        dE = "" if len(h) < 2 else f"{math.log10(max(abs(h[-1] - h[-2]), 1e-99)):9.2f}"
+        diag = np.mean(info["diagonalization"]["n_iter"])
+        print(f"{info['n_iter']:3d}   {h[-1]:+15.12f}   {dE:>9}   {math.log10(info['history_drho'][-1]):9.2f}   "
+              f"{diag:4.1f}   {info['time_step']:6.2f}s", flush=True)
+    return cb
