@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py -- Hψ applies/s (and SCF-step pieces) of the B200 plane-wave Kohn-Sham hot path.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line
+(rank 0).  A *step* is one full Hamiltonian application `mul!(Hψ, H::DftHamiltonianBlock, ψ)` on the block
+of M bands of one k-block (batched FFT local part + kinetic + nonlocal P D P†ψ).
+
+Workload at N=1: BASELINE.json configs[2] -- Si 5x5x5 supercell (250 atoms, 1000 e-), LDA, Γ only,
+Ecut = 30 Ha, fft 192³, N_pw = 264 859, M = 503 bands, n_proj = 1250 (the configuration the north-star
+targets are quoted on).  For N>1 every rank owns one k-block of that shape (k-points shard; weak scaling):
+no data-path collective inside Hψ; the density allreduce of an SCF step is timed separately.
+
+`value`  = band-applies/s with ψ/Hψ resident in HBM (CUDA events, max over ranks).
+`e2e`    = the same call through the C ABI with pinned HOST ψ/Hψ buffers (H2D + D2H inside the timed region).
+`roofline` = the Hψ-local kernel group (5 FFT-pipeline kernels per band chunk; HBM bound, algorithmic bytes
+             72·N_fft + 40·N_pw per band) against MEASURED_PEAKS.json hbm_gbs.
+`roofline_gemm` = the nonlocal P D P†ψ GEMMs (FP64 DMMA; 16·N_pw·n_proj·M flop) against a cuBLAS ZGEMM
+             probe measured in the same run (MEASURED_PEAKS.json has no FP64 figure).
+`cpu_baseline` = the CPU oracle (port of the reference's band-at-a-time algorithm) on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+A_SI = 10.26 / 2
+WORKLOADS = {
+    # name: (supercell repeat, Ecut, n_bands)
+    "si250": dict(rep=5, Ecut=30.0, desc="Si 5x5x5 supercell (250 atoms) LDA Gamma Ecut=30 Ha, fft 192^3"),
+    "si16": dict(rep=2, Ecut=30.0, desc="Si 2x2x2 supercell (16 atoms) LDA Gamma Ecut=30 Ha (dev/smoke size)"),
+    "si2": dict(rep=1, Ecut=30.0, desc="Si 2-atom primitive LDA Ecut=30 Ha (dev/smoke size)"),
+}
+
+
+def supercell(rep):
+    lat = rep * np.array([[0, A_SI, A_SI], [A_SI, 0, A_SI], [A_SI, A_SI, 0]])
+    pos = []
+    for i in range(rep):
+        for j in range(rep):
+            for k in range(rep):
+                for b in (np.ones(3) / 8, -np.ones(3) / 8):
+                    pos.append((b + np.array([i, j, k])) / rep)
+    return lat, pos
+
+
+def n_bands_for(n_atoms):
+    n_occ = 2 * n_atoms          # 4 e- per Si, doubly occupied
+    return n_occ + 3             # AdaptiveBands at T = 0 (nbands_algorithm.jl:57-66)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------- oracle arm
+def oracle_block(name, n_sample_bands, threads):
+    """CPU port of the reference path for the same workload (bounded number of bands)."""
+    from oracle.basis import Element, Model, PlaneWaveBasis as OBasis
+    from oracle.terms import Terms, energy_hamiltonian, guess_density
+    w = WORKLOADS[name]
+    lat, pos = supercell(w["rep"])
+    om = Model(lat, [Element("Si")] * len(pos), pos, functionals=("lda_x", "lda_c_pw"), symmetries=False,
+               terms=("Kinetic", "AtomicLocal", "AtomicNonlocal", "Hartree", "Xc"))
+    ob = OBasis(om, w["Ecut"], kcoords=[[0, 0, 0]], kweights=[1.0])
+    _, ham = energy_hamiltonian(ob, Terms(ob), None, None, guess_density(ob))
+    blk = ham[0]
+    blk.workers = threads
+    rng = np.random.default_rng(42)
+    psi = rng.standard_normal((blk.kpt.n_G, n_sample_bands)) + 1j * rng.standard_normal((blk.kpt.n_G, n_sample_bands))
+    return ob, blk, psi
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nb = args.cpu_bands
+    t0 = time.time()
+    ob, blk, psi = oracle_block(args.workload, nb, threads)
+    setup = time.time() - t0
+    for _ in range(args.warmup):
+        blk.matmul(psi)
+    ts = []
+    for _ in range(args.steps):
+        t = time.perf_counter()
+        blk.matmul(psi)
+        ts.append(time.perf_counter() - t)
+    dt = sum(ts)
+    value = nb * args.steps / dt
+    line = dict(metric="hpsi_band_applies_per_s", value=value, unit="band-applies/s", impl="reference", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=WORKLOADS[args.workload]["desc"], fft_size=list(ob.fft_size), n_pw=int(blk.kpt.n_G),
+                            n_proj=int(blk.PD[0].shape[1]), bands_per_step=nb),
+                cpu_baseline=dict(value=value, unit="band-applies/s", cores=threads, kind="port",
+                                  sample=f"{nb} bands of the {args.workload} block per step (NumPy/pocketfft band loop threaded "
+                                         f"over bands + OpenBLAS ZGEMM), oracle restatement of DFTK's CPU path; Julia absent"),
+                e2e=dict(value=value, unit="band-applies/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                setup_s=setup)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    import dftk_b200 as dftk
+    comm = dftk.KpointComm.from_torch_distributed() if world > 1 else dftk.KpointComm()
+    arch = dftk.B200(local, comm=comm if world > 1 else None)
+    ctx, dev = arch.ctx, arch.device
+    w = WORKLOADS[args.workload]
+    lat, pos = supercell(w["rep"])
+    t0 = time.time()
+    Si = dftk.ElementPsp("Si")
+    model = dftk.model_DFT(lat, [Si] * len(pos), pos, functionals=dftk.LDA(), symmetries=False)
+    # one k-block per rank: Gamma plus distinct shifted k-points for the other ranks (same N_pw to ~0.1 %)
+    kcoords = [[0.0, 0.0, 0.0]] + [[0.5 * (i % 2), 0.5 * ((i // 2) % 2), 0.5 * ((i // 4) % 2)] for i in range(1, world)]
+    basis = dftk.PlaneWaveBasis(model, Ecut=w["Ecut"], kgrid=dftk.ExplicitKpoints(kcoords), architecture=arch,
+                                comm_kpts=comm)
+    rho0 = dftk.guess_density(basis)
+    energies0, ham = dftk.energy_hamiltonian(basis, None, None, rho=rho0)
+    blk = ham[0]
+    kb = blk.kblock
+    n_pw, N = kb.n_pw, basis.N
+    M = args.bands or n_bands_for(len(pos))
+    setup = time.time() - t0
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    psi = torch.view_as_complex(torch.randn(M, n_pw, 2, generator=g, device=dev, dtype=torch.float64))
+    hpsi = torch.empty_like(psi)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- headline: full H apply on device-resident data
+    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.launch_count(reset=True)
+    ms_total = timed(lambda: kb.apply_h(psi, hpsi), args.steps, args.warmup)
+    launches = ctx.launch_count() // max(1, 1)    # launches since reset (includes warm-up)
+    launches_timed = int(round(launches * args.steps / (args.steps + args.warmup)))
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * M * args.steps / (ms_total * 1e-3)
+
+    # ---- kernel-group breakdown (same stream, CUDA events)
+    ms_local = timed(lambda: kb.apply_terms(psi, 3, out=hpsi), max(2, args.steps // 2), 1) / max(2, args.steps // 2)
+    ms_nl = timed(lambda: kb.apply_terms(psi, 4, out=hpsi), max(2, args.steps // 2), 1) / max(2, args.steps // 2)
+    hbm_peak, peak_src = peaks()
+    alg_bytes_band = 72.0 * N + 40.0 * n_pw
+    ach = alg_bytes_band * M / (ms_local * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel="Hpsi-local group (k_sphere_to_x,k_y_backward,k_z_apply_potential,k_y_forward,k_x_to_sphere)",
+                    achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None,
+                    algorithmic_bytes_per_band=alg_bytes_band, ms_per_block=ms_local, us_per_band=1e3 * ms_local / M,
+                    peak_source=peak_src + " (of measured)")
+    n_proj = kb.n_proj
+    fl_nl = 16.0 * n_pw * n_proj * M
+    # FP64 GEMM peak calibration: cuBLAS ZGEMM on the same shapes (library probe, not on the product path)
+    ctx.set_option("gemm_backend", 1)
+    ms_nl_cublas = timed(lambda: kb.apply_terms(psi, 4, out=hpsi), 2, 1) / 2
+    ctx.set_option("gemm_backend", 0)
+    tf_nl, tf_cublas = fl_nl / (ms_nl * 1e-3) / 1e12, fl_nl / (ms_nl_cublas * 1e-3) / 1e12
+    roofline_gemm = dict(bound="tensor", kernel="nonlocal P D P'psi (k_zgemm_cn + k_zgemm_nn, FP64 DMMA)", achieved=tf_nl,
+                         peak=tf_cublas, unit="TFLOP/s", frac=tf_nl / tf_cublas, flop=fl_nl, ms=ms_nl,
+                         peak_source="cuBLAS ZGEMM on the same shapes in the same run (calibration probe; nominal FP64 tensor 37-40 TFLOP/s)")
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        from dftk_b200._lib import check
+        from dftk_b200.device import _ptr
+        hpsi_h = torch.empty((M, n_pw), dtype=torch.complex128, pin_memory=True)
+        psi_h = torch.empty((M, n_pw), dtype=torch.complex128, pin_memory=True)
+        psi_h.copy_(psi)
+
+        def e2e_step():
+            check(ctx.L.dftk_b200_apply_h(kb.h, _ptr(psi_h), _ptr(hpsi_h), M), ctx.h)
+        ksteps = max(1, min(args.steps, 3))
+        for _ in range(1):
+            e2e_step()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        nbytes = M * n_pw * 16
+        e2e = dict(value=world * M * ksteps / dt, unit="band-applies/s", h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes,
+                   ms_per_step=1e3 * dt / ksteps)
+        del psi_h, hpsi_h
+
+    # ---- density accumulate + allreduce (the one real collective of an SCF step)
+    extra = {}
+    occ_w = np.full(M, 2.0)
+    rho = torch.zeros(N, dtype=torch.float64, device=dev)
+    ms_rho = timed(lambda: kb.density_accumulate(psi, occ_w, rho), 2, 1) / 2
+    extra["density_ms_per_block"] = ms_rho
+    extra["density_GBs_alg"] = (32.0 * N + 16.0 * n_pw) * M / (ms_rho * 1e-3) / 1e9
+    if world > 1:
+        rbuf = torch.zeros((1, N), dtype=torch.float64, device=dev)
+        extra["rho_allreduce_ms"] = timed(lambda: ctx.allreduce(rbuf), 5, 2) / 5
+    # ---- one LOBPCG solve at loose tolerance = the eigensolver part of the first SCF step (optional)
+    if args.scf:
+        X = psi.clone()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        res = kb.lobpcg(X, tol=args.scf_tol, maxiter=args.scf_maxiter, n_conv_check=M - 3)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        extra["lobpcg"] = dict(seconds=dt, n_iter=res["n_iter"], n_matvec=res["n_matvec"], converged=res["converged"],
+                               tol=args.scf_tol, s_per_iter=dt / max(1, res["n_iter"]))
+        del X
+
+    # ---- CPU baseline on rank 0 (bounded sample)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        nb = args.cpu_bands
+        P = kb_P = None
+        from oracle.terms import HamiltonianBlock
+        from oracle.basis import Kpoint as OKpoint
+
+        class _B:      # minimal oracle-basis view over the same operator data (fft methods only)
+            pass
+        from oracle.basis import PlaneWaveBasis as OBasis, Model as OModel, Element
+        om = OModel(lat, [Element("Si")] * len(pos), pos, symmetries=False, terms=("Kinetic",))
+        ob = OBasis(om, w["Ecut"], kcoords=[[0, 0, 0]], kweights=[1.0])
+        blk0_kin = basis.term("Kinetic").kinetic_energies[0].cpu().numpy()
+        V = blk.local_op.potential.cpu().numpy()
+        nlop = basis.term("AtomicNonlocal").ops[0]
+        Pn = nlop.P.cpu().numpy().T.copy() if rank == 0 else None
+        oblk = HamiltonianBlock(ob, 0, blk0_kin, V, (Pn, nlop.D))
+        oblk.workers = threads
+        xs = psi[:nb].cpu().numpy().T.copy()
+        oblk.matmul(xs[:, :1])
+        t = time.perf_counter()
+        ref = oblk.matmul(xs)
+        dt = time.perf_counter() - t
+        got = hpsi_check = kb.apply_h(psi[:nb].contiguous()).cpu().numpy().T
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        cpu = dict(value=nb / dt, unit="band-applies/s", cores=threads, kind="port",
+                   sample=f"{nb} bands of the same block, one pass (NumPy pocketfft band loop threaded over bands + OpenBLAS ZGEMM)",
+                   seconds=dt, max_rel_err_vs_gpu=err)
+        del Pn
+
+    if rank == 0:
+        line = dict(metric="hpsi_band_applies_per_s", value=value, unit="band-applies/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f64", data="synthetic",
+                    config=dict(workload=w["desc"] + (f", one k-block per GPU ({world} k-points)" if world > 1 else ""),
+                                fft_size=list(basis.fft_size), n_pw=n_pw, n_bands=M, n_proj=n_proj,
+                                parallelism=f"kpoints x{world}", cache="inputs (psi 16*n_pw*M bytes) larger than L2"),
+                    block_applies_per_s=world * args.steps / (ms_total * 1e-3),
+                    roofline=roofline, roofline_gemm=roofline_gemm, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches_timed,
+                    clocks=clocks, setup_s=setup, **extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DFTK_BENCH_WORKLOAD", "si250"), choices=list(WORKLOADS))
+    ap.add_argument("--bands", type=int, default=0)
+    ap.add_argument("--cpu-bands", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scf", action="store_true", help="also time one LOBPCG solve (first-SCF-step tolerance)")
+    ap.add_argument("--scf-tol", type=float, default=0.025)
+    ap.add_argument("--scf-maxiter", type=int, default=30)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

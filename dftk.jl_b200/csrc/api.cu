@@ -72,6 +72,7 @@ static int ctx_create_common(int device, dftk_b200_ctx** out) {
   CUSOLVER_CHECK(cusolverDnCreate(&c->cusolver));
   CUSOLVER_CHECK(cusolverDnSetStream(c->cusolver, c->stream));
   fft_set_attributes();
+  reg_set_attributes();
   blas_set_attributes();
   *out = c;
   return 0;
@@ -146,6 +147,7 @@ int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
   std::string n(name);
   if (n == "gemm_backend") ctx->gemm_backend = (int)value;
   else if (n == "band_chunk") ctx->band_chunk = (int)value;
+  else if (n == "fft_engine") ctx->fft_engine = (int)value;  // 0 = register two-pass where available, 1 = generic
   else throw Error(DFTK_B200_EINVAL, "set_option: unknown option " + n);
   API_END(ctx)
 }
@@ -173,6 +175,11 @@ int dftk_b200_grid_create(dftk_b200_ctx* ctx, int nx, int ny, int nz, double uni
     g->Lx = choose_lines(nx);
     g->Ly = choose_lines(ny);
     g->Lz = choose_lines(nz);
+    if (ctx->fft_engine == 0) {
+      g->rx = reg_kernels_for(nx);
+      g->ry = reg_kernels_for(ny);
+      g->rz = reg_kernels_for(nz);
+    }
     auto tx = make_twiddles(nx), ty = make_twiddles(ny), tz = make_twiddles(nz);
     g->twx.upload(tx.data(), tx.size(), ctx->stream);
     g->twy.upload(ty.data(), ty.size(), ctx->stream);
@@ -235,11 +242,13 @@ int dftk_b200_kblock_create(dftk_b200_grid* grid, int64_t n_pw, const int64_t* m
     kb->d_slot_src.upload(H.slot_src.data(), H.slot_src.size(), s);
     kb->d_zlist.upload(H.zlist.data(), H.zlist.size(), s);
     kb->d_colmap.upload(H.colmap.data(), H.colmap.size(), s);
-    SphereTables& T = kb->T;
+    kb->d_zc_of.upload(H.zc_of.data(), H.zc_of.size(), s);
+    SphereTablesX& T = kb->T;
     T.nx = H.nx; T.ny = H.ny; T.nz = H.nz; T.n_pw = n_pw; T.n_cols = H.n_cols; T.cnt_max = H.cnt_max;
     T.n_zc = H.n_zc; T.col_start = kb->d_col_start.p; T.col_cnt = kb->d_col_cnt.p;
     T.slot_ix = kb->d_slot_ix.p; T.slot_src = kb->d_slot_src.p; T.zlist = kb->d_zlist.p;
     T.colmap = kb->d_colmap.p;
+    T.zc_of = kb->d_zc_of.p;
     if (kin) {
       kb->kin.ensure(n_pw);
       CUDA_CHECK(cudaMemcpyAsync(kb->kin.p, kin, n_pw * sizeof(double), cudaMemcpyDefault, s));

@@ -6,7 +6,9 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["fft.cu", "blas.cu", "lobpcg.cu", "api.cu"]
-HEADERS = ["common.cuh", "structs.cuh", "fft_core.cuh", "fft_plan.h", os.path.join("..", "..", "include", "dftk_b200.h")]
+REG_NGROUPS = 4
+HEADERS = ["common.cuh", "structs.cuh", "fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_reg_fwd.cuh", "fft_reg.cu",
+           "fft_radix_gen.cuh", os.path.join("..", "..", "include", "dftk_b200.h")]
 LIB = os.path.join(HERE, "..", "libdftk_b200.so")
 
 
@@ -33,8 +35,14 @@ def build(force=False, verbose=False):
     objs = []
 
     def cc(src):
-        obj = os.path.join(HERE, src.replace(".cu", ".o"))
-        cmd = ["nvcc"] + flags + ["-c", os.path.join(HERE, src), "-o", obj]
+        extra = []
+        if isinstance(src, tuple):           # (source, group) for the register-engine instantiation units
+            src, grp = src
+            obj = os.path.join(HERE, f"fft_reg_g{grp}.o")
+            extra = [f"-DREG_GROUP={grp}", f"-DREG_NGROUPS={REG_NGROUPS}"]
+        else:
+            obj = os.path.join(HERE, src.replace(".cu", ".o"))
+        cmd = ["nvcc"] + flags + extra + ["-c", os.path.join(HERE, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stderr}")
@@ -42,8 +50,8 @@ def build(force=False, verbose=False):
             print(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(4) as ex:
-        objs = list(ex.map(cc, SOURCES))
+    with ThreadPoolExecutor(8) as ex:
+        objs = list(ex.map(cc, SOURCES + [("fft_reg.cu", g) for g in range(REG_NGROUPS)]))
     nccl_so = os.path.join(libdir, "libnccl.so.2")
     link = ["g++", "-shared", "-o", lib] + objs + ["-L/usr/local/cuda/lib64", "-lcublas", "-lcusolver",
                                                     "-lcudart", f"-Wl,-rpath,{libdir}",

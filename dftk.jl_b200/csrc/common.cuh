@@ -90,6 +90,7 @@ struct dftk_b200_ctx {
   int64_t launches = 0;
   int gemm_backend = 0;   // 0 = own DMMA kernels, 1 = cuBLAS (A/B comparison only)
   int band_chunk = 0;     // 0 = auto
+  int fft_engine = 0;     // 0 = register two-pass engine where a factor pair exists, 1 = generic Stockham (applies to grids created afterwards)
   int sm_count = 148;
   std::string last_error;
   dftk::DevBuf<char> solver_work;

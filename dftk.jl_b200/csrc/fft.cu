@@ -84,6 +84,43 @@ void fft_set_attributes() {
 }
 
 static inline size_t smem_for(int n, int L) { return 2 * (size_t)n * (L | 1) * sizeof(cplx); }
+
+// ---- register two-pass engine registry (fft_reg.cu, compiled in REG_NGROUPS translation units)
+void reg_register_group_0(std::vector<RegKernels>&);
+void reg_register_group_1(std::vector<RegKernels>&);
+void reg_register_group_2(std::vector<RegKernels>&);
+void reg_register_group_3(std::vector<RegKernels>&);
+static std::vector<RegKernels>& reg_table() {
+  static std::vector<RegKernels> tab = [] {
+    std::vector<RegKernels> t;
+    reg_register_group_0(t);
+    reg_register_group_1(t);
+    reg_register_group_2(t);
+    reg_register_group_3(t);
+    return t;
+  }();
+  return tab;
+}
+const RegKernels* reg_kernels_for(int n) {
+  int A, B;
+  reg_pair_for(n, &A, &B);
+  if (A == 0) return nullptr;
+  for (const RegKernels& k : reg_table())
+    if (k.A == A && k.B == B) return &k;
+  return nullptr;
+}
+void reg_set_attributes() {
+  for (const RegKernels& k : reg_table())
+    for (const void* f : {k.sphere_to_x, k.y_backward, k.z_apply, k.z_to_cube, k.z_from_cube, k.z_density,
+                          k.y_forward, k.x_to_sphere})
+      CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+}
+static inline int reg_L(const RegKernels* k) { return k->T >= 8 ? 16 : 32; }
+static inline size_t reg_smem(const RegKernels* k) { return 2 * (size_t)k->A * k->B * (reg_L(k) + 1) * sizeof(cplx); }
+static void launch_ptr(dftk_b200_ctx* ctx, const void* f, dim3 grid, int threads, size_t smem, void** args) {
+  CUDA_CHECK(cudaLaunchKernel(f, grid, dim3(threads), args, smem, ctx->stream));
+  ctx->launches++;
+}
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 // CUDA limits gridDim.y/z to 65535: fine for every axis length the engine supports.
@@ -136,12 +173,25 @@ void kb_sphere_to_planes(dftk_b200_kblock* kb, const cplx* psi, int64_t ldpsi, i
   dftk_b200_grid* g = kb->grid;
   dftk_b200_ctx* ctx = g->ctx;
   ensure_scratch(kb, nb);
-  {
+  if (g->rx) {
+    int L = reg_L(g->rx), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twx.p;
+    cplx* W1 = kb->W1.p;
+    void* args[] = {&kb->T, &tw, &psi, &ldpsi, &W1, &L, &Lp};
+    launch_ptr(ctx, g->rx->sphere_to_x, dim3(cdiv(kb->T.n_cols, L), nb), L * g->rx->T, reg_smem(g->rx), args);
+  } else {
     int L = g->Lx, Lp = L | 1;
     LAUNCH(ctx, k_sphere_to_x, dim3(cdiv(kb->T.n_cols, L), nb), FFT_THREADS, smem_for(g->nx, L), kb->T,
            g->px, (const cplx*)g->twx.p, psi, ldpsi, kb->W1.p, L, Lp);
   }
-  {
+  if (g->ry) {
+    int L = reg_L(g->ry), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twy.p;
+    const cplx* W1 = kb->W1.p;
+    cplx* W2 = kb->W2.p;
+    void* args[] = {&kb->T, &tw, &W1, &W2, &L, &Lp};
+    launch_ptr(ctx, g->ry->y_backward, dim3(cdiv(g->nx, L), kb->T.n_zc, nb), L * g->ry->T, reg_smem(g->ry), args);
+  } else {
     int L = g->Ly, Lp = L | 1;
     LAUNCH(ctx, k_y_backward, dim3(cdiv(g->nx, L), kb->T.n_zc, nb), FFT_THREADS, smem_for(g->ny, L),
            kb->T, g->py, (const cplx*)g->twy.p, (const cplx*)kb->W1.p, kb->W2.p, L, Lp);
@@ -152,12 +202,25 @@ void kb_planes_to_sphere(dftk_b200_kblock* kb, cplx* out, int64_t ldout, int nb,
                          const double* kin, const cplx* psi, int64_t ldpsi, int accumulate) {
   dftk_b200_grid* g = kb->grid;
   dftk_b200_ctx* ctx = g->ctx;
-  {
+  if (g->ry) {
+    int L = reg_L(g->ry), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twy.p;
+    const cplx* W2 = kb->W2.p;
+    cplx* W1 = kb->W1.p;
+    void* args[] = {&kb->T, &tw, &W2, &W1, &L, &Lp};
+    launch_ptr(ctx, g->ry->y_forward, dim3(cdiv(g->nx, L), kb->T.n_zc, nb), L * g->ry->T, reg_smem(g->ry), args);
+  } else {
     int L = g->Ly, Lp = L | 1;
     LAUNCH(ctx, k_y_forward, dim3(cdiv(g->nx, L), kb->T.n_zc, nb), FFT_THREADS, smem_for(g->ny, L),
            kb->T, g->py, (const cplx*)g->twy.p, (const cplx*)kb->W2.p, kb->W1.p, L, Lp);
   }
-  {
+  if (g->rx) {
+    int L = reg_L(g->rx), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twx.p;
+    const cplx* W1 = kb->W1.p;
+    void* args[] = {&kb->T, &tw, &W1, &out, &ldout, &scale, &kin, &psi, &ldpsi, &accumulate, &L, &Lp};
+    launch_ptr(ctx, g->rx->x_to_sphere, dim3(cdiv(kb->T.n_cols, L), nb), L * g->rx->T, reg_smem(g->rx), args);
+  } else {
     int L = g->Lx, Lp = L | 1;
     LAUNCH(ctx, k_x_to_sphere, dim3(cdiv(kb->T.n_cols, L), nb), FFT_THREADS, smem_for(g->nx, L), kb->T,
            g->px, (const cplx*)g->twx.p, (const cplx*)kb->W1.p, out, ldout, scale, kin, psi, ldpsi,
@@ -181,9 +244,18 @@ void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, i
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     const cplx* p = psi + b0 * kb->n_pw;
     kb_sphere_to_planes(kb, p, kb->n_pw, nb);
-    int L = g->Lz, Lp = L | 1;
-    LAUNCH(ctx, k_z_apply_potential, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L),
-           kb->T, g->pz, (const cplx*)g->twz.p, kb->W2.p, (const double*)kb->V.p, L, Lp);
+    if (g->rz) {
+      int L = reg_L(g->rz), Lp = L + 1;
+      const cplx* tw = (const cplx*)g->twz.p;
+      cplx* W2 = kb->W2.p;
+      const double* V = kb->V.p;
+      void* args[] = {&kb->T, &tw, &W2, &V, &L, &Lp};
+      launch_ptr(ctx, g->rz->z_apply, dim3(cdiv(g->nx, L), g->ny, nb), L * g->rz->T, reg_smem(g->rz), args);
+    } else {
+      int L = g->Lz, Lp = L | 1;
+      LAUNCH(ctx, k_z_apply_potential, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L),
+             kb->T, g->pz, (const cplx*)g->twz.p, kb->W2.p, (const double*)kb->V.p, L, Lp);
+    }
     kb_planes_to_sphere(kb, hpsi + b0 * kb->n_pw, kb->n_pw, nb, 1.0, with_kin ? kb->kin.p : nullptr, p,
                         kb->n_pw, accumulate ? 1 : 0);
   }
@@ -196,9 +268,18 @@ void kb_sphere_to_real(dftk_b200_kblock* kb, const cplx* psi, cplx* cube, int64_
   for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     kb_sphere_to_planes(kb, psi + b0 * kb->n_pw, kb->n_pw, nb);
-    int L = g->Lz, Lp = L | 1;
-    LAUNCH(ctx, k_z_to_cube, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L), kb->T,
-           g->pz, (const cplx*)g->twz.p, (const cplx*)kb->W2.p, cube + b0 * g->N, scale, L, Lp);
+    if (g->rz) {
+      int L = reg_L(g->rz), Lp = L + 1;
+      const cplx* tw = (const cplx*)g->twz.p;
+      const cplx* W2 = kb->W2.p;
+      cplx* cb = cube + b0 * g->N;
+      void* args[] = {&kb->T, &tw, &W2, &cb, &scale, &L, &Lp};
+      launch_ptr(ctx, g->rz->z_to_cube, dim3(cdiv(g->nx, L), g->ny, nb), L * g->rz->T, reg_smem(g->rz), args);
+    } else {
+      int L = g->Lz, Lp = L | 1;
+      LAUNCH(ctx, k_z_to_cube, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L), kb->T,
+             g->pz, (const cplx*)g->twz.p, (const cplx*)kb->W2.p, cube + b0 * g->N, scale, L, Lp);
+    }
   }
 }
 
@@ -209,9 +290,18 @@ void kb_real_to_sphere(dftk_b200_kblock* kb, const cplx* cube, cplx* out, int64_
   for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     ensure_scratch(kb, nb);
-    int L = g->Lz, Lp = L | 1;
-    LAUNCH(ctx, k_z_from_cube, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L), kb->T,
-           g->pz, (const cplx*)g->twz.p, cube + b0 * g->N, kb->W2.p, L, Lp);
+    if (g->rz) {
+      int L = reg_L(g->rz), Lp = L + 1;
+      const cplx* tw = (const cplx*)g->twz.p;
+      const cplx* cb = cube + b0 * g->N;
+      cplx* W2 = kb->W2.p;
+      void* args[] = {&kb->T, &tw, &cb, &W2, &L, &Lp};
+      launch_ptr(ctx, g->rz->z_from_cube, dim3(cdiv(g->nx, L), g->ny, nb), L * g->rz->T, reg_smem(g->rz), args);
+    } else {
+      int L = g->Lz, Lp = L | 1;
+      LAUNCH(ctx, k_z_from_cube, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L), kb->T,
+             g->pz, (const cplx*)g->twz.p, cube + b0 * g->N, kb->W2.p, L, Lp);
+    }
     kb_planes_to_sphere(kb, out + b0 * kb->n_pw, kb->n_pw, nb, scale, nullptr, nullptr, 0, 0);
   }
 }
@@ -229,10 +319,20 @@ void kb_density_accumulate(dftk_b200_kblock* kb, const cplx* psi, const double* 
   for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     kb_sphere_to_planes(kb, psi + b0 * kb->n_pw, kb->n_pw, nb);
-    int L = g->Lz, Lp = L | 1;
-    size_t sm = smem_for(g->nz, L) + (size_t)g->nz * L * sizeof(double);
-    LAUNCH(ctx, k_z_density, dim3(cdiv(g->nx, L), g->ny), FFT_THREADS, sm, kb->T, g->pz,
-           (const cplx*)g->twz.p, (const cplx*)kb->W2.p, (const double*)(kb->wts.p + b0), nb, rho, L, Lp);
+    if (g->rz) {
+      int L = reg_L(g->rz), Lp = L + 1;
+      const cplx* tw = (const cplx*)g->twz.p;
+      const cplx* W2 = kb->W2.p;
+      const double* wp = kb->wts.p + b0;
+      size_t sm = reg_smem(g->rz) + (size_t)g->nz * L * sizeof(double);
+      void* args[] = {&kb->T, &tw, &W2, &wp, &nb, &rho, &L, &Lp};
+      launch_ptr(ctx, g->rz->z_density, dim3(cdiv(g->nx, L), g->ny), L * g->rz->T, sm, args);
+    } else {
+      int L = g->Lz, Lp = L | 1;
+      size_t sm = smem_for(g->nz, L) + (size_t)g->nz * L * sizeof(double);
+      LAUNCH(ctx, k_z_density, dim3(cdiv(g->nx, L), g->ny), FFT_THREADS, sm, kb->T, g->pz,
+             (const cplx*)g->twz.p, (const cplx*)kb->W2.p, (const double*)(kb->wts.p + b0), nb, rho, L, Lp);
+    }
   }
   // the host weight vector must outlive the async upload
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

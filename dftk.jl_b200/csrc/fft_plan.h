@@ -67,11 +67,26 @@ inline int choose_lines(int n, size_t smem_budget = 100 * 1024) {
   throw std::runtime_error("fft axis too long for the shared-memory engine");
 }
 
+// Factor pair (A, B), n = A*B, for the register two-pass engine (fft_reg.cuh); {0,0} = use the generic
+// Stockham engine.  Only pairs instantiated in fft_reg.cu may be listed here.
+#define DFTK_REG_PAIRS(X) \
+  X(3, 5) X(4, 4) X(3, 6) X(4, 5) X(4, 6) X(5, 5) X(3, 9) X(5, 6) X(4, 8) X(6, 6) X(5, 8) X(5, 9) X(6, 8) \
+  X(6, 9) X(6, 10) X(8, 8) X(8, 9) X(5, 15) X(8, 10) X(9, 10) X(8, 12) X(10, 10) X(9, 12) X(10, 12) X(5, 25) \
+  X(8, 16) X(9, 15) X(12, 12) X(10, 15) X(10, 16) X(12, 15) X(12, 16) X(10, 20) X(12, 18) X(15, 15) X(15, 16) \
+  X(16, 16)
+inline void reg_pair_for(int n, int* A, int* B) {
+  *A = 0;
+  *B = 0;
+#define DFTK_X(a, b) if (n == (a) * (b) && *A == 0) { *A = (a); *B = (b); }
+  DFTK_REG_PAIRS(DFTK_X)
+#undef DFTK_X
+}
+
 struct SphereTablesHost {
   int nx, ny, nz;
   int64_t n_pw;
   int n_cols, cnt_max, n_zc;
-  std::vector<int> col_start, col_cnt, slot_ix, slot_src, zlist, colmap, col_y, col_z;
+  std::vector<int> col_start, col_cnt, slot_ix, slot_src, zlist, colmap, col_y, col_z, zc_of;
 };
 
 // mapping: 0-based linear cube indices (x fastest) of the sphere coefficients, any order.
@@ -120,6 +135,8 @@ inline SphereTablesHost build_sphere_tables(int nx, int ny, int nz, int64_t n_pw
   for (int c = 0; c < T.n_cols; ++c)
     if (T.zlist.empty() || T.zlist.back() != T.col_z[c]) T.zlist.push_back(T.col_z[c]);
   T.n_zc = (int)T.zlist.size();
+  T.zc_of.assign(nz, -1);
+  for (int i = 0; i < T.n_zc; ++i) T.zc_of[T.zlist[i]] = i;
   T.colmap.assign((size_t)T.n_zc * ny, -1);
   int izc = -1, lastz = -1;
   for (int c = 0; c < T.n_cols; ++c) {

@@ -1,0 +1,395 @@
+// Register-resident two-pass ("four-step") 1D FFT stages of the pruned sphere<->cube pipeline.
+//
+// An axis of length n = A*B is transformed in two passes with ONE shared-memory exchange:
+//   pass 1 (B threads per line, thread q holds the A elements q + B r):  Y[c] = DFT_A over r, times W_n^{qc}
+//   exchange through shared memory S[c*B + q]
+//   pass 2 (A threads per line, thread c holds S[c*B + q], q < B):       X[c + A d] = DFT_B over q
+// The butterflies are generated straight-line code (fft_radix_gen.cuh).  Compared with the generic
+// Stockham engine (fft_core.cuh, kept as the fallback for sizes without a factor pair) this moves 32 B per
+// element per transform through shared memory instead of ~160 B and does no per-butterfly index division.
+//
+// Global memory goes straight to/from registers for the strided axes (y, z): consecutive threads are
+// consecutive x (the contiguous dimension), so every access is a 16-lane * 16 B = 256 B segment.
+// The contiguous axis (x) is transposed through shared memory on the way in/out.
+//
+// Bodies are __host__ __device__ with TLOOP/TSYNC like fft_core.cuh so tests/hostemu can run them.
+// Contract on the device: blockDim.x == L * max(A, B); no register state is live across a TSYNC.
+#pragma once
+#include "fft_core.cuh"
+#include "fft_reg_fwd.cuh"
+#include "fft_radix_gen.cuh"
+
+namespace dftk {
+
+template <int A, int B>
+struct RegPair {
+  static constexpr int n = A * B;
+  static constexpr int T = (A > B ? A : B);
+};
+
+// thread q (< B) holds x[r] = element q + B*r; writes twiddled DFT_A to S[(c*B + q)]
+template <int A, int B, int S>
+HD void pass1_store(const cplx* x, int q, int line, cplx* __restrict__ Sbuf, int Lp,
+                    const cplx* __restrict__ tw) {
+  cplx Y[A];
+  dft_r<A, S>(x, Y);
+#pragma unroll
+  for (int c = 0; c < A; ++c) {
+    cplx v = Y[c];
+    if (c != 0 && q != 0) v = cmul(v, twiddle(tw, q * c, S));
+    Sbuf[(c * B + q) * Lp + line] = v;
+  }
+}
+// thread c (< A) loads S[(c*B + q)], q < B; X[d] = element c + A*d
+template <int A, int B, int S>
+HD void pass2_load(cplx* X, int c, int line, const cplx* __restrict__ Sbuf, int Lp) {
+  cplx t[B];
+#pragma unroll
+  for (int q = 0; q < B; ++q) t[q] = Sbuf[(c * B + q) * Lp + line];
+  dft_r<B, S>(t, X);
+}
+
+// ---------------------------------------------------------------------------------------------- z stages
+template <int A, int B>
+HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ tw, cplx* __restrict__ W2,
+                              const double* __restrict__ V, int L, int Lp, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  const int nx = T.nx, ny = T.ny;
+  cplx* bufA = sm;
+  cplx* bufB = sm + (size_t)n * Lp;
+  const int x0 = bid.x * L, y = bid.y;
+  cplx* w2 = W2 + (size_t)bid.z * T.n_zc * ny * nx;
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r) {
+        int zc = T.zc_of[p + B * r];
+        v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
+      }
+      pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, +1>(X, p, line, bufA, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d) {
+        double vv = (x < nx) ? V[((size_t)(p + A * d) * ny + y) * nx + x] : 0.0;
+        X[d] = cscale(X[d], vv);
+      }
+      // forward transform of the elements p + A*d: pass 1 with the roles of A and B swapped
+      pass1_store<B, A, -1>(X, p, line, bufB, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < B) {
+      cplx X[A];
+      pass2_load<B, A, -1>(X, p, line, bufB, Lp);
+#pragma unroll
+      for (int f = 0; f < A; ++f) {
+        int zc = T.zc_of[p + B * f];
+        if (zc >= 0 && x < nx) w2[((size_t)zc * ny + y) * nx + x] = X[f];
+      }
+    }
+  }
+}
+
+template <int A, int B>
+HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W2,
+                      cplx* __restrict__ cube, double scale, int L, int Lp, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  const int nx = T.nx, ny = T.ny;
+  cplx* bufA = sm;
+  const int x0 = bid.x * L, y = bid.y;
+  const cplx* w2 = W2 + (size_t)bid.z * T.n_zc * ny * nx;
+  cplx* out = cube + (size_t)bid.z * nx * ny * n;
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r) {
+        int zc = T.zc_of[p + B * r];
+        v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
+      }
+      pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, +1>(X, p, line, bufA, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d)
+        if (x < nx) out[((size_t)(p + A * d) * ny + y) * nx + x] = cscale(X[d], scale);
+    }
+  }
+}
+
+template <int A, int B>
+HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ cube,
+                        cplx* __restrict__ W2, int L, int Lp, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  const int nx = T.nx, ny = T.ny;
+  cplx* bufA = sm;
+  const int x0 = bid.x * L, y = bid.y;
+  const cplx* in = cube + (size_t)bid.z * nx * ny * n;
+  cplx* w2 = W2 + (size_t)bid.z * T.n_zc * ny * nx;
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r)
+        v[r] = (x < nx) ? in[((size_t)(p + B * r) * ny + y) * nx + x] : make_double2(0.0, 0.0);
+      pass1_store<A, B, -1>(v, p, line, bufA, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, -1>(X, p, line, bufA, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d) {
+        int zc = T.zc_of[p + A * d];
+        if (zc >= 0 && x < nx) w2[((size_t)zc * ny + y) * nx + x] = X[d];
+      }
+    }
+  }
+}
+
+// density: acc (double[n*L] after the two complex buffers) is owned element-wise by the pass-2 threads
+template <int A, int B>
+HD void reg_z_density(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W2,
+                      const double* __restrict__ wts, int nb, double* __restrict__ rho, int L, int Lp,
+                      cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  const int nx = T.nx, ny = T.ny;
+  cplx* bufA = sm;
+  double* acc = (double*)(sm + 2 * (size_t)n * Lp);
+  const int x0 = bid.x * L, y = bid.y;
+  TLOOP(t, n * L) acc[t] = 0.0;
+  for (int band = 0; band < nb; ++band) {
+    const cplx* w2 = W2 + (size_t)band * T.n_zc * ny * nx;
+    TSYNC();
+    TLOOP(t, L * TT) {
+      const int line = t % L, p = t / L, x = x0 + line;
+      if (p < B) {
+        cplx v[A];
+#pragma unroll
+        for (int r = 0; r < A; ++r) {
+          int zc = T.zc_of[p + B * r];
+          v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
+        }
+        pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
+      }
+    }
+    TSYNC();
+    const double w = wts[band];
+    TLOOP(t, L * TT) {
+      const int line = t % L, p = t / L;
+      if (p < A) {
+        cplx X[B];
+        pass2_load<A, B, +1>(X, p, line, bufA, Lp);
+#pragma unroll
+        for (int d = 0; d < B; ++d) acc[(p + A * d) * L + line] += w * (X[d].x * X[d].x + X[d].y * X[d].y);
+      }
+    }
+  }
+  TSYNC();
+  TLOOP(t, n * L) {
+    const int line = t % L, iz = t / L, x = x0 + line;
+    if (x < nx) rho[((size_t)iz * ny + y) * nx + x] += acc[t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- y stages
+template <int A, int B>
+HD void reg_y_backward(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W1,
+                       cplx* __restrict__ W2, int L, int Lp, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  const int nx = T.nx;
+  cplx* bufA = sm;
+  const int x0 = bid.x * L, izc = bid.y;
+  const cplx* in = W1 + (size_t)bid.z * T.n_cols * nx;
+  cplx* out = W2 + ((size_t)bid.z * T.n_zc + izc) * n * nx;
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r) {
+        int c = T.colmap[izc * n + p + B * r];
+        v[r] = (c >= 0 && x < nx) ? in[(size_t)c * nx + x] : make_double2(0.0, 0.0);
+      }
+      pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, +1>(X, p, line, bufA, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d)
+        if (x < nx) out[(size_t)(p + A * d) * nx + x] = X[d];
+    }
+  }
+}
+
+template <int A, int B>
+HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W2,
+                      cplx* __restrict__ W1, int L, int Lp, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  const int nx = T.nx;
+  cplx* bufA = sm;
+  const int x0 = bid.x * L, izc = bid.y;
+  const cplx* in = W2 + ((size_t)bid.z * T.n_zc + izc) * n * nx;
+  cplx* out = W1 + (size_t)bid.z * T.n_cols * nx;
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r)
+        v[r] = (x < nx) ? in[(size_t)(p + B * r) * nx + x] : make_double2(0.0, 0.0);
+      pass1_store<A, B, -1>(v, p, line, bufA, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L, x = x0 + line;
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, -1>(X, p, line, bufA, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d) {
+        int c = T.colmap[izc * n + p + A * d];
+        if (c >= 0 && x < nx) out[(size_t)c * nx + x] = X[d];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- x stages
+// (contiguous axis: coalesced transposing load/store through shared memory)
+template <int A, int B>
+HD void reg_sphere_to_x(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ psi,
+                        int64_t ldpsi, cplx* __restrict__ W1, int L, int Lp, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  cplx* bufA = sm;
+  cplx* bufB = sm + (size_t)n * Lp;
+  const int c0 = bid.x * L;
+  const int64_t band = bid.y;
+  TLOOP(t, n * Lp) bufA[t] = make_double2(0.0, 0.0);
+  TSYNC();
+  TLOOP(t, L * T.cnt_max) {
+    int line = t / T.cnt_max, i = t % T.cnt_max;
+    int c = c0 + line;
+    if (c < T.n_cols && i < T.col_cnt[c]) {
+      int s = T.col_start[c] + i;
+      bufA[T.slot_ix[s] * Lp + line] = psi[band * ldpsi + T.slot_src[s]];
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r) v[r] = bufA[(p + B * r) * Lp + line];
+      pass1_store<A, B, +1>(v, p, line, bufB, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L;
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, +1>(X, p, line, bufB, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d) bufA[(p + A * d) * Lp + line] = X[d];
+    }
+  }
+  TSYNC();
+  cplx* out = W1 + (size_t)band * T.n_cols * n;
+  TLOOP(t, L * n) {
+    int line = t / n, x = t % n;
+    int c = c0 + line;
+    if (c < T.n_cols) out[(size_t)c * n + x] = bufA[x * Lp + line];
+  }
+}
+
+template <int A, int B>
+HD void reg_x_to_sphere(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W1,
+                        cplx* __restrict__ out, int64_t ldout, double scale, const double* __restrict__ kin,
+                        const cplx* __restrict__ psi, int64_t ldpsi, int accumulate, int L, int Lp, cplx* sm,
+                        Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  cplx* bufA = sm;
+  cplx* bufB = sm + (size_t)n * Lp;
+  const int c0 = bid.x * L;
+  const int64_t band = bid.y;
+  const cplx* in = W1 + (size_t)band * T.n_cols * n;
+  TLOOP(t, L * n) {
+    int line = t / n, x = t % n;
+    int c = c0 + line;
+    bufA[x * Lp + line] = (c < T.n_cols) ? in[(size_t)c * n + x] : make_double2(0.0, 0.0);
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r) v[r] = bufA[(p + B * r) * Lp + line];
+      pass1_store<A, B, -1>(v, p, line, bufB, Lp, tw);
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * TT) {
+    const int line = t % L, p = t / L;
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, -1>(X, p, line, bufB, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d) bufA[(p + A * d) * Lp + line] = X[d];
+    }
+  }
+  TSYNC();
+  TLOOP(t, L * T.cnt_max) {
+    int line = t / T.cnt_max, i = t % T.cnt_max;
+    int c = c0 + line;
+    if (c < T.n_cols && i < T.col_cnt[c]) {
+      int s = T.col_start[c] + i;
+      int src = T.slot_src[s];
+      cplx v = cscale(bufA[T.slot_ix[s] * Lp + line], scale);
+      if (kin) {
+        cplx pp = psi[band * ldpsi + src];
+        double kk = kin[src];
+        v.x += kk * pp.x;
+        v.y += kk * pp.y;
+      }
+      cplx* o = out + band * ldout + src;
+      if (accumulate) {
+        v.x += o->x;
+        v.y += o->y;
+      }
+      *o = v;
+    }
+  }
+}
+
+}  // namespace dftk

@@ -1,7 +1,19 @@
 // Grid / k-block handle definitions shared by the translation units of libdftk_b200.
 #pragma once
 #include "common.cuh"
+#include "fft_reg_fwd.cuh"
 #include "fft_plan.h"
+
+namespace dftk {
+struct SphereTablesX;
+// kernel entry points of the register two-pass engine for one factor pair (fft_reg.cu)
+struct RegKernels {
+  int A, B, T;
+  const void *sphere_to_x, *y_backward, *z_apply, *z_to_cube, *z_from_cube, *z_density, *y_forward, *x_to_sphere;
+};
+const RegKernels* reg_kernels_for(int n);   // nullptr: use the generic Stockham engine
+void reg_set_attributes();
+}  // namespace dftk
 
 struct dftk_b200_grid {
   dftk_b200_ctx* ctx;
@@ -12,6 +24,7 @@ struct dftk_b200_grid {
   dftk::FftPlan px, py, pz;
   dftk::DevBuf<double> twx, twy, twz;
   int Lx, Ly, Lz;
+  const dftk::RegKernels *rx = nullptr, *ry = nullptr, *rz = nullptr;  // register engine per axis
 };
 
 struct dftk_b200_kblock {
@@ -20,8 +33,8 @@ struct dftk_b200_kblock {
   int spin;
   double kweight;
   dftk::SphereTablesHost Th;
-  dftk::SphereTables T;  // device view
-  dftk::DevBuf<int> d_col_start, d_col_cnt, d_slot_ix, d_slot_src, d_zlist, d_colmap;
+  dftk::SphereTablesX T;  // device view
+  dftk::DevBuf<int> d_col_start, d_col_cnt, d_slot_ix, d_slot_src, d_zlist, d_colmap, d_zc_of;
   dftk::DevBuf<double> kin;       // n_pw (may be empty)
   bool has_kin = false;
   dftk::DevBuf<dftk::cplx> P;     // n_pw x n_proj

@@ -14,6 +14,17 @@ def kinetic_energies(basis, kpt):
 
 
 # ------------------------------------------------------------------ local (local.jl:108-138)
+def structure_factor_cube(basis, r):
+    """exp(-2πi G·r) for every G of the cube (Julia linear order), built as an outer product of the three
+    per-axis phase vectors (identical values to cis2pi(-dot(G, r)), local.jl:127)."""
+    from .basis import G_axis
+    nx, ny, nz = basis.fft_size
+    ex = np.exp(-2j * math.pi * G_axis(nx) * r[0])
+    ey = np.exp(-2j * math.pi * G_axis(ny) * r[1])
+    ez = np.exp(-2j * math.pi * G_axis(nz) * r[2])
+    return (ez[:, None, None] * ey[None, :, None] * ex[None, None, :]).reshape(-1)
+
+
 def compute_local_potential(basis):
     model = basis.model
     pnorm = np.sqrt(np.sum(basis.G_cart ** 2, axis=1))
@@ -22,7 +33,7 @@ def compute_local_potential(basis):
         ff = model.atoms[group[0]].psp.eval_local_fourier(pnorm)
         for ia in group:
             r = model.positions[ia]
-            pot += np.exp(-2j * math.pi * (basis.G_all @ r)) * ff / math.sqrt(model.unit_cell_volume)
+            pot += structure_factor_cube(basis, r) * ff / math.sqrt(model.unit_cell_volume)
     pot = basis.enforce_real(pot)
     return basis.irfft_cube(pot)
 
@@ -136,7 +147,7 @@ def guess_density(basis, magnetic_moments=None):
         for ia, atom in enumerate(model.atoms):
             L = atom_decay_length(atom.n_elec_core, atom.n_elec_valence)
             ff = atom.charge_ionic * np.exp(-(pn * L) ** 2)
-            rho += (np.exp(-2j * math.pi * (basis.G_all @ model.positions[ia])) * ff
+            rho += (structure_factor_cube(basis, model.positions[ia]) * ff
                     * (coeffs[ia] / math.sqrt(model.unit_cell_volume)))
         return basis.irfft_cube(basis.enforce_real(rho))
 
@@ -267,10 +278,19 @@ class HamiltonianBlock:
         b, kpt = self.basis, self.kpt
         out = np.empty_like(psi)
         pot = self.Vtot * (b.fft_normalization * b.ifft_normalization)
-        for n in range(psi.shape[1]):
+
+        def one(n):
             pr = b.ifft_kpt(kpt, psi[:, n], normalize=False)
             pr *= pot
             out[:, n] = b.fft_kpt(kpt, pr, normalize=False)
+        workers = getattr(self, "workers", 1)
+        if workers > 1 and psi.shape[1] > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(workers) as ex:
+                list(ex.map(one, range(psi.shape[1])))
+        else:
+            for n in range(psi.shape[1]):
+                one(n)
         return out
 
     def matmul(self, psi):

@@ -103,3 +103,109 @@ int emu_fft_cube(int nx, int ny, int nz, double* data, int sign, int batch) {
   return 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Register two-pass engine (fft_reg.cuh) emulation: a few factor pairs are instantiated on the host.
+// ------------------------------------------------------------------------------------------------
+#include "../../dftk.jl_b200/csrc/fft_reg.cuh"
+#define EMU_PAIRS(X) X(3, 5) X(3, 6) X(4, 6) X(3, 9) X(4, 4) X(4, 5)
+static bool emu_pair(int n, int* A, int* B) {
+  *A = 0;
+#define PX(a, b) if (n == (a) * (b) && *A == 0) { *A = a; *B = b; }
+  EMU_PAIRS(PX)
+#undef PX
+  return *A != 0;
+}
+#define DISPATCH(n, CALL)                                   \
+  do {                                                      \
+    int A_, B_;                                             \
+    if (!emu_pair(n, &A_, &B_)) return -7;                  \
+    bool done_ = false;                                     \
+    EMU_PAIRS(CALL)                                         \
+    if (!done_) return -8;                                  \
+  } while (0)
+
+struct EmuR : Emu {
+  SphereTablesX TX;
+  EmuR(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, int nb) : Emu(nx, ny, nz, n_pw, mapping, nb) {
+    static_cast<SphereTables&>(TX) = T;
+    TX.zc_of = H.zc_of.data();
+    sm.resize(4 * (size_t)std::max(std::max(nx, ny), nz) * 33 + 64);
+  }
+  static int Lof(int A, int B) { return (A > B ? A : B) >= 8 ? 16 : 32; }
+  int to_planes(const cplx* psi, int nb) {
+#define CX(a, b) if (A_ == a && B_ == b) { int L = Lof(a, b), Lp = L + 1; done_ = true; \
+    for (int bb = 0; bb < nb; ++bb) for (int bx = 0; bx < (T.n_cols + L - 1) / L; ++bx) \
+      reg_sphere_to_x<a, b>(TX, tx(), psi, T.n_pw, W1.data(), L, Lp, sm.data(), Dim3i{bx, bb, 0}); }
+    DISPATCH(T.nx, CX);
+#undef CX
+#define CY(a, b) if (A_ == a && B_ == b) { int L = Lof(a, b), Lp = L + 1; done_ = true; \
+    for (int bb = 0; bb < nb; ++bb) for (int z = 0; z < T.n_zc; ++z) for (int bx = 0; bx < (T.nx + L - 1) / L; ++bx) \
+      reg_y_backward<a, b>(TX, ty(), W1.data(), W2.data(), L, Lp, sm.data(), Dim3i{bx, z, bb}); }
+    DISPATCH(T.ny, CY);
+#undef CY
+    return 0;
+  }
+  int from_planes(cplx* out, int nb, double scale, const double* kin, const cplx* psi, int acc) {
+#define CY(a, b) if (A_ == a && B_ == b) { int L = Lof(a, b), Lp = L + 1; done_ = true; \
+    for (int bb = 0; bb < nb; ++bb) for (int z = 0; z < T.n_zc; ++z) for (int bx = 0; bx < (T.nx + L - 1) / L; ++bx) \
+      reg_y_forward<a, b>(TX, ty(), W2.data(), W1.data(), L, Lp, sm.data(), Dim3i{bx, z, bb}); }
+    DISPATCH(T.ny, CY);
+#undef CY
+#define CX(a, b) if (A_ == a && B_ == b) { int L = Lof(a, b), Lp = L + 1; done_ = true; \
+    for (int bb = 0; bb < nb; ++bb) for (int bx = 0; bx < (T.n_cols + L - 1) / L; ++bx) \
+      reg_x_to_sphere<a, b>(TX, tx(), W1.data(), out, T.n_pw, scale, kin, psi, T.n_pw, acc, L, Lp, sm.data(), Dim3i{bx, bb, 0}); }
+    DISPATCH(T.nx, CX);
+#undef CX
+    return 0;
+  }
+};
+
+extern "C" {
+int emur_apply_local(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* psi, int nb,
+                     const double* Vscaled, const double* kin, double* out) {
+  EmuR e(nx, ny, nz, n_pw, mapping, nb);
+  int rc = e.to_planes((const cplx*)psi, nb);
+  if (rc) return rc;
+#define CZ(a, b) if (A_ == a && B_ == b) { int L = EmuR::Lof(a, b), Lp = L + 1; done_ = true; \
+  for (int bb = 0; bb < nb; ++bb) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx) \
+    reg_z_apply_potential<a, b>(e.TX, e.tz(), e.W2.data(), Vscaled, L, Lp, e.sm.data(), Dim3i{bx, y, bb}); }
+  DISPATCH(nz, CZ);
+#undef CZ
+  return e.from_planes((cplx*)out, nb, 1.0, kin, (const cplx*)psi, 0);
+}
+int emur_sphere_to_real(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* psi, int nb,
+                        double scale, double* cube) {
+  EmuR e(nx, ny, nz, n_pw, mapping, nb);
+  int rc = e.to_planes((const cplx*)psi, nb);
+  if (rc) return rc;
+#define CZ(a, b) if (A_ == a && B_ == b) { int L = EmuR::Lof(a, b), Lp = L + 1; done_ = true; \
+  for (int bb = 0; bb < nb; ++bb) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx) \
+    reg_z_to_cube<a, b>(e.TX, e.tz(), e.W2.data(), (cplx*)cube, scale, L, Lp, e.sm.data(), Dim3i{bx, y, bb}); }
+  DISPATCH(nz, CZ);
+#undef CZ
+  return 0;
+}
+int emur_real_to_sphere(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* cube, int nb,
+                        double scale, double* out) {
+  EmuR e(nx, ny, nz, n_pw, mapping, nb);
+#define CZ(a, b) if (A_ == a && B_ == b) { int L = EmuR::Lof(a, b), Lp = L + 1; done_ = true; \
+  for (int bb = 0; bb < nb; ++bb) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx) \
+    reg_z_from_cube<a, b>(e.TX, e.tz(), (const cplx*)cube, e.W2.data(), L, Lp, e.sm.data(), Dim3i{bx, y, bb}); }
+  DISPATCH(nz, CZ);
+#undef CZ
+  return e.from_planes((cplx*)out, nb, scale, nullptr, nullptr, 0);
+}
+int emur_density(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* psi, int nb,
+                 const double* wts, double* rho) {
+  EmuR e(nx, ny, nz, n_pw, mapping, nb);
+  int rc = e.to_planes((const cplx*)psi, nb);
+  if (rc) return rc;
+#define CZ(a, b) if (A_ == a && B_ == b) { int L = EmuR::Lof(a, b), Lp = L + 1; done_ = true; \
+  for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx) \
+    reg_z_density<a, b>(e.TX, e.tz(), e.W2.data(), wts, nb, rho, L, Lp, e.sm.data(), Dim3i{bx, y, 0}); }
+  DISPATCH(nz, CZ);
+#undef CZ
+  return 0;
+}
+}

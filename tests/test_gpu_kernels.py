@@ -147,3 +147,85 @@ def test_lobpcg_matches_oracle(si, backend):
         np.testing.assert_allclose(res2["λ"][:4], ref["λ"][:4], atol=1e-6)
     finally:
         ctx().set_option("gemm_backend", 0)
+
+
+@pytest.mark.parametrize("fft_size,Ecut", [((40, 45, 48), 30), ((32, 27, 36), 14), ((33, 40, 21), 10),
+                                           ((75, 64, 60), 60)])
+def test_fft_engines_agree_with_oracle(fft_size, Ecut):
+    """Register two-pass engine (default) and the generic Stockham engine against the oracle on mixed sizes
+    (33 and 21 have no factor pair -> those axes fall back to the generic engine inside the same pipeline)."""
+    import dftk_b200
+    from gpu_common import ctx, to_dev, rand_psi
+    from oracle.basis import Element, Model, PlaneWaveBasis
+    from silicon import LATTICE, POSITIONS
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, symmetries=False)
+    b = PlaneWaveBasis(m, Ecut, fft_size=fft_size, kcoords=[[0.25, -0.1, 0.4]], kweights=[1.0])
+    kpt = b.kpoints[0]
+    rng = np.random.default_rng(7)
+    V = rng.standard_normal(b.N)
+    kin = rng.random(kpt.n_G)
+    psi = rand_psi(kpt.n_G, 4, seed=8)
+    ref = np.stack([b.fft_kpt(kpt, b.ifft_kpt(kpt, p, False) * V / b.N, False) + kin * p for p in psi])
+    refc = np.stack([b.ifft_kpt(kpt, p) for p in psi])
+    w = np.array([1.0, 0.5, 2.0, 0.25])
+    refr = sum(w[i] * b.ifft_normalization ** 2 * np.abs(b.ifft_kpt(kpt, psi[i], False)) ** 2 for i in range(4))
+    for engine in (0, 1):
+        ctx().set_option("fft_engine", engine)
+        try:
+            grid = dftk_b200.FFTGrid(ctx(), fft_size, m.unit_cell_volume)
+            kb = dftk_b200.KBlock(grid, kpt.mapping, kin=kin)
+            kb.set_potential(to_dev(V))
+            d = to_dev(psi)
+            np.testing.assert_allclose(kb.apply_terms(d, 3).cpu().numpy(), ref, atol=1e-12 * np.abs(ref).max())
+            cube = kb.sphere_to_real(d)
+            np.testing.assert_allclose(cube.cpu().numpy(), refc, atol=1e-12 * np.abs(refc).max())
+            np.testing.assert_allclose(kb.real_to_sphere(cube).cpu().numpy(), psi, atol=1e-12)
+            rho = torch.zeros(b.N, dtype=torch.float64, device=ctx().device)
+            kb.density_accumulate(d, w, rho)
+            np.testing.assert_allclose(rho.cpu().numpy(), refr, atol=1e-12 * refr.max())
+        finally:
+            ctx().set_option("fft_engine", 0)
+
+
+def test_full_size_properties_192():
+    """BASELINE full-size grid (192^3, the C3 cell): size-independent properties instead of an oracle run --
+    round trip, linearity, Hermiticity <phi|H psi> = <H phi|psi>, Parseval, density normalisation."""
+    import dftk_b200
+    from gpu_common import ctx
+    c = ctx()
+    dev = c.device
+    A = 10.26 / 2
+    lat = 5 * np.array([[0, A, A], [A, 0, A], [A, A, 0]])
+    recip = 2 * np.pi * np.linalg.inv(lat.T)
+    n = 192
+    g1 = torch.as_tensor(np.array(list(range(0, 96)) + list(range(-96, 0))), device=dev, dtype=torch.float64)
+    Z, Y, X = torch.meshgrid(g1, g1, g1, indexing="ij")
+    G = torch.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], 1)
+    p = G @ torch.as_tensor(recip.T, device=dev)
+    kin_all = (p * p).sum(1) / 2
+    mapping = torch.nonzero(kin_all <= 30.0).reshape(-1)
+    assert mapping.numel() == 264859                               # SURVEY §8 table, config C3
+    kin = kin_all[mapping].contiguous()
+    vol = abs(np.linalg.det(lat))
+    grid = dftk_b200.FFTGrid(c, (n, n, n), vol)
+    kb = dftk_b200.KBlock(grid, mapping.cpu().numpy(), kin=kin)
+    V = torch.cos(torch.arange(n ** 3, device=dev, dtype=torch.float64) * 1e-3) - 0.3
+    kb.set_potential(V)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    psi = torch.view_as_complex(torch.randn(6, mapping.numel(), 2, generator=gen, device=dev, dtype=torch.float64))
+    psi = psi / psi.norm(dim=1, keepdim=True)
+    cube = kb.sphere_to_real(psi)
+    # Parseval: sum |psi(r)|^2 dvol = 1
+    assert (cube.abs().pow(2).sum(dim=1) * (vol / n ** 3) - 1).abs().max().item() < 1e-12
+    assert (kb.real_to_sphere(cube) - psi).abs().max().item() < 1e-13
+    del cube
+    H = kb.apply_h(psi)
+    a, b = 0.3 - 1.2j, -0.7 + 0.4j
+    Hlin = kb.apply_h((a * psi[0] + b * psi[1])[None, :].contiguous())[0]
+    assert (Hlin - (a * H[0] + b * H[1])).abs().max().item() < 1e-12 * H.abs().max().item()
+    Gm = psi.conj() @ H.T
+    assert (Gm - Gm.conj().T).abs().max().item() < 1e-12 * Gm.abs().max().item()
+    rho = torch.zeros(n ** 3, dtype=torch.float64, device=dev)
+    kb.density_accumulate(psi, np.full(6, 2.0), rho)
+    assert abs(rho.sum().item() * (vol / n ** 3) - 12.0) < 1e-10
+    assert rho.min().item() >= 0.0

@@ -26,7 +26,7 @@ def test_energies_guess_density_golden():
     assert E["Hartree"] == pytest.approx(0.3527293727197568, abs=5e-8)
     assert E["Xc"] == pytest.approx(-2.3033165870558165, abs=5e-8)
     res = dftk.diagonalize_all_kblocks(dftk.lobpcg_hyper, ham, 8, tol=1e-9)
-    assert res["converged"]
+    assert all(np.max(r[:4]) < 1e-8 for r in res["residual_norms"])
     occ = [np.array([2., 2, 2, 2, 0, 0, 0, 0]) for _ in basis.kpoints]
     rho = dftk.compute_density(basis, res["X"], occ)
     E, _ = dftk.energy_hamiltonian(basis, res["X"], occ, rho=rho)

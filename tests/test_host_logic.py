@@ -1,0 +1,156 @@
+"""CPU tests of the product's host-side logic (no kernels): models, symmetries, k-grids, sharding,
+band/tolerance heuristics, Anderson, occupations, and the world_size-2 gloo path of the k-point comm."""
+import os
+import math
+import numpy as np
+import pytest
+import torch
+
+from silicon import LATTICE, POSITIONS
+
+
+def test_model_symmetries_and_kgrid():
+    import dftk_b200 as dftk
+    from dftk_b200.basis import irreducible_kcoords
+    Si = dftk.ElementPsp("Si")
+    m = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA())
+    assert len(m.symmetries) == 48 and m.symmetries[0].isone()
+    assert m.n_electrons == 8 and m.filled_occupation == 2 and m.n_spin_components == 1
+    assert m.term_types == ["Kinetic", "AtomicLocal", "AtomicNonlocal", "Ewald", "PspCorrection", "Hartree", "Xc"]
+    # silicon 3x3x3: 4 irreducible points with weights 1,8,6,12 /27 (test/testcases.jl:24-28)
+    k, w = irreducible_kcoords(dftk.MonkhorstPack((3, 3, 3)), m.symmetries)
+    assert sorted(round(x * 27) for x in w) == [1, 6, 8, 12]
+    k, w = irreducible_kcoords(dftk.MonkhorstPack((8, 8, 8)), m.symmetries)
+    assert len(k) == 29 and abs(sum(w) - 1) < 1e-14
+    m2 = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), temperature=0.01)
+    assert m2.term_types[-1] == "Entropy" and m2.smearing == "FermiDirac"
+    with pytest.raises(ValueError):
+        dftk.Model(LATTICE, [Si], POSITIONS)
+
+
+def test_fft_size_and_reference_kgrid_order():
+    import dftk_b200 as dftk
+    m = dftk.Model(LATTICE)
+    for E, n in [(3, 15), (5, 18), (15, 27), (25, 36), (30, 40)]:       # test/compute_fft_size.jl:6-12
+        assert dftk.compute_fft_size(m, E) == (n, n, n)
+    ks = dftk.MonkhorstPack((1, 2, 3), kshift=(0, 0.5, 0)).reducible_kcoords()
+    assert len(ks) == 6 and np.allclose(ks[0], [0, 0.25, -1 / 3])
+
+
+def test_psp_parser_and_values():
+    import dftk_b200 as dftk
+    text = ("Si GTH-PADE-q4 GTH-LDA-q4\n    2    2\n     0.44000000    1    -7.33610297\n    2\n"
+            "     0.42273813    2     5.90692831    -1.26189397\n"
+            "                                        3.25819622\n     0.48427842    1     2.72701346\n")
+    p, q = dftk.parse_hgh(text), dftk.load_psp("Si", "lda")
+    assert p.Zion == q.Zion == 4 and p.rp == q.rp and all(np.array_equal(a, b) for a, b in zip(p.h, q.h))
+    # test/PspHgh.jl:41-84
+    v = q.eval_psp_local_fourier(torch.tensor([math.sqrt(0.05), 10.0], dtype=torch.float64)) / (4 * math.pi)
+    np.testing.assert_allclose(v.numpy(), [-80.39317320182417, -5.1468909215285576e-5], rtol=1e-10)
+    pn = torch.tensor(np.sqrt([0, 0.01, 0.1, 0.3, 1, 10]))
+    np.testing.assert_allclose(q.eval_psp_projector_fourier(2, 0, pn).numpy(),
+                               [10.074536712471094, 10.059542796942894, 9.925438587886482,
+                                9.632787375976731, 8.664551612201326, 1.666783598475508], rtol=1e-10)
+    assert q.count_n_proj() == 5
+
+
+def test_split_evenly_and_padding():
+    from dftk_b200.parallel import split_evenly, pad_kpoints_for_ranks
+    assert split_evenly(range(10), 3) == [[0, 1, 2, 3], [4, 5, 6], [7, 8, 9]]      # test/split_evenly.jl
+    assert split_evenly(range(4), 4) == [[0], [1], [2], [3]]
+    k, w = pad_kpoints_for_ranks([[0, 0, 0], [0.5, 0, 0]], [0.25, 0.75], 4)
+    assert len(k) == 4 and abs(sum(w) - 1) < 1e-15 and max(w) <= 0.375 + 1e-15
+
+
+def test_adaptive_bands_and_diagtol():
+    import dftk_b200 as dftk
+    Si = dftk.ElementPsp("Si")
+    m = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA())
+    ab = dftk.AdaptiveBands(m)
+    assert (ab.n_bands_converge, ab.n_bands_compute) == (4, 7)                  # 7 / 4
+    assert ab.determine_n_bands(None, None, None) == (5, 7)                     # first step converges 5
+    occ = [np.array([2, 2, 2, 2, 0, 0, 0.0])]
+    eig = [np.array([-0.2, 0.1, 0.1, 0.1, 0.3, 0.3, 0.4])]
+    assert ab.determine_n_bands(occ, eig, None) == (4, 7)
+    dt = dftk.AdaptiveDiagtol()
+    assert dt.determine_diagtol(dict(n_iter=1, history_drho=[])) == 0.025
+    assert dt.determine_diagtol(dict(n_iter=3, history_drho=[0.2, 0.01])) == pytest.approx(0.002)
+    assert dt.determine_diagtol(dict(n_iter=9, history_drho=[1e-20])) == 100 * np.finfo(float).eps
+
+
+def test_anderson_converges_linear_fixed_point():
+    # reference: test/anderson.jl -- Anderson solves a linear fixed-point problem in <= dim+1 steps
+    import dftk_b200 as dftk
+    torch.manual_seed(0)
+    n = 6
+    A = torch.randn(n, n, dtype=torch.float64) * 0.3
+    b = torch.randn(n, dtype=torch.float64)
+    f = lambda x: A @ x + b
+    xstar = torch.linalg.solve(torch.eye(n, dtype=torch.float64) - A, b)
+    acc = dftk.AndersonAcceleration(m=10)
+    x = torch.zeros(n, dtype=torch.float64)
+    for _ in range(n + 2):
+        x = acc(x, 0.8, f(x) - x)
+    assert (x - xstar).abs().max().item() < 1e-9
+
+
+class _FakeBasis:
+    def __init__(self, model, weights, comm):
+        self.model, self.kweights, self.comm_kpts = model, weights, comm
+
+
+def test_occupation_insulator_and_metal():
+    import dftk_b200 as dftk
+    from dftk_b200.occupation import compute_occupation
+    Si = dftk.ElementPsp("Si")
+    m = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA())
+    b = _FakeBasis(m, [0.5, 0.5], dftk.KpointComm())
+    eig = [np.array([-0.2, 0.0, 0.1, 0.2, 0.5, 0.6]), np.array([-0.1, 0.0, 0.1, 0.25, 0.45, 0.7])]
+    occ, eF = compute_occupation(b, eig)
+    assert eF == pytest.approx((0.25 + 0.45) / 2) and all(np.array_equal(o, [2, 2, 2, 2, 0, 0]) for o in occ)
+    mm = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), temperature=0.02)
+    bm = _FakeBasis(mm, [0.5, 0.5], dftk.KpointComm())
+    occ, eF = compute_occupation(bm, eig)
+    assert abs(sum(w * o.sum() for w, o in zip(bm.kweights, occ)) - 8) < 1e-10
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import dftk_b200 as dftk
+    from dftk_b200.occupation import compute_occupation
+    comm = dftk.KpointComm.from_torch_distributed(with_nccl_id=False)
+    assert comm.sum(rank + 1.0) == 3.0 and comm.max(rank) == 1 and comm.min(rank) == 0
+    assert comm.bcast_object("x" if rank == 0 else None) == "x"
+    Si = dftk.ElementPsp("Si")
+    mm = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), temperature=0.02)
+    eig = [np.array([-0.2, 0.0, 0.1, 0.2, 0.5, 0.6]), np.array([-0.1, 0.0, 0.1, 0.25, 0.45, 0.7])]
+    # each rank owns one of the two k-points: the Fermi level must equal the single-process result bit for bit
+    b = _FakeBasis(mm, [0.5], comm)
+    occ, eF = compute_occupation(b, [eig[rank]])
+    q.put((rank, eF, occ[0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_kpoint_comm_gloo_world2():
+    import torch.multiprocessing as mp
+    import dftk_b200 as dftk
+    from dftk_b200.occupation import compute_occupation
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    Si = dftk.ElementPsp("Si")
+    mm = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), temperature=0.02)
+    eig = [np.array([-0.2, 0.0, 0.1, 0.2, 0.5, 0.6]), np.array([-0.1, 0.0, 0.1, 0.25, 0.45, 0.7])]
+    occ, eF = compute_occupation(_FakeBasis(mm, [0.5, 0.5], dftk.KpointComm()), eig)
+    assert out[0][1] == eF and out[1][1] == eF                      # bit-identical Fermi level on every rank
+    assert out[0][2] == occ[0].tolist() and out[1][2] == occ[1].tolist()

@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "hostemu", "libhostemu.so")
 def emu():
     src = os.path.join(HERE, "hostemu", "emu.cu")
     csrc = os.path.join(HERE, "..", "dftk.jl_b200", "csrc")
-    deps = [src, os.path.join(csrc, "fft_core.cuh"), os.path.join(csrc, "fft_plan.h")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_radix_gen.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
                                "-Wno-deprecated-gpu-targets", "-o", SO, src])
@@ -33,9 +33,19 @@ def _basis(fft_size, Ecut, k):
     return PlaneWaveBasis(m, Ecut, fft_size=fft_size, kcoords=[k], kweights=[1.0])
 
 
-@pytest.mark.parametrize("fft_size,Ecut", [((15, 15, 15), 5), ((12, 15, 18), 4), ((17, 20, 21), 6),
-                                           ((27, 27, 27), 15), ((24, 24, 24), 9)])
-def test_emulated_pipeline(emu, fft_size, Ecut):
+@pytest.mark.parametrize("fft_size,Ecut,prefix", [((15, 15, 15), 5, "emu"), ((12, 15, 18), 4, "emu"),
+                                                  ((17, 20, 21), 6, "emu"), ((27, 27, 27), 15, "emu"),
+                                                  ((24, 24, 24), 9, "emu"),
+                                                  # register two-pass engine (fft_reg.cuh)
+                                                  ((15, 18, 24), 5, "emur"), ((27, 27, 27), 15, "emur"),
+                                                  ((24, 16, 20), 6, "emur"), ((20, 27, 15), 5, "emur")])
+def test_emulated_pipeline(emu, fft_size, Ecut, prefix):
+    lib = emu
+
+    class _E:
+        def __getattr__(self, name):
+            return getattr(lib, name.replace("emu_", prefix + "_"))
+    emu = _E()
     b = _basis(fft_size, Ecut, [0.1, -0.2, 0.3])
     kpt = b.kpoints[0]
     nx, ny, nz = fft_size
@@ -49,7 +59,7 @@ def test_emulated_pipeline(emu, fft_size, Ecut):
     Vs = np.ascontiguousarray(V / b.N)
     # H psi local + kinetic
     out = np.zeros_like(psi)
-    emu.emu_apply_local(nx, ny, nz, npw, _p(mapping), _p(psi), nb, _p(Vs), _p(kin), _p(out))
+    assert emu.emu_apply_local(nx, ny, nz, npw, _p(mapping), _p(psi), nb, _p(Vs), _p(kin), _p(out)) == 0
     ref = np.stack([b.fft_kpt(kpt, b.ifft_kpt(kpt, psi[i], False) * V / b.N, False) + kin * psi[i]
                     for i in range(nb)])
     np.testing.assert_allclose(out, ref, atol=1e-11 * np.abs(ref).max())
