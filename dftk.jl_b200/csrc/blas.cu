@@ -44,7 +44,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 #define GT_N 32
 __global__ void __launch_bounds__(GEMM_THREADS)
 k_zgemm_cn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, int64_t ldb,
-           cplx* __restrict__ ws, int64_t m, int64_t n, int64_t K, int64_t k_per_split) {
+           cplx* __restrict__ ws, int64_t m, int64_t n, int64_t K, int64_t k_per_split, int upper_only) {
+  // Hermitian results (X'X, X'AX): tiles strictly below the diagonal are never read by the callers
+  if (upper_only && (int64_t)blockIdx.x * GT_M >= (int64_t)blockIdx.y * GT_N + GT_N) return;
   extern __shared__ __align__(16) double smem_d[];
   double* As = smem_d;                                   // [STAGES][GT_M][LDK]
   double* Bs = smem_d + GEMM_STAGES * GT_M * LDK;        // [STAGES][GT_N][LDK]
@@ -159,7 +161,8 @@ k_zgemm_nn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, 
   double* As = smem_d;                                   // [STAGES][BKC][LDA_U]
   double* Bs = smem_d + GEMM_STAGES * BKC * LDA_U;       // [STAGES][UT_N][LDK]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * UT_M, j0 = (int64_t)blockIdx.y * UT_N;
+  // blockIdx.x = column tile (fastest): CTAs sharing one A row panel run together and hit it in L2
+  const int64_t r0 = (int64_t)blockIdx.y * UT_M, j0 = (int64_t)blockIdx.x * UT_N;
   const int nkt = (int)((m + BKC - 1) / BKC);
 
   auto load_tile = [&](int kt, int slot) {
@@ -350,7 +353,7 @@ void scale_kin_add(dftk_b200_ctx* ctx, const cplx* psi, cplx* hpsi, const double
 //   transA == 2: A is (k x m), B is (k x n), C is (m x n)        [Gram type, k large]
 //   transA == 0: A is (m x k), B is (k x n), C is (m x n)        [update type, m large]
 void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx alpha, const cplx* A,
-           int64_t lda, const cplx* B, int64_t ldb, cplx beta, cplx* C, int64_t ldc) {
+           int64_t lda, const cplx* B, int64_t ldb, cplx beta, cplx* C, int64_t ldc, bool upper_only) {
   if (m == 0 || n == 0) return;
   REQUIRE(transA == 0 || transA == 2, "zgemm: transA must be 0 (N) or 2 (C)");
   if (ctx->gemm_backend == 1) {
@@ -369,19 +372,33 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
   }
   if (transA == 2) {
     int64_t tiles = ((m + GT_M - 1) / GT_M) * ((n + GT_N - 1) / GT_N);
-    int64_t want = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
-    int64_t max_split = (k + 8 * BKC - 1) / (8 * BKC);
-    int64_t nsplit = std::max<int64_t>(1, std::min(want, max_split));
+    // split K so that the CTA count fills whole waves (3 resident CTAs per SM) at least twice over
+    const int64_t slots = 3 * (int64_t)ctx->sm_count;
+    int64_t max_split = std::min<int64_t>(64, (k + 8 * BKC - 1) / (8 * BKC));
+    int64_t nsplit = 1;
+    double best = -1.0;
+    for (int64_t sp = 1; sp <= max_split; ++sp) {
+      int64_t total = tiles * sp;
+      double eff = (double)total / (double)(((total + slots - 1) / slots) * slots);
+      if (total < 2 * slots) eff *= 0.5 + 0.25 * (double)total / (double)slots;   // prefer >= 2 waves
+      eff -= 0.002 * sp;                                                          // mild penalty: reduce pass
+      if (eff > best) {
+        best = eff;
+        nsplit = sp;
+      }
+    }
     int64_t kps = (k + nsplit - 1) / nsplit;
     kps = ((kps + BKC - 1) / BKC) * BKC;
     nsplit = (k + kps - 1) / kps;
     cplx* ws = (cplx*)ctx->gemm_ws.ensure((size_t)nsplit * m * n * sizeof(cplx));
     dim3 grid((unsigned)((m + GT_M - 1) / GT_M), (unsigned)((n + GT_N - 1) / GT_N), (unsigned)nsplit);
-    LAUNCH(ctx, k_zgemm_cn, grid, GEMM_THREADS, smem_cn(), A, lda, B, ldb, ws, m, n, k, kps);
+    LAUNCH(ctx, k_zgemm_cn, grid, GEMM_THREADS, smem_cn(), A, lda, B, ldb, ws, m, n, k, kps,
+           (upper_only && m == n) ? 1 : 0);
     LAUNCH(ctx, k_reduce_partials, (unsigned)((m * n + 255) / 256), 256, 0, (const cplx*)ws, (int)nsplit, m,
            n, alpha, beta, C, ldc);
   } else {
-    dim3 grid((unsigned)((m + UT_M - 1) / UT_M), (unsigned)((n + UT_N - 1) / UT_N));
+    REQUIRE((m + UT_M - 1) / UT_M <= 65535, "zgemm: more than 4.19M rows are not supported by the update kernel grid");
+    dim3 grid((unsigned)((n + UT_N - 1) / UT_N), (unsigned)((m + UT_M - 1) / UT_M));
     LAUNCH(ctx, k_zgemm_nn, grid, GEMM_THREADS, smem_nn(), A, lda, B, ldb, C, ldc, m, n, k, alpha, beta);
   }
 }

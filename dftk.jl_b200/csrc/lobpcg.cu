@@ -266,7 +266,7 @@ struct Lobpcg {
       for (size_t ia = 0; ia < A.size(); ++ia) {
         if (!(upper_only && ib < ia))
           zgemm(ctx, 2, A[ia].cols, B[ib].cols, A[ia].rows, one, A[ia].p, A[ia].ld, B[ib].p, B[ib].ld,
-                zero, C + orow + ldc * oc, ldc);
+                zero, C + orow + ldc * oc, ldc, /*upper tiles only on diagonal blocks*/ upper_only && ia == ib);
         orow += A[ia].cols;
       }
       oc += B[ib].cols;

@@ -66,7 +66,7 @@ void kb_density_accumulate(dftk_b200_kblock* kb, const cplx* psi, const double* 
 void fft_set_attributes();
 // blas.cu
 void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx alpha, const cplx* A,
-           int64_t lda, const cplx* B, int64_t ldb, cplx beta, cplx* C, int64_t ldc);
+           int64_t lda, const cplx* B, int64_t ldb, cplx beta, cplx* C, int64_t ldc, bool upper_only = false);
 void blas_set_attributes();
 void kb_apply_nonlocal(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_t n_bands);
 void columnwise_dots(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,

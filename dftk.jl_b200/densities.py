@@ -31,8 +31,8 @@ def symmetrize_rho(basis, rho):
         tabs = []
         Gf = basis.G_vectors.to(torch.float64)
         for s in syms:
-            invS = torch.as_tensor(np.rint(np.linalg.inv(s.S)).astype(np.int64), device=rho.device)
-            idx = basis.index_G_vectors(basis.G_vectors @ invS.T)
+            invS = torch.as_tensor(np.rint(np.linalg.inv(s.S)), device=rho.device, dtype=torch.float64)
+            idx = basis.index_G_vectors((Gf @ invS.T).round().to(torch.int64))   # (no int64 matmul on CUDA)
             phase = None
             if np.any(np.abs(s.tau) > 1e-12):
                 ph = -2 * math.pi * (Gf @ torch.as_tensor(s.tau, device=rho.device))
