@@ -31,7 +31,6 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 #define GEMM_THREADS 128
-#define GEMM_STAGES 3
 #define BKC 16              // complex k per stage (32 real)
 #define LDK (2 * BKC + 4)   // doubles per k-major smem row; LDK % 16 == 4 => conflict-free fragments
 
@@ -42,6 +41,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // ------------------------------------------------------------------------------------------------
 #define GT_M 64
 #define GT_N 32
+template <int GEMM_STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 k_zgemm_cn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, int64_t ldb,
            cplx* __restrict__ ws, int64_t m, int64_t n, int64_t K, int64_t k_per_split, int upper_only) {
@@ -154,16 +154,20 @@ __global__ void k_reduce_partials(const cplx* __restrict__ ws, int nsplit, int64
 #define UT_M 64                 // complex rows
 #define UT_N 32
 #define LDA_U (2 * UT_M + 4)    // doubles per inner-index row of the A tile (132 % 16 == 4)
+template <int GEMM_STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 k_zgemm_nn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, int64_t ldb,
-           cplx* __restrict__ C, int64_t ldc, int64_t Krows, int64_t n, int64_t m, cplx alpha, cplx beta) {
+           cplx* __restrict__ C, int64_t ldc, int64_t Krows, int64_t n, int64_t m, cplx alpha, cplx beta,
+           int b_upper) {
   extern __shared__ __align__(16) double smem_d[];
   double* As = smem_d;                                   // [STAGES][BKC][LDA_U]
   double* Bs = smem_d + GEMM_STAGES * BKC * LDA_U;       // [STAGES][UT_N][LDK]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // blockIdx.x = column tile (fastest): CTAs sharing one A row panel run together and hit it in L2
   const int64_t r0 = (int64_t)blockIdx.y * UT_M, j0 = (int64_t)blockIdx.x * UT_N;
-  const int nkt = (int)((m + BKC - 1) / BKC);
+  // B upper triangular (X * inv(R), rmul! with an UpperTriangular): rows i > j of column j are zero
+  const int64_t m_eff = b_upper ? min(m, j0 + UT_N) : m;
+  const int nkt = (int)((m_eff + BKC - 1) / BKC);
 
   auto load_tile = [&](int kt, int slot) {
     const int64_t i0 = (int64_t)kt * BKC;
@@ -251,8 +255,8 @@ k_zgemm_nn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, 
       }
 }
 
-static size_t smem_cn() { return (size_t)GEMM_STAGES * (GT_M + GT_N) * LDK * sizeof(double); }
-static size_t smem_nn() { return (size_t)GEMM_STAGES * (BKC * LDA_U + UT_N * LDK) * sizeof(double); }
+static size_t smem_cn(int st) { return (size_t)st * (GT_M + GT_N) * LDK * sizeof(double); }
+static size_t smem_nn(int st) { return (size_t)st * (BKC * LDA_U + UT_N * LDK) * sizeof(double); }
 
 // ---------------------------------------------------------------- elementwise / reduction kernels
 __global__ void k_columnwise_dots(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B,
@@ -326,8 +330,10 @@ __global__ void k_scale_kin_add(const cplx* __restrict__ psi, cplx* __restrict__
 }
 
 void blas_set_attributes() {
-  CUDA_CHECK(cudaFuncSetAttribute(k_zgemm_cn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cn()));
-  CUDA_CHECK(cudaFuncSetAttribute(k_zgemm_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nn()));
+  CUDA_CHECK(cudaFuncSetAttribute(k_zgemm_cn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cn(2)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_zgemm_nn<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nn(2)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_zgemm_cn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cn(3)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_zgemm_nn<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nn(3)));
 }
 
 void columnwise_dots(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
@@ -373,7 +379,7 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
   if (transA == 2) {
     int64_t tiles = ((m + GT_M - 1) / GT_M) * ((n + GT_N - 1) / GT_N);
     // split K so that the CTA count fills whole waves (3 resident CTAs per SM) at least twice over
-    const int64_t slots = 3 * (int64_t)ctx->sm_count;
+    const int64_t slots = (ctx->gemm_stages == 3 ? 2 : 4) * (int64_t)ctx->sm_count;   // resident CTAs
     int64_t max_split = std::min<int64_t>(64, (k + 8 * BKC - 1) / (8 * BKC));
     int64_t nsplit = 1;
     double best = -1.0;
@@ -392,14 +398,23 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
     nsplit = (k + kps - 1) / kps;
     cplx* ws = (cplx*)ctx->gemm_ws.ensure((size_t)nsplit * m * n * sizeof(cplx));
     dim3 grid((unsigned)((m + GT_M - 1) / GT_M), (unsigned)((n + GT_N - 1) / GT_N), (unsigned)nsplit);
-    LAUNCH(ctx, k_zgemm_cn, grid, GEMM_THREADS, smem_cn(), A, lda, B, ldb, ws, m, n, k, kps,
-           (upper_only && m == n) ? 1 : 0);
+    if (ctx->gemm_stages == 3)
+      LAUNCH(ctx, k_zgemm_cn<3>, grid, GEMM_THREADS, smem_cn(3), A, lda, B, ldb, ws, m, n, k, kps,
+             (upper_only && m == n) ? 1 : 0);
+    else
+      LAUNCH(ctx, k_zgemm_cn<2>, grid, GEMM_THREADS, smem_cn(2), A, lda, B, ldb, ws, m, n, k, kps,
+             (upper_only && m == n) ? 1 : 0);
     LAUNCH(ctx, k_reduce_partials, (unsigned)((m * n + 255) / 256), 256, 0, (const cplx*)ws, (int)nsplit, m,
            n, alpha, beta, C, ldc);
   } else {
     REQUIRE((m + UT_M - 1) / UT_M <= 65535, "zgemm: more than 4.19M rows are not supported by the update kernel grid");
     dim3 grid((unsigned)((n + UT_N - 1) / UT_N), (unsigned)((m + UT_M - 1) / UT_M));
-    LAUNCH(ctx, k_zgemm_nn, grid, GEMM_THREADS, smem_nn(), A, lda, B, ldb, C, ldc, m, n, k, alpha, beta);
+    if (ctx->gemm_stages == 3)
+      LAUNCH(ctx, k_zgemm_nn<3>, grid, GEMM_THREADS, smem_nn(3), A, lda, B, ldb, C, ldc, m, n, k, alpha, beta,
+             (upper_only && k == n) ? 1 : 0);
+    else
+      LAUNCH(ctx, k_zgemm_nn<2>, grid, GEMM_THREADS, smem_nn(2), A, lda, B, ldb, C, ldc, m, n, k, alpha, beta,
+             (upper_only && k == n) ? 1 : 0);
   }
 }
 

@@ -115,8 +115,13 @@ void reg_set_attributes() {
                           k.y_forward, k.x_to_sphere})
       CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
 }
-static inline int reg_L(const RegKernels* k) { return k->T >= 8 ? 16 : 32; }
+static int g_fft_lines = 0;
+static inline int reg_L(const RegKernels* k) {
+  if (g_fft_lines > 0 && g_fft_lines * k->T <= 32 * k->T) return g_fft_lines;
+  return k->T >= 8 ? 16 : 32;
+}
 static inline size_t reg_smem(const RegKernels* k) { return 2 * (size_t)k->A * k->B * (reg_L(k) + 1) * sizeof(cplx); }
+void reg_set_lines(int L) { g_fft_lines = (L == 8 || L == 16 || L == 32) ? L : 0; }
 static void launch_ptr(dftk_b200_ctx* ctx, const void* f, dim3 grid, int threads, size_t smem, void** args) {
   CUDA_CHECK(cudaLaunchKernel(f, grid, dim3(threads), args, smem, ctx->stream));
   ctx->launches++;
@@ -250,7 +255,8 @@ void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, i
       cplx* W2 = kb->W2.p;
       const double* V = kb->V.p;
       void* args[] = {&kb->T, &tw, &W2, &V, &L, &Lp};
-      launch_ptr(ctx, g->rz->z_apply, dim3(cdiv(g->nx, L), g->ny, nb), L * g->rz->T, reg_smem(g->rz), args);
+      // single (aliased) exchange buffer on the device, cf. DFTK_Z_ALIAS in fft_reg.cuh
+      launch_ptr(ctx, g->rz->z_apply, dim3(cdiv(g->nx, L), g->ny, nb), L * g->rz->T, reg_smem(g->rz) / 2, args);
     } else {
       int L = g->Lz, Lp = L | 1;
       LAUNCH(ctx, k_z_apply_potential, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L),

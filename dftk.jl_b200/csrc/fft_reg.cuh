@@ -50,13 +50,30 @@ HD void pass2_load(cplx* X, int c, int line, const cplx* __restrict__ Sbuf, int 
 }
 
 // ---------------------------------------------------------------------------------------------- z stages
+// compute-only half of pass 1 (the caller stores Y[c] to S[(c*B + q)])
+template <int A, int B, int S>
+HD void pass1_compute(const cplx* x, int q, const cplx* __restrict__ tw, cplx* Y) {
+  dft_r<A, S>(x, Y);
+#pragma unroll
+  for (int c = 1; c < A; ++c)
+    if (q != 0) Y[c] = cmul(Y[c], twiddle(tw, q * c, S));
+}
+
+// On the device the two exchange buffers of the fused z stage alias (one buffer, an extra barrier between the
+// last read and the first write), halving the shared-memory footprint; the host emulation keeps two buffers.
+#if defined(__CUDA_ARCH__)
+#define DFTK_Z_ALIAS 1
+#else
+#define DFTK_Z_ALIAS 0
+#endif
+
 template <int A, int B>
 HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ tw, cplx* __restrict__ W2,
                               const double* __restrict__ V, int L, int Lp, cplx* sm, Dim3i bid) {
   constexpr int n = A * B, TT = RegPair<A, B>::T;
   const int nx = T.nx, ny = T.ny;
   cplx* bufA = sm;
-  cplx* bufB = sm + (size_t)n * Lp;
+  cplx* bufB = DFTK_Z_ALIAS ? sm : sm + (size_t)n * Lp;
   const int x0 = bid.x * L, y = bid.y;
   cplx* w2 = W2 + (size_t)bid.z * T.n_zc * ny * nx;
   TLOOP(t, L * TT) {
@@ -74,6 +91,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
   TSYNC();
   TLOOP(t, L * TT) {
     const int line = t % L, p = t / L, x = x0 + line;
+    cplx Y[B];
     if (p < A) {
       cplx X[B];
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
@@ -83,7 +101,14 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
         X[d] = cscale(X[d], vv);
       }
       // forward transform of the elements p + A*d: pass 1 with the roles of A and B swapped
-      pass1_store<B, A, -1>(X, p, line, bufB, Lp, tw);
+      pass1_compute<B, A, -1>(X, p, tw, Y);
+    }
+#if DFTK_Z_ALIAS
+    __syncthreads();   // every thread of the CTA runs this body exactly once (blockDim == L*TT)
+#endif
+    if (p < A) {
+#pragma unroll
+      for (int c = 0; c < B; ++c) bufB[(c * A + p) * Lp + line] = Y[c];
     }
   }
   TSYNC();

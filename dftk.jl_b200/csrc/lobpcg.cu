@@ -324,7 +324,8 @@ struct Lobpcg {
       }
       if (!ok) throw Error(DFTK_B200_ENUM, "ortho!: Cholesky failing badly (SVD fallback not implemented)");
       // X <- X * invR   (rmul!(X, invR))
-      zgemm(ctx, 0, X.rows, n, n, make_double2(1, 0), X.p, X.ld, invR, S3, make_double2(0, 0), tmp, ldtmp);
+      zgemm(ctx, 0, X.rows, n, n, make_double2(1, 0), X.p, X.ld, invR, S3, make_double2(0, 0), tmp, ldtmp,
+            /*invR is upper triangular*/ true);
       copy2d(X, Mat{tmp, ldtmp, X.rows, n});
       double norminvR = normest(invR, S3, n);
       growth *= norminvR;

@@ -13,6 +13,7 @@ struct RegKernels {
 };
 const RegKernels* reg_kernels_for(int n);   // nullptr: use the generic Stockham engine
 void reg_set_attributes();
+void reg_set_lines(int L);
 }  // namespace dftk
 
 struct dftk_b200_grid {
@@ -67,6 +68,8 @@ void fft_set_attributes();
 // blas.cu
 void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx alpha, const cplx* A,
            int64_t lda, const cplx* B, int64_t ldb, cplx beta, cplx* C, int64_t ldc, bool upper_only = false);
+// upper_only: transA == 2 -> only tiles on/above the diagonal are computed (Hermitian result);
+//             transA == 0 -> B is upper triangular (trmm-like: half the flops)
 void blas_set_attributes();
 void kb_apply_nonlocal(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_t n_bands);
 void columnwise_dots(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,

@@ -55,16 +55,20 @@ def timeit(fn, n=3, warm=1):
 
 
 res = {}
-for chunk in (8, 16, 32, 64):
-    ctx.set_option("band_chunk", chunk)
-    nb = 128
-    t, _ = timeit(lambda: kb.apply_terms(psi[:nb], 3, out=out[:nb]))
-    bytes_alg = (72 * 192 ** 3 + 40 * npw) * nb
-    res[f"local_kin_chunk{chunk}"] = dict(ms=t, us_per_band=t * 1e3 / nb, GBs_alg=bytes_alg / t / 1e6)
-    print(chunk, res[f"local_kin_chunk{chunk}"], flush=True)
+for lines in (16, 8):
+    ctx.set_option("fft_lines", lines)
+    for chunk in (16, 51):
+        ctx.set_option("band_chunk", chunk)
+        nb = 153
+        t, _ = timeit(lambda: kb.apply_terms(psi[:nb], 3, out=out[:nb]))
+        bytes_alg = (72 * 192 ** 3 + 40 * npw) * nb
+        res[f"local_kin_L{lines}_chunk{chunk}"] = dict(ms=t, us_per_band=t * 1e3 / nb, GBs_alg=bytes_alg / t / 1e6)
+        print("L", lines, "chunk", chunk, res[f"local_kin_L{lines}_chunk{chunk}"], flush=True)
 ctx.set_option("band_chunk", 0)
-for backend in (0, 1):
-    ctx.set_option("gemm_backend", backend)
+ctx.set_option("fft_lines", int(os.environ.get("FFT_LINES", 0)))
+for backend in (0, 2, 1):
+    ctx.set_option("gemm_backend", 1 if backend == 1 else 0)
+    ctx.set_option("gemm_stages", 3 if backend == 2 else 2)
     t, _ = timeit(lambda: kb.apply_terms(psi, 4, out=out), n=2)
     fl = 16.0 * npw * nproj * M
     res[f"nonlocal_backend{backend}"] = dict(ms=t, TFLOPs=fl / t / 1e9)

@@ -229,3 +229,23 @@ def test_full_size_properties_192():
     kb.density_accumulate(psi, np.full(6, 2.0), rho)
     assert abs(rho.sum().item() * (vol / n ** 3) - 12.0) < 1e-10
     assert rho.min().item() >= 0.0
+
+
+def test_against_committed_golden_fixture():
+    """Committed vectors (tests/golden/si_block_fixture.npz, made by tests/golden/make_fixtures.py): the CUDA
+    path must reproduce the stored Hψ, eigenvalues and density from the stored operator data alone."""
+    import os
+    import dftk_b200
+    from gpu_common import ctx, to_dev
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "si_block_fixture.npz"))
+    grid = dftk_b200.FFTGrid(ctx(), tuple(int(x) for x in f["fft_size"]), float(f["volume"]))
+    kb = dftk_b200.KBlock(grid, f["mapping"], kin=f["kin"], P=to_dev(f["P"].T), D=f["D"])
+    kb.set_potential(to_dev(f["V"]))
+    h = kb.apply_h(to_dev(f["psi"])).cpu().numpy()
+    np.testing.assert_allclose(h, f["hpsi"], atol=1e-12 * np.abs(f["hpsi"]).max())
+    X = to_dev(f["psi"])
+    res = kb.lobpcg(X, tol=1e-10, maxiter=200)
+    np.testing.assert_allclose(res["λ"], f["eigenvalues"], atol=1e-9)
+    rho = torch.zeros(grid.N, dtype=torch.float64, device=ctx().device)
+    kb.density_accumulate(X, f["occ"], rho)
+    np.testing.assert_allclose(rho.cpu().numpy(), f["rho"], atol=1e-9 * f["rho"].max())

@@ -1,0 +1,26 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): k-point sharding + NCCL density allreduce."""
+import json
+import os
+import subprocess
+import sys
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.01])
+def test_sharded_scf_matches_single_gpu(temperature):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, TEMPERATURE=str(temperature))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531",
+                        os.path.join(ROOT, "scripts", "multi_gpu_check.py")], capture_output=True, text=True, env=env,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("MULTIGPU_RESULT ")][-1]
+    out = json.loads(line[len("MULTIGPU_RESULT "):])
+    assert out["dE"] < 2e-8 and out["deig"] < 1e-6 and out["drho"] < 1e-7, out
+    assert out["nk_local"] < out["nk_total"]

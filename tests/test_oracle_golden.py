@@ -171,3 +171,15 @@ def test_silicon_lda_scf_vs_abinit():
     assert res["energies"]["total"] == pytest.approx(-7.911817522631488, abs=1e-5)
     for ik in range(4):
         np.testing.assert_allclose(res["eigenvalues"][ik][:8], ref[ik], atol=1e-5)
+
+
+def test_oracle_matches_committed_fixture():
+    # the oracle is frozen by tests/golden/si_block_fixture.npz (made by tests/golden/make_fixtures.py)
+    import os
+    from oracle.terms import HamiltonianBlock
+    f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "si_block_fixture.npz"))
+    m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, functionals=("lda_x", "lda_c_vwn"), symmetries=False)
+    b = PlaneWaveBasis(m, 10, fft_size=tuple(int(x) for x in f["fft_size"]), kcoords=[[0.1, -0.2, 0.3]], kweights=[1.0])
+    np.testing.assert_array_equal(b.kpoints[0].mapping, f["mapping"])
+    _, ham = energy_hamiltonian(b, Terms(b), None, None, guess_density(b))
+    np.testing.assert_allclose(ham[0].matmul(f["psi"].T).T, f["hpsi"], atol=1e-12 * np.abs(f["hpsi"]).max())
