@@ -87,6 +87,12 @@ struct SphereTablesHost {
   int64_t n_pw;
   int n_cols, cnt_max, n_zc;
   std::vector<int> col_start, col_cnt, slot_ix, slot_src, zlist, colmap, col_y, col_z, zc_of;
+  // Range form of the pruning maps: a convex sphere occupies at most two contiguous index ranges per axis
+  // (one if it does not wrap).  Planes: z in [z_s0, z_s0+z_n0) U [z_s1, z_s1+z_n1), numbered in that order.
+  // In plane izc the columns are y in [pl_s0, +pl_n0) U [pl_s1, +pl_n1), numbered from pl_col0 in that order.
+  // ranges_ok == 0 means the structure does not hold and the kernels use the lookup tables.
+  int ranges_ok = 0, z_s0 = 0, z_n0 = 0, z_s1 = 0, z_n1 = 0;
+  std::vector<int> pl_s0, pl_n0, pl_s1, pl_n1, pl_col0;
 };
 
 // mapping: 0-based linear cube indices (x fastest) of the sphere coefficients, any order.
@@ -145,6 +151,38 @@ inline SphereTablesHost build_sphere_tables(int nx, int ny, int nz, int64_t n_pw
       lastz = T.col_z[c];
     }
     T.colmap[(size_t)izc * ny + T.col_y[c]] = c;
+  }
+  // range descriptors (validated against the tables)
+  {
+    auto two_ranges = [](const std::vector<int>& present, int& s0, int& n0, int& s1, int& n1) {
+      // present[i] != 0 marks occupied indices; returns false if more than two runs
+      const int n = (int)present.size();
+      s0 = n0 = s1 = n1 = 0;
+      int i = 0, runs = 0;
+      while (i < n) {
+        if (!present[i]) { ++i; continue; }
+        int st = i;
+        while (i < n && present[i]) ++i;
+        if (runs == 0) { s0 = st; n0 = i - st; }
+        else if (runs == 1) { s1 = st; n1 = i - st; }
+        else return false;
+        ++runs;
+      }
+      return true;
+    };
+    std::vector<int> zp(nz, 0);
+    for (int z : T.zlist) zp[z] = 1;
+    bool ok = two_ranges(zp, T.z_s0, T.z_n0, T.z_s1, T.z_n1);
+    T.pl_s0.assign(T.n_zc, 0); T.pl_n0.assign(T.n_zc, 0); T.pl_s1.assign(T.n_zc, 0); T.pl_n1.assign(T.n_zc, 0);
+    T.pl_col0.assign(T.n_zc, 0);
+    std::vector<int> yp(ny);
+    for (int p = 0; p < T.n_zc && ok; ++p) {
+      const int* cm = &T.colmap[(size_t)p * ny];
+      for (int iy = 0; iy < ny; ++iy) yp[iy] = cm[iy] >= 0;
+      ok = two_ranges(yp, T.pl_s0[p], T.pl_n0[p], T.pl_s1[p], T.pl_n1[p]);
+      if (ok && T.pl_n0[p] > 0) T.pl_col0[p] = cm[T.pl_s0[p]];
+    }
+    T.ranges_ok = ok ? 1 : 0;
   }
   return T;
 }

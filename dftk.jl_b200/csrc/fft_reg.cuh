@@ -82,7 +82,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
       cplx v[A];
 #pragma unroll
       for (int r = 0; r < A; ++r) {
-        int zc = T.zc_of[p + B * r];
+        int zc = zc_index(T, p + B * r);
         v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
@@ -119,7 +119,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
       pass2_load<B, A, -1>(X, p, line, bufB, Lp);
 #pragma unroll
       for (int f = 0; f < A; ++f) {
-        int zc = T.zc_of[p + B * f];
+        int zc = zc_index(T, p + B * f);
         if (zc >= 0 && x < nx) w2[((size_t)zc * ny + y) * nx + x] = X[f];
       }
     }
@@ -141,7 +141,7 @@ HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const
       cplx v[A];
 #pragma unroll
       for (int r = 0; r < A; ++r) {
-        int zc = T.zc_of[p + B * r];
+        int zc = zc_index(T, p + B * r);
         v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
@@ -187,7 +187,7 @@ HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, con
       pass2_load<A, B, -1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d) {
-        int zc = T.zc_of[p + A * d];
+        int zc = zc_index(T, p + A * d);
         if (zc >= 0 && x < nx) w2[((size_t)zc * ny + y) * nx + x] = X[d];
       }
     }
@@ -214,7 +214,7 @@ HD void reg_z_density(const SphereTablesX& T, const cplx* __restrict__ tw, const
         cplx v[A];
 #pragma unroll
         for (int r = 0; r < A; ++r) {
-          int zc = T.zc_of[p + B * r];
+          int zc = zc_index(T, p + B * r);
           v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
         }
         pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
@@ -249,13 +249,14 @@ HD void reg_y_backward(const SphereTablesX& T, const cplx* __restrict__ tw, cons
   const int x0 = bid.x * L, izc = bid.y;
   const cplx* in = W1 + (size_t)bid.z * T.n_cols * nx;
   cplx* out = W2 + ((size_t)bid.z * T.n_zc + izc) * n * nx;
+  const PlaneCols pc = plane_cols(T, izc);
   TLOOP(t, L * TT) {
     const int line = t % L, p = t / L, x = x0 + line;
     if (p < B) {
       cplx v[A];
 #pragma unroll
       for (int r = 0; r < A; ++r) {
-        int c = T.colmap[izc * n + p + B * r];
+        int c = pc.col(p + B * r);
         v[r] = (c >= 0 && x < nx) ? in[(size_t)c * nx + x] : make_double2(0.0, 0.0);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
@@ -283,6 +284,7 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
   const int x0 = bid.x * L, izc = bid.y;
   const cplx* in = W2 + ((size_t)bid.z * T.n_zc + izc) * n * nx;
   cplx* out = W1 + (size_t)bid.z * T.n_cols * nx;
+  const PlaneCols pc = plane_cols(T, izc);
   TLOOP(t, L * TT) {
     const int line = t % L, p = t / L, x = x0 + line;
     if (p < B) {
@@ -301,7 +303,7 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
       pass2_load<A, B, -1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d) {
-        int c = T.colmap[izc * n + p + A * d];
+        int c = pc.col(p + A * d);
         if (c >= 0 && x < nx) out[(size_t)c * nx + x] = X[d];
       }
     }

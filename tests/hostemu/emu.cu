@@ -125,11 +125,20 @@ static bool emu_pair(int n, int* A, int* B) {
     if (!done_) return -8;                                  \
   } while (0)
 
+static bool force_tables = false;
+extern "C" void emur_force_tables(int f) { force_tables = f != 0; }
+extern "C" int emur_ranges_ok(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping) {
+  return build_sphere_tables(nx, ny, nz, n_pw, mapping).ranges_ok;
+}
 struct EmuR : Emu {
   SphereTablesX TX;
   EmuR(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, int nb) : Emu(nx, ny, nz, n_pw, mapping, nb) {
     static_cast<SphereTables&>(TX) = T;
     TX.zc_of = H.zc_of.data();
+    TX.ranges_ok = force_tables ? 0 : H.ranges_ok;
+    TX.z_s0 = H.z_s0; TX.z_n0 = H.z_n0; TX.z_s1 = H.z_s1; TX.z_n1 = H.z_n1;
+    TX.pl_s0 = H.pl_s0.data(); TX.pl_n0 = H.pl_n0.data(); TX.pl_s1 = H.pl_s1.data(); TX.pl_n1 = H.pl_n1.data();
+    TX.pl_col0 = H.pl_col0.data();
     sm.resize(4 * (size_t)std::max(std::max(nx, ny), nz) * 33 + 64);
   }
   static int Lof(int A, int B) { return (A > B ? A : B) >= 8 ? 16 : 32; }
