@@ -178,7 +178,7 @@ void kb_sphere_to_planes(dftk_b200_kblock* kb, const cplx* psi, int64_t ldpsi, i
   dftk_b200_grid* g = kb->grid;
   dftk_b200_ctx* ctx = g->ctx;
   ensure_scratch(kb, nb);
-  if (g->rx) {
+  if ((g->rx && kb->T.ranges_ok)) {
     int L = reg_L(g->rx), Lp = L + 1;
     const cplx* tw = (const cplx*)g->twx.p;
     cplx* W1 = kb->W1.p;
@@ -189,7 +189,7 @@ void kb_sphere_to_planes(dftk_b200_kblock* kb, const cplx* psi, int64_t ldpsi, i
     LAUNCH(ctx, k_sphere_to_x, dim3(cdiv(kb->T.n_cols, L), nb), FFT_THREADS, smem_for(g->nx, L), kb->T,
            g->px, (const cplx*)g->twx.p, psi, ldpsi, kb->W1.p, L, Lp);
   }
-  if (g->ry) {
+  if ((g->ry && kb->T.ranges_ok)) {
     int L = reg_L(g->ry), Lp = L + 1;
     const cplx* tw = (const cplx*)g->twy.p;
     const cplx* W1 = kb->W1.p;
@@ -207,7 +207,7 @@ void kb_planes_to_sphere(dftk_b200_kblock* kb, cplx* out, int64_t ldout, int nb,
                          const double* kin, const cplx* psi, int64_t ldpsi, int accumulate) {
   dftk_b200_grid* g = kb->grid;
   dftk_b200_ctx* ctx = g->ctx;
-  if (g->ry) {
+  if ((g->ry && kb->T.ranges_ok)) {
     int L = reg_L(g->ry), Lp = L + 1;
     const cplx* tw = (const cplx*)g->twy.p;
     const cplx* W2 = kb->W2.p;
@@ -219,7 +219,7 @@ void kb_planes_to_sphere(dftk_b200_kblock* kb, cplx* out, int64_t ldout, int nb,
     LAUNCH(ctx, k_y_forward, dim3(cdiv(g->nx, L), kb->T.n_zc, nb), FFT_THREADS, smem_for(g->ny, L),
            kb->T, g->py, (const cplx*)g->twy.p, (const cplx*)kb->W2.p, kb->W1.p, L, Lp);
   }
-  if (g->rx) {
+  if ((g->rx && kb->T.ranges_ok)) {
     int L = reg_L(g->rx), Lp = L + 1;
     const cplx* tw = (const cplx*)g->twx.p;
     const cplx* W1 = kb->W1.p;
@@ -249,7 +249,7 @@ void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, i
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     const cplx* p = psi + b0 * kb->n_pw;
     kb_sphere_to_planes(kb, p, kb->n_pw, nb);
-    if (g->rz) {
+    if ((g->rz && kb->T.ranges_ok)) {
       int L = reg_L(g->rz), Lp = L + 1;
       const cplx* tw = (const cplx*)g->twz.p;
       cplx* W2 = kb->W2.p;
@@ -274,7 +274,7 @@ void kb_sphere_to_real(dftk_b200_kblock* kb, const cplx* psi, cplx* cube, int64_
   for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     kb_sphere_to_planes(kb, psi + b0 * kb->n_pw, kb->n_pw, nb);
-    if (g->rz) {
+    if ((g->rz && kb->T.ranges_ok)) {
       int L = reg_L(g->rz), Lp = L + 1;
       const cplx* tw = (const cplx*)g->twz.p;
       const cplx* W2 = kb->W2.p;
@@ -296,7 +296,7 @@ void kb_real_to_sphere(dftk_b200_kblock* kb, const cplx* cube, cplx* out, int64_
   for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     ensure_scratch(kb, nb);
-    if (g->rz) {
+    if ((g->rz && kb->T.ranges_ok)) {
       int L = reg_L(g->rz), Lp = L + 1;
       const cplx* tw = (const cplx*)g->twz.p;
       const cplx* cb = cube + b0 * g->N;
@@ -325,7 +325,7 @@ void kb_density_accumulate(dftk_b200_kblock* kb, const cplx* psi, const double* 
   for (int64_t b0 = 0; b0 < n_bands; b0 += chunk) {
     int nb = (int)std::min<int64_t>(chunk, n_bands - b0);
     kb_sphere_to_planes(kb, psi + b0 * kb->n_pw, kb->n_pw, nb);
-    if (g->rz) {
+    if ((g->rz && kb->T.ranges_ok)) {
       int L = reg_L(g->rz), Lp = L + 1;
       const cplx* tw = (const cplx*)g->twz.p;
       const cplx* W2 = kb->W2.p;

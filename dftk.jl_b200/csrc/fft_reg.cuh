@@ -83,7 +83,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
 #pragma unroll
       for (int r = 0; r < A; ++r) {
         int zc = zc_index(T, p + B * r);
-        v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
+        v[r] = ld_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
     }
@@ -97,7 +97,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d) {
-        double vv = (x < nx) ? V[((size_t)(p + A * d) * ny + y) * nx + x] : 0.0;
+        double vv = ld_pred(V + ((size_t)(p + A * d) * ny + y) * nx + x, x < nx);
         X[d] = cscale(X[d], vv);
       }
       // forward transform of the elements p + A*d: pass 1 with the roles of A and B swapped
@@ -120,7 +120,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
 #pragma unroll
       for (int f = 0; f < A; ++f) {
         int zc = zc_index(T, p + B * f);
-        if (zc >= 0 && x < nx) w2[((size_t)zc * ny + y) * nx + x] = X[f];
+        st_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, X[f], zc >= 0 && x < nx);
       }
     }
   }
@@ -142,7 +142,7 @@ HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const
 #pragma unroll
       for (int r = 0; r < A; ++r) {
         int zc = zc_index(T, p + B * r);
-        v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
+        v[r] = ld_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
     }
@@ -155,7 +155,7 @@ HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d)
-        if (x < nx) out[((size_t)(p + A * d) * ny + y) * nx + x] = cscale(X[d], scale);
+        st_pred(out + ((size_t)(p + A * d) * ny + y) * nx + x, cscale(X[d], scale), x < nx);
     }
   }
 }
@@ -175,7 +175,7 @@ HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, con
       cplx v[A];
 #pragma unroll
       for (int r = 0; r < A; ++r)
-        v[r] = (x < nx) ? in[((size_t)(p + B * r) * ny + y) * nx + x] : make_double2(0.0, 0.0);
+        v[r] = ld_pred(in + ((size_t)(p + B * r) * ny + y) * nx + x, x < nx);
       pass1_store<A, B, -1>(v, p, line, bufA, Lp, tw);
     }
   }
@@ -188,7 +188,7 @@ HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, con
 #pragma unroll
       for (int d = 0; d < B; ++d) {
         int zc = zc_index(T, p + A * d);
-        if (zc >= 0 && x < nx) w2[((size_t)zc * ny + y) * nx + x] = X[d];
+        st_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, X[d], zc >= 0 && x < nx);
       }
     }
   }
@@ -215,7 +215,7 @@ HD void reg_z_density(const SphereTablesX& T, const cplx* __restrict__ tw, const
 #pragma unroll
         for (int r = 0; r < A; ++r) {
           int zc = zc_index(T, p + B * r);
-          v[r] = (zc >= 0 && x < nx) ? w2[((size_t)zc * ny + y) * nx + x] : make_double2(0.0, 0.0);
+          v[r] = ld_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx);
         }
         pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
       }
@@ -257,7 +257,7 @@ HD void reg_y_backward(const SphereTablesX& T, const cplx* __restrict__ tw, cons
 #pragma unroll
       for (int r = 0; r < A; ++r) {
         int c = pc.col(p + B * r);
-        v[r] = (c >= 0 && x < nx) ? in[(size_t)c * nx + x] : make_double2(0.0, 0.0);
+        v[r] = ld_pred(in + (size_t)(c < 0 ? 0 : c) * nx + x, c >= 0 && x < nx);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
     }
@@ -270,7 +270,7 @@ HD void reg_y_backward(const SphereTablesX& T, const cplx* __restrict__ tw, cons
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d)
-        if (x < nx) out[(size_t)(p + A * d) * nx + x] = X[d];
+        st_pred(out + (size_t)(p + A * d) * nx + x, X[d], x < nx);
     }
   }
 }
@@ -291,7 +291,7 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
       cplx v[A];
 #pragma unroll
       for (int r = 0; r < A; ++r)
-        v[r] = (x < nx) ? in[(size_t)(p + B * r) * nx + x] : make_double2(0.0, 0.0);
+        v[r] = ld_pred(in + (size_t)(p + B * r) * nx + x, x < nx);
       pass1_store<A, B, -1>(v, p, line, bufA, Lp, tw);
     }
   }
@@ -304,7 +304,7 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
 #pragma unroll
       for (int d = 0; d < B; ++d) {
         int c = pc.col(p + A * d);
-        if (c >= 0 && x < nx) out[(size_t)c * nx + x] = X[d];
+        st_pred(out + (size_t)(c < 0 ? 0 : c) * nx + x, X[d], c >= 0 && x < nx);
       }
     }
   }

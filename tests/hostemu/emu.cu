@@ -135,7 +135,7 @@ struct EmuR : Emu {
   EmuR(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, int nb) : Emu(nx, ny, nz, n_pw, mapping, nb) {
     static_cast<SphereTables&>(TX) = T;
     TX.zc_of = H.zc_of.data();
-    TX.ranges_ok = force_tables ? 0 : H.ranges_ok;
+    TX.ranges_ok = H.ranges_ok;
     TX.z_s0 = H.z_s0; TX.z_n0 = H.z_n0; TX.z_s1 = H.z_s1; TX.z_n1 = H.z_n1;
     TX.pl_s0 = H.pl_s0.data(); TX.pl_n0 = H.pl_n0.data(); TX.pl_s1 = H.pl_s1.data(); TX.pl_n1 = H.pl_n1.data();
     TX.pl_col0 = H.pl_col0.data();

@@ -41,9 +41,6 @@ def _basis(fft_size, Ecut, k):
                                                   ((24, 16, 20), 6, "emur"), ((20, 27, 15), 5, "emur")])
 def test_emulated_pipeline(emu, fft_size, Ecut, prefix):
     lib = emu
-    if prefix == "emur":
-        # once with the arithmetic range form of the pruning maps, once with the lookup tables
-        lib.emur_force_tables(1 if fft_size == (24, 16, 20) else 0)
 
     class _E:
         def __getattr__(self, name):
@@ -87,7 +84,6 @@ def test_emulated_pipeline(emu, fft_size, Ecut, prefix):
     np.testing.assert_allclose(rho, refr, atol=1e-11 * refr.max())
     if prefix == "emur":
         assert lib.emur_ranges_ok(nx, ny, nz, npw, _p(mapping)) == 1      # a k-point sphere always has the range form
-        lib.emur_force_tables(0)
     # unsorted mapping (construct_from_equivalent_kpt, src/Kpoint.jl:44-56)
     perm = rng.permutation(kpt.n_G)
     out2 = np.zeros_like(psi)
