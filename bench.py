@@ -223,7 +223,7 @@ def run_gpu(args):
     hbm_peak, peak_src = peaks()
     alg_bytes_band = 72.0 * N + 40.0 * n_pw
     ach = alg_bytes_band * M / (ms_local * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel="Hpsi-local group (k_sphere_to_x,k_y_backward,k_z_apply_potential,k_y_forward,k_x_to_sphere)",
+    roofline = dict(bound="hbm", kernel="Hpsi-local group (kr_sphere_to_x, kr_y_backward, kr_z_apply, kr_y_forward, kr_x_to_sphere)",
                     achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None,
                     algorithmic_bytes_per_band=alg_bytes_band, ms_per_block=ms_local, us_per_band=1e3 * ms_local / M,
                     peak_source=peak_src + " (of measured)")

@@ -118,7 +118,8 @@ void reg_set_attributes() {
 static int g_fft_lines = 0;
 static inline int reg_L(const RegKernels* k) {
   if (g_fft_lines > 0 && g_fft_lines * k->T <= 32 * k->T) return g_fft_lines;
-  return k->T >= 8 ? 16 : 32;
+  // about 128 threads per CTA: more independent CTAs per SM overlap the load / exchange / store phases better
+  return k->T >= 12 ? 8 : (k->T >= 5 ? 16 : 32);
 }
 static inline size_t reg_smem(const RegKernels* k) { return 2 * (size_t)k->A * k->B * (reg_L(k) + 1) * sizeof(cplx); }
 void reg_set_lines(int L) { g_fft_lines = (L == 8 || L == 16 || L == 32) ? L : 0; }
