@@ -61,9 +61,11 @@ class KpointComm:
         import torch
         import torch.distributed as dist
         t = torch.as_tensor(np.asarray(value, dtype=np.float64)).clone()
+        if dist.get_backend(self.group) == "nccl":          # NCCL groups only move device tensors
+            t = t.cuda()
         dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op],
                         group=self.group)
-        r = t.numpy()
+        r = t.cpu().numpy()
         return float(r) if r.ndim == 0 else r
 
     def sum(self, v): return self._all(v, "sum")
