@@ -222,6 +222,48 @@ __global__ void k_compute_lambda(const cplx* __restrict__ num, const cplx* __res
 
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
 
+// Optional section timing (env DFTK_B200_PROFILE=1): stream-synchronising wall clock per LOBPCG section.
+struct SectionProf {
+  bool on;
+  cudaStream_t st;
+  std::vector<std::pair<std::string, double>> acc;
+  double t0 = 0;
+  std::string cur;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  }
+  void begin(const char* name) {
+    if (!on) return;
+    end();
+    cudaStreamSynchronize(st);
+    cur = name;
+    t0 = now();
+  }
+  void end() {
+    if (!on || cur.empty()) return;
+    cudaStreamSynchronize(st);
+    double dt = now() - t0;
+    for (auto& a : acc)
+      if (a.first == cur) {
+        a.second += dt;
+        cur.clear();
+        return;
+      }
+    acc.push_back({cur, dt});
+    cur.clear();
+  }
+  void report(int niter) {
+    if (!on) return;
+    end();
+    double tot = 0;
+    for (auto& a : acc) tot += a.second;
+    fprintf(stderr, "[dftk_b200 lobpcg profile] %d iterations, %.3f s in sections\n", niter, tot);
+    for (auto& a : acc) fprintf(stderr, "  %-22s %9.3f s  %5.1f %%\n", a.first.c_str(), a.second, 100 * a.second / tot);
+  }
+};
+
 // ------------------------------------------------------------------ solver object
 struct Lobpcg {
   dftk_b200_kblock* kb;
@@ -431,6 +473,9 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
   if (n_conv_check <= 0 || n_conv_check > M) n_conv_check = M;
   use_prec = use_prec && kb->has_kin;
 
+  SectionProf prof;
+  prof.on = getenv("DFTK_B200_PROFILE") != nullptr;
+  prof.st = ctx->stream;
   Lobpcg L;
   L.kb = kb;
   L.ctx = ctx;
@@ -480,9 +525,12 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
   auto RH = [&](int64_t i, int it) -> double& { return resid_hist[(size_t)it * M + i]; };
 
   // X = ortho!(copy(X)) :370
+  prof.begin("ortho(X0)");
   L.ortho(X, L.tmpN, N);
+  prof.begin("H*X");
   int64_t n_matvec = M;
   applyH(X, mat(AX));
+  prof.begin("misc");
   CUDA_CHECK(cudaMemsetAsync(big + N * M, 0, (size_t)4 * N * M * sizeof(cplx), ctx->stream));   // R, AR, P, AP
   CUDA_CHECK(cudaMemsetAsync(nR, 0, (size_t)3 * N * M * sizeof(cplx), ctx->stream));           // nR, nP, nAP
   copycols(nX, Xio, 0, M);
@@ -503,6 +551,7 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
     const int64_t Ma = M - a0;
     std::vector<Mat> Y, AY;
     if (niter > 0) {
+      prof.begin("H*R");
       applyH(mat(R).cols_from(a0), mat(AR).cols_from(a0));
       n_matvec += Ma;
       Y = {X.cols_from(a0), mat(R).cols_from(a0)};
@@ -513,15 +562,19 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
       }
       ncolsY = (int64_t)Y.size() * Ma;
       // rayleigh_ritz :141-171
+      prof.begin("RR gram Y'AY");
       L.gram(Y, AY, L.G, S3, true);
+      prof.begin("RR heevd");
       // only the block upper triangle of G is written; heevd reads the upper triangle only
       L.heevd(L.G, ncolsY);
+      prof.begin("X,AX = Y cX");
       // cX = vectors[:, 1:Ma], λ = values[1:Ma]
       L.copy2d(Mat{L.cX, S3, ncolsY, Ma}, Mat{L.G, S3, ncolsY, Ma});
       CUDA_CHECK(cudaMemcpyAsync(L.d_lam + a0, L.d_w, Ma * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       L.blocks_times(Y, L.cX, S3, Ma, mat(nX).cols_from(a0), 1.0, 0.0);
       L.blocks_times(AY, L.cX, S3, Ma, mat(nAX).cols_from(a0), 1.0, 0.0);
     }
+    prof.begin("residual+precond");
     // residuals :443-445 (+ precondprep! :452-457 fused)
     LAUNCH(ctx, k_residual, (unsigned)Ma, 256, 0, (const cplx*)(nAX + N * a0), (const cplx*)(nX + N * a0),
            (const double*)(L.d_lam + a0), nR + N * a0, N, N, use_prec ? (const double*)kb->kin.p : nullptr,
@@ -550,13 +603,16 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
 
     if (niter > 0) {
       const int64_t lenXn = Ma - newly;
+      prof.begin("cP ortho");
       // cP = (cX - e)[:, newly:Ma]; ortho!(cP, cX, cX)
       LAUNCH(ctx, k_make_cP, nblk(ncolsY * lenXn), 256, 0, L.cP, (const cplx*)L.cX, S3, ncolsY, lenXn, newly,
              lenXn);
       L.ortho_against(Mat{L.cP, S3, ncolsY, lenXn}, {Mat{L.cX, S3, ncolsY, Ma}}, L.G, S3);
+      prof.begin("P,AP = Y cP");
       L.blocks_times(Y, L.cP, S3, lenXn, mat(nP).cols_from(a0 + newly), 1.0, 0.0);
       L.blocks_times(AY, L.cP, S3, lenXn, mat(nAP).cols_from(a0 + newly), 1.0, 0.0);
     }
+    prof.begin("copies+check");
     copycols(Xio, nX, a0, Ma);
     copycols(AX, nAX, a0, Ma);
     copycols(R, nR, a0, Ma);
@@ -575,12 +631,15 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
       copycols(AP, nAP, a0, M - a0);
       Z.push_back(mat(P).cols_from(a0));
     }
+    prof.begin("ortho R vs (X,P)");
     L.ortho_against(mat(R).cols_from(a0), Z, L.tmpN, N);
+    prof.end();
 
     if (niter >= maxiter) break;
     niter++;
   }
   (void)done;
+  prof.report(niter);
   // final_retval :325-338
   L.get(lam_h.data(), L.d_lam, M * sizeof(double));
   std::vector<int64_t> perm(M);

@@ -1,0 +1,23 @@
+"""Development probe: section timing of one LOBPCG solve at the C3 shape (DFTK_B200_PROFILE=1)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["DFTK_B200_PROFILE"] = "1"
+import numpy as np
+import torch
+sys.argv = ["bench.py"]
+import bench
+import dftk_b200 as dftk
+
+lat, pos = bench.supercell(int(os.environ.get("REP", 5)))
+Si = dftk.ElementPsp("Si")
+model = dftk.model_DFT(lat, [Si] * len(pos), pos, functionals=dftk.LDA(), symmetries=False)
+basis = dftk.PlaneWaveBasis(model, Ecut=30.0, kgrid=dftk.ExplicitKpoints([[0, 0, 0]]))
+_, ham = dftk.energy_hamiltonian(basis, None, None, rho=dftk.guess_density(basis))
+kb = ham[0].kblock
+M = bench.n_bands_for(len(pos))
+X = dftk.random_orbitals(basis, basis.kpoints[0], M)
+torch.cuda.synchronize()
+t = time.perf_counter()
+res = kb.lobpcg(X, tol=float(os.environ.get("TOL", 0.025)), maxiter=int(os.environ.get("MAXITER", 8)), n_conv_check=M - 3)
+torch.cuda.synchronize()
+print("lobpcg", time.perf_counter() - t, "s", res["n_iter"], res["n_matvec"], res["converged"], flush=True)
