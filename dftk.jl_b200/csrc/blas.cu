@@ -57,22 +57,29 @@ k_zgemm_cn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, 
   const int nkt = (int)((ke - kb + BKC - 1) / BKC);
   const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
 
+  // Per-thread copy plan (fixed across k tiles): element e = tid + 128 i -> column tid/16 + 8 i, row tid%16.
+  const int lkk = tid & (BKC - 1), lcol = tid >> 4;
+  const cplx* pA = A + kb + lkk + lda * (i0 + lcol);
+  const cplx* pB = B + kb + lkk + ldb * (j0 + lcol);
+  unsigned okA = 0, okB = 0;   // column-in-range masks
+#pragma unroll
+  for (int i = 0; i < GT_M / 8; ++i) okA |= (i0 + lcol + 8 * i < m) ? (1u << i) : 0u;
+#pragma unroll
+  for (int i = 0; i < GT_N / 8; ++i) okB |= (j0 + lcol + 8 * i < n) ? (1u << i) : 0u;
   auto load_tile = [&](int kt, int slot) {
-    const int64_t k0 = kb + (int64_t)kt * BKC;
-    // A tile: 64 columns x 16 complex rows; one 16-byte cp.async per complex element
-    for (int e = tid; e < GT_M * BKC; e += GEMM_THREADS) {
-      int col = e / BKC, kk = e % BKC;
-      int64_t gi = i0 + col, gk = k0 + kk;
-      bool ok = (gi < m) && (gk < ke);
-      const cplx* src = A + (ok ? (gk + lda * gi) : 0);
-      cp_async16(As + ((size_t)slot * GT_M + col) * LDK + 2 * kk, src, ok);
+    const int64_t koff = (int64_t)kt * BKC;
+    const bool rowok = kb + koff + lkk < ke;
+    double* da = As + ((size_t)slot * GT_M + lcol) * LDK + 2 * lkk;
+    double* db = Bs + ((size_t)slot * GT_N + lcol) * LDK + 2 * lkk;
+#pragma unroll
+    for (int i = 0; i < GT_M / 8; ++i) {
+      bool ok = rowok && ((okA >> i) & 1u);
+      cp_async16(da + (size_t)8 * i * LDK, ok ? (pA + koff + (int64_t)8 * i * lda) : A, ok);
     }
-    for (int e = tid; e < GT_N * BKC; e += GEMM_THREADS) {
-      int col = e / BKC, kk = e % BKC;
-      int64_t gj = j0 + col, gk = k0 + kk;
-      bool ok = (gj < n) && (gk < ke);
-      const cplx* src = B + (ok ? (gk + ldb * gj) : 0);
-      cp_async16(Bs + ((size_t)slot * GT_N + col) * LDK + 2 * kk, src, ok);
+#pragma unroll
+    for (int i = 0; i < GT_N / 8; ++i) {
+      bool ok = rowok && ((okB >> i) & 1u);
+      cp_async16(db + (size_t)8 * i * LDK, ok ? (pB + koff + (int64_t)8 * i * ldb) : B, ok);
     }
   };
 
@@ -87,7 +94,7 @@ k_zgemm_cn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, 
     cp_async_commit();
   }
   const int fr = lane >> 2, fk = lane & 3;
-  const double sgn = (lane & 1) ? -1.0 : 1.0;
+  const int sgnmask = (lane & 1) ? (int)0x80000000 : 0;   // J-image sign, applied with an integer XOR (ALU pipe)
   for (int kt = 0; kt < nkt; ++kt) {
     cp_async_wait<GEMM_STAGES - 2>();
     __syncthreads();
@@ -107,7 +114,8 @@ k_zgemm_cn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, 
       for (int b = 0; b < 2; ++b) {
         const double* row = bs + (wj + 8 * b + fr) * LDK + 4 * s4;
         bf[b] = row[fk];
-        bh[b] = sgn * row[fk ^ 1];
+        double t = row[fk ^ 1];
+        bh[b] = __hiloint2double(__double2hiint(t) ^ sgnmask, __double2loint(t));
       }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
@@ -169,21 +177,30 @@ k_zgemm_nn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, 
   const int64_t m_eff = b_upper ? min(m, j0 + UT_N) : m;
   const int nkt = (int)((m_eff + BKC - 1) / BKC);
 
+  // Per-thread copy plan: A tile element e = tid + 128 i -> inner index e/64 = tid/64 + 2 i, row e%64 = tid%64;
+  //                       B tile element e = tid + 128 i -> column tid/16 + 8 i, inner index tid%16.
+  const int arow = tid & (UT_M - 1), aii = tid >> 6;
+  const int bii = tid & (BKC - 1), bcol = tid >> 4;
+  const bool arow_ok = r0 + arow < Krows;
+  const cplx* pA = A + (r0 + arow) + lda * aii;
+  const cplx* pB = B + bii + ldb * (j0 + bcol);
+  unsigned okB = 0;
+#pragma unroll
+  for (int i = 0; i < UT_N / 8; ++i) okB |= (j0 + bcol + 8 * i < n) ? (1u << i) : 0u;
   auto load_tile = [&](int kt, int slot) {
     const int64_t i0 = (int64_t)kt * BKC;
-    for (int e = tid; e < BKC * UT_M; e += GEMM_THREADS) {
-      int ii = e / UT_M, rr = e % UT_M;
-      int64_t gi = i0 + ii, gr = r0 + rr;
-      bool ok = (gi < m) && (gr < Krows);
-      const cplx* src = A + (ok ? (gr + lda * gi) : 0);
-      cp_async16(As + ((size_t)slot * BKC + ii) * LDA_U + 2 * rr, src, ok);
+    double* da = As + ((size_t)slot * BKC + aii) * LDA_U + 2 * arow;
+    double* db = Bs + ((size_t)slot * UT_N + bcol) * LDK + 2 * bii;
+#pragma unroll
+    for (int i = 0; i < BKC / 2; ++i) {
+      bool ok = arow_ok && (i0 + aii + 2 * i < m_eff);
+      cp_async16(da + (size_t)2 * i * LDA_U, ok ? (pA + (i0 + 2 * i) * lda) : A, ok);
     }
-    for (int e = tid; e < UT_N * BKC; e += GEMM_THREADS) {
-      int col = e / BKC, ii = e % BKC;
-      int64_t gj = j0 + col, gi = i0 + ii;
-      bool ok = (gj < n) && (gi < m);
-      const cplx* src = B + (ok ? (gi + ldb * gj) : 0);
-      cp_async16(Bs + ((size_t)slot * UT_N + col) * LDK + 2 * ii, src, ok);
+    const bool iiok = i0 + bii < m_eff;
+#pragma unroll
+    for (int i = 0; i < UT_N / 8; ++i) {
+      bool ok = iiok && ((okB >> i) & 1u);
+      cp_async16(db + (size_t)8 * i * LDK, ok ? (pB + i0 + (int64_t)8 * i * ldb) : B, ok);
     }
   };
 
@@ -218,7 +235,7 @@ k_zgemm_nn(const cplx* __restrict__ A, int64_t lda, const cplx* __restrict__ B, 
         int R = wr + 8 * a + fr;  // real row inside the tile
         // A^[R][2i] = A~[R][i];  A^[R][2i+1] = (R odd) ? A~[R-1][i] : -A~[R+1][i]
         double v = as[ii * LDA_U + ((fk & 1) ? (R ^ 1) : R)];
-        af[a] = ((fk & 1) && !(R & 1)) ? -v : v;
+        af[a] = ((fk & 1) && !(R & 1)) ? __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v)) : v;
       }
 #pragma unroll
       for (int b = 0; b < 4; ++b) bf[b] = bs[(8 * b + fr) * LDK + 4 * s4 + fk];

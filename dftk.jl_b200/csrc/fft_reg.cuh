@@ -76,6 +76,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
   cplx* bufB = DFTK_Z_ALIAS ? sm : sm + (size_t)n * Lp;
   const int x0 = bid.x * L, y = bid.y;
   cplx* w2 = W2 + (size_t)bid.z * T.n_zc * ny * nx;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   TLOOP(t, L * TT) {
     const int line = t % L, p = t / L, x = x0 + line;
     if (p < B) {
@@ -83,7 +84,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
 #pragma unroll
       for (int r = 0; r < A; ++r) {
         int zc = zc_index(T, p + B * r);
-        v[r] = ld_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx);
+        v[r] = ld_pred_hint(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx, pol_stream);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
     }
@@ -97,7 +98,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d) {
-        double vv = ld_pred(V + ((size_t)(p + A * d) * ny + y) * nx + x, x < nx);
+        double vv = ld_pred_hint(V + ((size_t)(p + A * d) * ny + y) * nx + x, x < nx, pol_keep);
         X[d] = cscale(X[d], vv);
       }
       // forward transform of the elements p + A*d: pass 1 with the roles of A and B swapped
@@ -120,7 +121,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
 #pragma unroll
       for (int f = 0; f < A; ++f) {
         int zc = zc_index(T, p + B * f);
-        st_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, X[f], zc >= 0 && x < nx);
+        st_pred_hint(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, X[f], zc >= 0 && x < nx, pol_stream);
       }
     }
   }

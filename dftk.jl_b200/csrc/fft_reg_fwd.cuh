@@ -39,6 +39,58 @@ HD cplx ld_pred(const cplx* p, bool ok) {
   return ok ? *p : make_double2(0.0, 0.0);
 #endif
 }
+// L2 eviction policies: the potential V(r) (N_fft doubles, re-read by every band) should stay resident in the
+// 126 MB L2 while the per-band pruned intermediates stream through it once.
+HD uint64_t l2_policy_evict_last() {
+#if defined(__CUDA_ARCH__)
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#else
+  return 0;
+#endif
+}
+HD uint64_t l2_policy_evict_first() {
+#if defined(__CUDA_ARCH__)
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+#else
+  return 0;
+#endif
+}
+HD double ld_pred_hint(const double* p, bool ok, uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  double x;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t"
+               "@q ld.global.L2::cache_hint.f64 %0, [%1], %3;\n\t}" : "=d"(x) : "l"(p), "r"((int)ok), "l"(pol));
+  return x;
+#else
+  (void)pol;
+  return ok ? *p : 0.0;
+#endif
+}
+HD cplx ld_pred_hint(const cplx* p, bool ok, uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  double x, y;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t"
+               "mov.f64 %1, 0d0000000000000000;\n\t@q ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %4;\n\t}"
+               : "=d"(x), "=d"(y) : "l"(p), "r"((int)ok), "l"(pol));
+  return make_double2(x, y);
+#else
+  (void)pol;
+  return ok ? *p : make_double2(0.0, 0.0);
+#endif
+}
+HD void st_pred_hint(cplx* p, cplx v, bool ok, uint64_t pol) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %4;\n\t}"
+               :: "l"(p), "d"(v.x), "d"(v.y), "r"((int)ok), "l"(pol) : "memory");
+#else
+  (void)pol;
+  if (ok) *p = v;
+#endif
+}
 HD double ld_pred(const double* p, bool ok) {
 #if defined(__CUDA_ARCH__)
   double x;
