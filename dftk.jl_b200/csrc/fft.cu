@@ -115,14 +115,10 @@ void reg_set_attributes() {
                           k.y_forward, k.x_to_sphere})
       CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
 }
-static int g_fft_lines = 0;
-static inline int reg_L(const RegKernels* k) {
-  if (g_fft_lines > 0 && g_fft_lines * k->T <= 32 * k->T) return g_fft_lines;
-  // about 128 threads per CTA: more independent CTAs per SM overlap the load / exchange / store phases better
-  return k->T >= 12 ? 8 : (k->T >= 5 ? 16 : 32);
-}
+// must match RegPair<A,B>::L (fft_reg.cuh)
+static inline int reg_L(const RegKernels* k) { return k->T >= 12 ? 8 : (k->T >= 5 ? 16 : 32); }
 static inline size_t reg_smem(const RegKernels* k) { return 2 * (size_t)k->A * k->B * (reg_L(k) + 1) * sizeof(cplx); }
-void reg_set_lines(int L) { g_fft_lines = (L == 8 || L == 16 || L == 32) ? L : 0; }
+void reg_set_lines(int) {}
 static void launch_ptr(dftk_b200_ctx* ctx, const void* f, dim3 grid, int threads, size_t smem, void** args) {
   CUDA_CHECK(cudaLaunchKernel(f, grid, dim3(threads), args, smem, ctx->stream));
   ctx->launches++;

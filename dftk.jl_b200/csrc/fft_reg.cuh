@@ -25,6 +25,10 @@ template <int A, int B>
 struct RegPair {
   static constexpr int n = A * B;
   static constexpr int T = (A > B ? A : B);
+  // lines per CTA: about 128 threads per CTA (more independent CTAs per SM overlap the load / exchange / store
+  // phases better); compile-time so that every shared-memory offset folds into an immediate
+  static constexpr int L = (T >= 12 ? 8 : (T >= 5 ? 16 : 32));
+  static constexpr int Lp = L + 1;
 };
 
 // thread q (< B) holds x[r] = element q + B*r; writes twiddled DFT_A to S[(c*B + q)]
@@ -69,8 +73,10 @@ HD void pass1_compute(const cplx* x, int q, const cplx* __restrict__ tw, cplx* Y
 
 template <int A, int B>
 HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ tw, cplx* __restrict__ W2,
-                              const double* __restrict__ V, int L, int Lp, cplx* sm, Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+                              const double* __restrict__ V, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   const int nx = T.nx, ny = T.ny;
   cplx* bufA = sm;
   cplx* bufB = DFTK_Z_ALIAS ? sm : sm + (size_t)n * Lp;
@@ -84,7 +90,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
 #pragma unroll
       for (int r = 0; r < A; ++r) {
         int zc = zc_index(T, p + B * r);
-        v[r] = ld_pred_hint(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx, pol_stream);
+        v[r] = ld_pred_hint(w2 + (unsigned)(((zc < 0 ? 0 : zc) * ny + y) * nx + x), zc >= 0 && x < nx, pol_stream);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
     }
@@ -98,7 +104,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d) {
-        double vv = ld_pred_hint(V + ((size_t)(p + A * d) * ny + y) * nx + x, x < nx, pol_keep);
+        double vv = ld_pred_hint(V + (unsigned)(((p + A * d) * ny + y) * nx + x), x < nx, pol_keep);
         X[d] = cscale(X[d], vv);
       }
       // forward transform of the elements p + A*d: pass 1 with the roles of A and B swapped
@@ -121,7 +127,7 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
 #pragma unroll
       for (int f = 0; f < A; ++f) {
         int zc = zc_index(T, p + B * f);
-        st_pred_hint(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, X[f], zc >= 0 && x < nx, pol_stream);
+        st_pred_hint(w2 + (unsigned)(((zc < 0 ? 0 : zc) * ny + y) * nx + x), X[f], zc >= 0 && x < nx, pol_stream);
       }
     }
   }
@@ -129,8 +135,10 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
 
 template <int A, int B>
 HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W2,
-                      cplx* __restrict__ cube, double scale, int L, int Lp, cplx* sm, Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+                      cplx* __restrict__ cube, double scale, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   const int nx = T.nx, ny = T.ny;
   cplx* bufA = sm;
   const int x0 = bid.x * L, y = bid.y;
@@ -143,7 +151,7 @@ HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const
 #pragma unroll
       for (int r = 0; r < A; ++r) {
         int zc = zc_index(T, p + B * r);
-        v[r] = ld_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx);
+        v[r] = ld_pred(w2 + (unsigned)(((zc < 0 ? 0 : zc) * ny + y) * nx + x), zc >= 0 && x < nx);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
     }
@@ -156,15 +164,17 @@ HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d)
-        st_pred(out + ((size_t)(p + A * d) * ny + y) * nx + x, cscale(X[d], scale), x < nx);
+        st_pred(out + (unsigned)(((p + A * d) * ny + y) * nx + x), cscale(X[d], scale), x < nx);
     }
   }
 }
 
 template <int A, int B>
 HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ cube,
-                        cplx* __restrict__ W2, int L, int Lp, cplx* sm, Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+                        cplx* __restrict__ W2, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   const int nx = T.nx, ny = T.ny;
   cplx* bufA = sm;
   const int x0 = bid.x * L, y = bid.y;
@@ -176,7 +186,7 @@ HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, con
       cplx v[A];
 #pragma unroll
       for (int r = 0; r < A; ++r)
-        v[r] = ld_pred(in + ((size_t)(p + B * r) * ny + y) * nx + x, x < nx);
+        v[r] = ld_pred(in + (unsigned)(((p + B * r) * ny + y) * nx + x), x < nx);
       pass1_store<A, B, -1>(v, p, line, bufA, Lp, tw);
     }
   }
@@ -189,7 +199,7 @@ HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, con
 #pragma unroll
       for (int d = 0; d < B; ++d) {
         int zc = zc_index(T, p + A * d);
-        st_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, X[d], zc >= 0 && x < nx);
+        st_pred(w2 + (unsigned)(((zc < 0 ? 0 : zc) * ny + y) * nx + x), X[d], zc >= 0 && x < nx);
       }
     }
   }
@@ -198,9 +208,11 @@ HD void reg_z_from_cube(const SphereTablesX& T, const cplx* __restrict__ tw, con
 // density: acc (double[n*L] after the two complex buffers) is owned element-wise by the pass-2 threads
 template <int A, int B>
 HD void reg_z_density(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W2,
-                      const double* __restrict__ wts, int nb, double* __restrict__ rho, int L, int Lp,
+                      const double* __restrict__ wts, int nb, double* __restrict__ rho, int L_rt, int Lp_rt,
                       cplx* sm, Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   const int nx = T.nx, ny = T.ny;
   cplx* bufA = sm;
   double* acc = (double*)(sm + 2 * (size_t)n * Lp);
@@ -216,7 +228,7 @@ HD void reg_z_density(const SphereTablesX& T, const cplx* __restrict__ tw, const
 #pragma unroll
         for (int r = 0; r < A; ++r) {
           int zc = zc_index(T, p + B * r);
-          v[r] = ld_pred(w2 + ((size_t)(zc < 0 ? 0 : zc) * ny + y) * nx + x, zc >= 0 && x < nx);
+          v[r] = ld_pred(w2 + (unsigned)(((zc < 0 ? 0 : zc) * ny + y) * nx + x), zc >= 0 && x < nx);
         }
         pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
       }
@@ -243,8 +255,10 @@ HD void reg_z_density(const SphereTablesX& T, const cplx* __restrict__ tw, const
 // ---------------------------------------------------------------------------------------------- y stages
 template <int A, int B>
 HD void reg_y_backward(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W1,
-                       cplx* __restrict__ W2, int L, int Lp, cplx* sm, Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+                       cplx* __restrict__ W2, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   const int nx = T.nx;
   cplx* bufA = sm;
   const int x0 = bid.x * L, izc = bid.y;
@@ -258,7 +272,7 @@ HD void reg_y_backward(const SphereTablesX& T, const cplx* __restrict__ tw, cons
 #pragma unroll
       for (int r = 0; r < A; ++r) {
         int c = pc.col(p + B * r);
-        v[r] = ld_pred(in + (size_t)(c < 0 ? 0 : c) * nx + x, c >= 0 && x < nx);
+        v[r] = ld_pred(in + (unsigned)((c < 0 ? 0 : c) * nx + x), c >= 0 && x < nx);
       }
       pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
     }
@@ -271,15 +285,17 @@ HD void reg_y_backward(const SphereTablesX& T, const cplx* __restrict__ tw, cons
       pass2_load<A, B, +1>(X, p, line, bufA, Lp);
 #pragma unroll
       for (int d = 0; d < B; ++d)
-        st_pred(out + (size_t)(p + A * d) * nx + x, X[d], x < nx);
+        st_pred(out + (unsigned)((p + A * d) * nx + x), X[d], x < nx);
     }
   }
 }
 
 template <int A, int B>
 HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W2,
-                      cplx* __restrict__ W1, int L, int Lp, cplx* sm, Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+                      cplx* __restrict__ W1, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   const int nx = T.nx;
   cplx* bufA = sm;
   const int x0 = bid.x * L, izc = bid.y;
@@ -292,7 +308,7 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
       cplx v[A];
 #pragma unroll
       for (int r = 0; r < A; ++r)
-        v[r] = ld_pred(in + (size_t)(p + B * r) * nx + x, x < nx);
+        v[r] = ld_pred(in + (unsigned)((p + B * r) * nx + x), x < nx);
       pass1_store<A, B, -1>(v, p, line, bufA, Lp, tw);
     }
   }
@@ -305,7 +321,7 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
 #pragma unroll
       for (int d = 0; d < B; ++d) {
         int c = pc.col(p + A * d);
-        st_pred(out + (size_t)(c < 0 ? 0 : c) * nx + x, X[d], c >= 0 && x < nx);
+        st_pred(out + (unsigned)((c < 0 ? 0 : c) * nx + x), X[d], c >= 0 && x < nx);
       }
     }
   }
@@ -315,8 +331,10 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
 // (contiguous axis: coalesced transposing load/store through shared memory)
 template <int A, int B>
 HD void reg_sphere_to_x(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ psi,
-                        int64_t ldpsi, cplx* __restrict__ W1, int L, int Lp, cplx* sm, Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+                        int64_t ldpsi, cplx* __restrict__ W1, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   cplx* bufA = sm;
   cplx* bufB = sm + (size_t)n * Lp;
   const int c0 = bid.x * L;
@@ -363,9 +381,11 @@ HD void reg_sphere_to_x(const SphereTablesX& T, const cplx* __restrict__ tw, con
 template <int A, int B>
 HD void reg_x_to_sphere(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W1,
                         cplx* __restrict__ out, int64_t ldout, double scale, const double* __restrict__ kin,
-                        const cplx* __restrict__ psi, int64_t ldpsi, int accumulate, int L, int Lp, cplx* sm,
+                        const cplx* __restrict__ psi, int64_t ldpsi, int accumulate, int L_rt, int Lp_rt, cplx* sm,
                         Dim3i bid) {
-  constexpr int n = A * B, TT = RegPair<A, B>::T;
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  (void)L_rt;
+  (void)Lp_rt;
   cplx* bufA = sm;
   cplx* bufB = sm + (size_t)n * Lp;
   const int c0 = bid.x * L;

@@ -141,7 +141,7 @@ struct EmuR : Emu {
     TX.pl_col0 = H.pl_col0.data();
     sm.resize(4 * (size_t)std::max(std::max(nx, ny), nz) * 33 + 64);
   }
-  static int Lof(int A, int B) { return (A > B ? A : B) >= 8 ? 16 : 32; }
+  static int Lof(int A, int B) { int T = A > B ? A : B; return T >= 12 ? 8 : (T >= 5 ? 16 : 32); }
   int to_planes(const cplx* psi, int nb) {
 #define CX(a, b) if (A_ == a && B_ == b) { int L = Lof(a, b), Lp = L + 1; done_ = true; \
     for (int bb = 0; bb < nb; ++bb) for (int bx = 0; bx < (T.n_cols + L - 1) / L; ++bx) \
