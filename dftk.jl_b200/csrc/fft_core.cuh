@@ -18,6 +18,17 @@
 #define TLOOP(t, n) for (int t = 0; t < (n); ++t)
 #define TSYNC() ((void)0)
 #endif
+// TLOOPC: thread loop with compile-time count and CTA size -> constant trip count, fully unrolled on the device
+// (all global loads of the iterations are issued before the first use); TLOOPU: runtime count, unrolled by 4.
+#if defined(__CUDA_ARCH__)
+#define TLOOPC(t, n, nthr)                                                        \
+  _Pragma("unroll") for (int i__ = 0; i__ < ((n) + (nthr)-1) / (nthr); ++i__)    \
+      for (int t = (int)threadIdx.x + i__ * (nthr), once__ = 1; once__ && t < (n); once__ = 0)
+#define TLOOPU(t, n) _Pragma("unroll 4") for (int t = threadIdx.x; t < (n); t += blockDim.x)
+#else
+#define TLOOPC(t, n, nthr) for (int t = 0; t < (n); ++t)
+#define TLOOPU(t, n) for (int t = 0; t < (n); ++t)
+#endif
 #define HD __host__ __device__ __forceinline__
 
 namespace dftk {

@@ -339,9 +339,9 @@ HD void reg_sphere_to_x(const SphereTablesX& T, const cplx* __restrict__ tw, con
   cplx* bufB = sm + (size_t)n * Lp;
   const int c0 = bid.x * L;
   const int64_t band = bid.y;
-  TLOOP(t, n * Lp) bufA[t] = make_double2(0.0, 0.0);
+  TLOOPC(t, n * Lp, L * TT) bufA[t] = make_double2(0.0, 0.0);
   TSYNC();
-  TLOOP(t, L * T.cnt_max) {
+  TLOOPU(t, L * T.cnt_max) {
     int line = t / T.cnt_max, i = t % T.cnt_max;
     int c = c0 + line;
     if (c < T.n_cols && i < T.col_cnt[c]) {
@@ -371,7 +371,7 @@ HD void reg_sphere_to_x(const SphereTablesX& T, const cplx* __restrict__ tw, con
   }
   TSYNC();
   cplx* out = W1 + (size_t)band * T.n_cols * n;
-  TLOOP(t, L * n) {
+  TLOOPC(t, L * n, L * TT) {
     int line = t / n, x = t % n;
     int c = c0 + line;
     if (c < T.n_cols) out[(size_t)c * n + x] = bufA[x * Lp + line];
@@ -391,7 +391,7 @@ HD void reg_x_to_sphere(const SphereTablesX& T, const cplx* __restrict__ tw, con
   const int c0 = bid.x * L;
   const int64_t band = bid.y;
   const cplx* in = W1 + (size_t)band * T.n_cols * n;
-  TLOOP(t, L * n) {
+  TLOOPC(t, L * n, L * TT) {
     int line = t / n, x = t % n;
     int c = c0 + line;
     bufA[x * Lp + line] = (c < T.n_cols) ? in[(size_t)c * n + x] : make_double2(0.0, 0.0);
@@ -417,7 +417,7 @@ HD void reg_x_to_sphere(const SphereTablesX& T, const cplx* __restrict__ tw, con
     }
   }
   TSYNC();
-  TLOOP(t, L * T.cnt_max) {
+  TLOOPU(t, L * T.cnt_max) {
     int line = t / T.cnt_max, i = t % T.cnt_max;
     int c = c0 + line;
     if (c < T.n_cols && i < T.col_cnt[c]) {
