@@ -347,9 +347,11 @@ def main():
     ap.add_argument("--cpu-bands", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--scf", action="store_true", help="also time one LOBPCG solve (first-SCF-step tolerance)")
+    ap.add_argument("--no-scf", dest="scf", action="store_false",
+                    help="skip the LOBPCG timing (eigensolver part of an SCF step, a few iterations)")
+    ap.set_defaults(scf=True)
     ap.add_argument("--scf-tol", type=float, default=0.025)
-    ap.add_argument("--scf-maxiter", type=int, default=30)
+    ap.add_argument("--scf-maxiter", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -47,6 +47,50 @@ static void with_staging(dftk_b200_ctx* ctx, const void* in, size_t in_bytes, vo
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
+// Host-resident psi/hpsi: overlap the PCIe copies with the kernels in chunks of bands (double buffered).
+static void apply_terms_host_pipelined(dftk_b200_kblock* kb, const cplx* psi_h, cplx* hpsi_h, int64_t n_bands,
+                                       bool loc, bool kinp, bool nl) {
+  dftk_b200_ctx* ctx = kb->grid->ctx;
+  if (!ctx->s_in) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  const int64_t chunk = std::min<int64_t>(n_bands, 128);
+  const size_t cbytes = (size_t)chunk * kb->n_pw * sizeof(cplx);
+  for (int i = 0; i < 2; ++i) {
+    ctx->pipe_in[i].ensure(cbytes);
+    ctx->pipe_out[i].ensure(cbytes);
+  }
+  int it = 0;
+  for (int64_t b0 = 0; b0 < n_bands; b0 += chunk, ++it) {
+    const int buf = it & 1;
+    const int64_t nb = std::min<int64_t>(chunk, n_bands - b0);
+    const size_t bytes = (size_t)nb * kb->n_pw * sizeof(cplx);
+    cplx* din = (cplx*)ctx->pipe_in[buf].p;
+    cplx* dout = (cplx*)ctx->pipe_out[buf].p;
+    // the input buffer may be overwritten once the compute that read it (two chunks ago) has finished
+    if (it >= 2) CUDA_CHECK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[buf], 0));
+    CUDA_CHECK(cudaMemcpyAsync(din, psi_h + b0 * kb->n_pw, bytes, cudaMemcpyHostToDevice, ctx->s_in));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_in[buf], ctx->s_in));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[buf], 0));
+    if (it >= 2) CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[buf], 0));   // output buffer drained
+    if (loc || kinp) kb_apply_local_kinetic(kb, din, dout, nb, loc, kinp, false);
+    else CUDA_CHECK(cudaMemsetAsync(dout, 0, bytes, ctx->stream));
+    if (nl) kb_apply_nonlocal(kb, din, dout, nb);
+    CUDA_CHECK(cudaEventRecord(ctx->ev_comp[buf], ctx->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[buf], 0));
+    CUDA_CHECK(cudaMemcpyAsync(hpsi_h + b0 * kb->n_pw, dout, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+    CUDA_CHECK(cudaEventRecord(ctx->ev_out[buf], ctx->s_out));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->s_out));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
 extern "C" {
 
 const char* dftk_b200_last_error(dftk_b200_ctx* ctx) {
@@ -111,6 +155,15 @@ int dftk_b200_ctx_destroy(dftk_b200_ctx* ctx) {
   if (!ctx) return DFTK_B200_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->s_in) {
+    cudaStreamDestroy(ctx->s_in);
+    cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 2; ++i) {
+      cudaEventDestroy(ctx->ev_in[i]);
+      cudaEventDestroy(ctx->ev_comp[i]);
+      cudaEventDestroy(ctx->ev_out[i]);
+    }
+  }
   if (ctx->nccl) ncclCommDestroy(ctx->nccl);
   if (ctx->cublas) cublasDestroy(ctx->cublas);
   if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
@@ -343,6 +396,10 @@ int dftk_b200_apply_terms(dftk_b200_kblock* kb, const void* psi, void* hpsi, int
   const bool loc = parts & 1, kinp = parts & 2, nl = parts & 4;
   REQUIRE(!kinp || kb->has_kin, "apply: kinetic energies were not given to kblock_create");
   size_t bytes = (size_t)kb->n_pw * n_bands * sizeof(cplx);
+  if (!accumulate && n_bands > 0 && !is_device_ptr(psi) && !is_device_ptr(hpsi)) {
+    apply_terms_host_pipelined(kb, (const cplx*)psi, (cplx*)hpsi, n_bands, loc, kinp, nl);
+    return DFTK_B200_OK;
+  }
   with_staging(ctx, psi, bytes, hpsi, bytes, accumulate != 0, [&](const void* i, void* o) {
     if (loc || kinp) kb_apply_local_kinetic(kb, (const cplx*)i, (cplx*)o, n_bands, loc, kinp, accumulate != 0);
     else if (!accumulate) CUDA_CHECK(cudaMemsetAsync(o, 0, bytes, ctx->stream));

@@ -100,6 +100,10 @@ struct dftk_b200_ctx {
   dftk::DevBuf<double> scal;     // small scalar scratch
   dftk::DevBuf<char> gemm_ws;    // split-K partials
   dftk::DevBuf<char> stage_in, stage_out;  // host<->device staging for host-buffer calls
+  // pipelined host staging (H2D of chunk k+1 || compute of chunk k || D2H of chunk k-1)
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  dftk::DevBuf<char> pipe_in[2], pipe_out[2];
 };
 
 namespace dftk {
