@@ -344,7 +344,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("DFTK_BENCH_WORKLOAD", "si250"), choices=list(WORKLOADS))
     ap.add_argument("--bands", type=int, default=0)
-    ap.add_argument("--cpu-bands", type=int, default=4)
+    ap.add_argument("--cpu-bands", type=int, default=0,
+                    help="bands in the CPU sample (0 = one per host thread, at most 32)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scf", dest="scf", action="store_false",
@@ -354,6 +355,8 @@ def main():
     ap.add_argument("--scf-maxiter", type=int, default=6)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.cpu_bands <= 0:
+        args.cpu_bands = max(4, min(32, os.cpu_count() or 4))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -303,6 +303,10 @@ int dftk_b200_kblock_create(dftk_b200_grid* grid, int64_t n_pw, const int64_t* m
     kb->d_pl_s1.upload(H.pl_s1.data(), H.pl_s1.size(), s);
     kb->d_pl_n1.upload(H.pl_n1.data(), H.pl_n1.size(), s);
     kb->d_pl_col0.upload(H.pl_col0.data(), H.pl_col0.size(), s);
+    kb->d_cx_s0.upload(H.cx_s0.data(), H.cx_s0.size(), s);
+    kb->d_cx_n0.upload(H.cx_n0.data(), H.cx_n0.size(), s);
+    kb->d_cx_s1.upload(H.cx_s1.data(), H.cx_s1.size(), s);
+    kb->d_cx_n1.upload(H.cx_n1.data(), H.cx_n1.size(), s);
     SphereTablesX& T = kb->T;
     T.nx = H.nx; T.ny = H.ny; T.nz = H.nz; T.n_pw = n_pw; T.n_cols = H.n_cols; T.cnt_max = H.cnt_max;
     T.n_zc = H.n_zc; T.col_start = kb->d_col_start.p; T.col_cnt = kb->d_col_cnt.p;
@@ -312,6 +316,7 @@ int dftk_b200_kblock_create(dftk_b200_grid* grid, int64_t n_pw, const int64_t* m
     T.ranges_ok = H.ranges_ok; T.z_s0 = H.z_s0; T.z_n0 = H.z_n0; T.z_s1 = H.z_s1; T.z_n1 = H.z_n1;
     T.pl_s0 = kb->d_pl_s0.p; T.pl_n0 = kb->d_pl_n0.p; T.pl_s1 = kb->d_pl_s1.p; T.pl_n1 = kb->d_pl_n1.p;
     T.pl_col0 = kb->d_pl_col0.p;
+    T.cx_s0 = kb->d_cx_s0.p; T.cx_n0 = kb->d_cx_n0.p; T.cx_s1 = kb->d_cx_s1.p; T.cx_n1 = kb->d_cx_n1.p;
     if (kin) {
       kb->kin.ensure(n_pw);
       CUDA_CHECK(cudaMemcpyAsync(kb->kin.p, kin, n_pw * sizeof(double), cudaMemcpyDefault, s));

@@ -180,7 +180,7 @@ void kb_sphere_to_planes(dftk_b200_kblock* kb, const cplx* psi, int64_t ldpsi, i
     const cplx* tw = (const cplx*)g->twx.p;
     cplx* W1 = kb->W1.p;
     void* args[] = {&kb->T, &tw, &psi, &ldpsi, &W1, &L, &Lp};
-    launch_ptr(ctx, g->rx->sphere_to_x, dim3(cdiv(kb->T.n_cols, L), nb), L * g->rx->T, reg_smem(g->rx), args);
+    launch_ptr(ctx, g->rx->sphere_to_x, dim3(cdiv(kb->T.n_cols, L), nb), L * g->rx->T, reg_smem(g->rx) + 5 * L * sizeof(int), args);
   } else {
     int L = g->Lx, Lp = L | 1;
     LAUNCH(ctx, k_sphere_to_x, dim3(cdiv(kb->T.n_cols, L), nb), FFT_THREADS, smem_for(g->nx, L), kb->T,
@@ -221,7 +221,7 @@ void kb_planes_to_sphere(dftk_b200_kblock* kb, cplx* out, int64_t ldout, int nb,
     const cplx* tw = (const cplx*)g->twx.p;
     const cplx* W1 = kb->W1.p;
     void* args[] = {&kb->T, &tw, &W1, &out, &ldout, &scale, &kin, &psi, &ldpsi, &accumulate, &L, &Lp};
-    launch_ptr(ctx, g->rx->x_to_sphere, dim3(cdiv(kb->T.n_cols, L), nb), L * g->rx->T, reg_smem(g->rx), args);
+    launch_ptr(ctx, g->rx->x_to_sphere, dim3(cdiv(kb->T.n_cols, L), nb), L * g->rx->T, reg_smem(g->rx) + 5 * L * sizeof(int), args);
   } else {
     int L = g->Lx, Lp = L | 1;
     LAUNCH(ctx, k_x_to_sphere, dim3(cdiv(kb->T.n_cols, L), nb), FFT_THREADS, smem_for(g->nx, L), kb->T,

@@ -93,6 +93,8 @@ struct SphereTablesHost {
   // ranges_ok == 0 means the structure does not hold and the kernels use the lookup tables.
   int ranges_ok = 0, z_s0 = 0, z_n0 = 0, z_s1 = 0, z_n1 = 0;
   std::vector<int> pl_s0, pl_n0, pl_s1, pl_n1, pl_col0;
+  // per column: sphere points are x in [cx_s0, +cx_n0) U [cx_s1, +cx_n1) in slot order (requires an ascending mapping)
+  std::vector<int> cx_s0, cx_n0, cx_s1, cx_n1;
 };
 
 // mapping: 0-based linear cube indices (x fastest) of the sphere coefficients, any order.
@@ -181,6 +183,16 @@ inline SphereTablesHost build_sphere_tables(int nx, int ny, int nz, int64_t n_pw
       for (int iy = 0; iy < ny; ++iy) yp[iy] = cm[iy] >= 0;
       ok = two_ranges(yp, T.pl_s0[p], T.pl_n0[p], T.pl_s1[p], T.pl_n1[p]);
       if (ok && T.pl_n0[p] > 0) T.pl_col0[p] = cm[T.pl_s0[p]];
+    }
+    // x ranges of every column; the register engine also assumes slot_src is the identity (ascending mapping)
+    T.cx_s0.assign(T.n_cols, 0); T.cx_n0.assign(T.n_cols, 0); T.cx_s1.assign(T.n_cols, 0); T.cx_n1.assign(T.n_cols, 0);
+    ok = ok && sorted;
+    std::vector<int> xp(nx);
+    for (int c = 0; c < T.n_cols && ok; ++c) {
+      std::fill(xp.begin(), xp.end(), 0);
+      for (int i = 0; i < T.col_cnt[c]; ++i) xp[T.slot_ix[T.col_start[c] + i]] = 1;
+      ok = two_ranges(xp, T.cx_s0[c], T.cx_n0[c], T.cx_s1[c], T.cx_n1[c]);
+      ok = ok && (T.cx_n0[c] + T.cx_n1[c] == T.col_cnt[c]);
     }
     T.ranges_ok = ok ? 1 : 0;
   }

@@ -329,6 +329,19 @@ HD void reg_y_forward(const SphereTablesX& T, const cplx* __restrict__ tw, const
 
 // ---------------------------------------------------------------------------------------------- x stages
 // (contiguous axis: coalesced transposing load/store through shared memory)
+// Column descriptors of the CTA's L columns, staged in shared memory: {first slot, n0, s0, n1, s1}
+HD void load_col_desc(const SphereTablesX& T, int c0, int L, int* cd) {
+  TLOOP(t, L) {
+    int c = c0 + t;
+    bool ok = c < T.n_cols;
+    cd[5 * t + 0] = ok ? T.col_start[c] : 0;
+    cd[5 * t + 1] = ok ? T.cx_n0[c] : 0;
+    cd[5 * t + 2] = ok ? T.cx_s0[c] : 0;
+    cd[5 * t + 3] = ok ? T.cx_n1[c] : 0;
+    cd[5 * t + 4] = ok ? T.cx_s1[c] : 0;
+  }
+}
+
 template <int A, int B>
 HD void reg_sphere_to_x(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ psi,
                         int64_t ldpsi, cplx* __restrict__ W1, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {
@@ -337,16 +350,20 @@ HD void reg_sphere_to_x(const SphereTablesX& T, const cplx* __restrict__ tw, con
   (void)Lp_rt;
   cplx* bufA = sm;
   cplx* bufB = sm + (size_t)n * Lp;
+  int* cd = (int*)(sm + 2 * (size_t)n * Lp);
   const int c0 = bid.x * L;
   const int64_t band = bid.y;
+  load_col_desc(T, c0, L, cd);
   TLOOPC(t, n * Lp, L * TT) bufA[t] = make_double2(0.0, 0.0);
   TSYNC();
-  TLOOPU(t, L * T.cnt_max) {
-    int line = t / T.cnt_max, i = t % T.cnt_max;
-    int c = c0 + line;
-    if (c < T.n_cols && i < T.col_cnt[c]) {
-      int s = T.col_start[c] + i;
-      bufA[T.slot_ix[s] * Lp + line] = psi[band * ldpsi + T.slot_src[s]];
+  // gather: TT threads per column walk its sphere points (contiguous in psi)
+  const cplx* pb = psi + band * ldpsi;
+  TLOOPC(t, L * n, L * TT) {
+    const int line = t / n, i = t % n;   // n is a compile-time constant
+    const int n0 = cd[5 * line + 1], n1 = cd[5 * line + 3];
+    if (i < n0 + n1) {
+      const int ix = i < n0 ? cd[5 * line + 2] + i : cd[5 * line + 4] + (i - n0);
+      bufA[ix * Lp + line] = pb[cd[5 * line] + i];
     }
   }
   TSYNC();
@@ -388,9 +405,11 @@ HD void reg_x_to_sphere(const SphereTablesX& T, const cplx* __restrict__ tw, con
   (void)Lp_rt;
   cplx* bufA = sm;
   cplx* bufB = sm + (size_t)n * Lp;
+  int* cd = (int*)(sm + 2 * (size_t)n * Lp);
   const int c0 = bid.x * L;
   const int64_t band = bid.y;
   const cplx* in = W1 + (size_t)band * T.n_cols * n;
+  load_col_desc(T, c0, L, cd);
   TLOOPC(t, L * n, L * TT) {
     int line = t / n, x = t % n;
     int c = c0 + line;
@@ -417,25 +436,27 @@ HD void reg_x_to_sphere(const SphereTablesX& T, const cplx* __restrict__ tw, con
     }
   }
   TSYNC();
-  TLOOPU(t, L * T.cnt_max) {
-    int line = t / T.cnt_max, i = t % T.cnt_max;
-    int c = c0 + line;
-    if (c < T.n_cols && i < T.col_cnt[c]) {
-      int s = T.col_start[c] + i;
-      int src = T.slot_src[s];
-      cplx v = cscale(bufA[T.slot_ix[s] * Lp + line], scale);
+  const cplx* pb = psi ? psi + band * ldpsi : nullptr;
+  cplx* ob = out + band * ldout;
+  TLOOPC(t, L * n, L * TT) {
+    const int line = t / n, i = t % n;
+    const int n0 = cd[5 * line + 1], n1 = cd[5 * line + 3];
+    if (i < n0 + n1) {
+      const int ix = i < n0 ? cd[5 * line + 2] + i : cd[5 * line + 4] + (i - n0);
+      const int s = cd[5 * line] + i;
+      cplx v = cscale(bufA[ix * Lp + line], scale);
       if (kin) {
-        cplx pp = psi[band * ldpsi + src];
-        double kk = kin[src];
+        cplx pp = pb[s];
+        double kk = kin[s];
         v.x += kk * pp.x;
         v.y += kk * pp.y;
       }
-      cplx* o = out + band * ldout + src;
       if (accumulate) {
-        v.x += o->x;
-        v.y += o->y;
+        cplx o = ob[s];
+        v.x += o.x;
+        v.y += o.y;
       }
-      *o = v;
+      ob[s] = v;
     }
   }
 }

@@ -7,6 +7,7 @@ struct SphereTablesX : SphereTables {
   // range form (see SphereTablesHost); ranges_ok == 0 => fall back to zc_of / colmap lookups
   int ranges_ok, z_s0, z_n0, z_s1, z_n1;
   const int *pl_s0, *pl_n0, *pl_s1, *pl_n1, *pl_col0;
+  const int *cx_s0, *cx_n0, *cx_s1, *cx_n1;   // per-column x ranges (slot order)
 };
 // plane index of wrapped z (or -1): pure arithmetic on the range form (no dependent global load).  The host only
 // selects the register engine for k-blocks whose tables have the range form (always true for a k-point sphere).

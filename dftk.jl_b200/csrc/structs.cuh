@@ -35,7 +35,8 @@ struct dftk_b200_kblock {
   double kweight;
   dftk::SphereTablesHost Th;
   dftk::SphereTablesX T;  // device view
-  dftk::DevBuf<int> d_col_start, d_col_cnt, d_slot_ix, d_slot_src, d_zlist, d_colmap, d_zc_of, d_pl_s0, d_pl_n0, d_pl_s1, d_pl_n1, d_pl_col0;
+  dftk::DevBuf<int> d_col_start, d_col_cnt, d_slot_ix, d_slot_src, d_zlist, d_colmap, d_zc_of, d_pl_s0, d_pl_n0, d_pl_s1, d_pl_n1, d_pl_col0, d_cx_s0, d_cx_n0, d_cx_s1,
+      d_cx_n1;
   dftk::DevBuf<double> kin;       // n_pw (may be empty)
   bool has_kin = false;
   dftk::DevBuf<dftk::cplx> P;     // n_pw x n_proj

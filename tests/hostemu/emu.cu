@@ -139,10 +139,12 @@ struct EmuR : Emu {
     TX.z_s0 = H.z_s0; TX.z_n0 = H.z_n0; TX.z_s1 = H.z_s1; TX.z_n1 = H.z_n1;
     TX.pl_s0 = H.pl_s0.data(); TX.pl_n0 = H.pl_n0.data(); TX.pl_s1 = H.pl_s1.data(); TX.pl_n1 = H.pl_n1.data();
     TX.pl_col0 = H.pl_col0.data();
+    TX.cx_s0 = H.cx_s0.data(); TX.cx_n0 = H.cx_n0.data(); TX.cx_s1 = H.cx_s1.data(); TX.cx_n1 = H.cx_n1.data();
     sm.resize(4 * (size_t)std::max(std::max(nx, ny), nz) * 33 + 64);
   }
   static int Lof(int A, int B) { int T = A > B ? A : B; return T >= 12 ? 8 : (T >= 5 ? 16 : 32); }
   int to_planes(const cplx* psi, int nb) {
+    if (!H.ranges_ok) return -9;   // the product falls back to the generic engine for such k-blocks
 #define CX(a, b) if (A_ == a && B_ == b) { int L = Lof(a, b), Lp = L + 1; done_ = true; \
     for (int bb = 0; bb < nb; ++bb) for (int bx = 0; bx < (T.n_cols + L - 1) / L; ++bx) \
       reg_sphere_to_x<a, b>(TX, tx(), psi, T.n_pw, W1.data(), L, Lp, sm.data(), Dim3i{bx, bb, 0}); }
@@ -198,6 +200,7 @@ int emur_sphere_to_real(int nx, int ny, int nz, int64_t n_pw, const int64_t* map
 int emur_real_to_sphere(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, const double* cube, int nb,
                         double scale, double* out) {
   EmuR e(nx, ny, nz, n_pw, mapping, nb);
+  if (!e.H.ranges_ok) return -9;
 #define CZ(a, b) if (A_ == a && B_ == b) { int L = EmuR::Lof(a, b), Lp = L + 1; done_ = true; \
   for (int bb = 0; bb < nb; ++bb) for (int y = 0; y < ny; ++y) for (int bx = 0; bx < (nx + L - 1) / L; ++bx) \
     reg_z_from_cube<a, b>(e.TX, e.tz(), (const cplx*)cube, e.W2.data(), L, Lp, e.sm.data(), Dim3i{bx, y, bb}); }

@@ -268,3 +268,21 @@ def test_host_buffer_pipeline_many_bands(si):
     # device-resident result of the same call must be identical (same kernels, same order)
     dev = kb.apply_h(torch.from_numpy(psi).to(kb.ctx.device)).cpu().numpy()
     np.testing.assert_allclose(out_pin.numpy(), dev, atol=1e-13 * np.abs(ref).max())
+
+
+def test_unsorted_mapping_falls_back(si):
+    """construct_from_equivalent_kpt (src/Kpoint.jl:44-56) yields mappings that are not ascending: the library
+    must still be exact (such k-blocks are routed to the generic FFT engine)."""
+    import dftk_b200
+    from gpu_common import to_dev, rand_psi, ctx
+    b, blk = si["b"], si["blk"]
+    kpt = blk.kpt
+    rng = np.random.default_rng(12)
+    perm = rng.permutation(kpt.n_G)
+    grid = dftk_b200.FFTGrid(ctx(), b.fft_size, b.model.unit_cell_volume)
+    kb = dftk_b200.KBlock(grid, kpt.mapping[perm], kin=blk.kin[perm])
+    kb.set_potential(to_dev(blk.Vtot))
+    psi = rand_psi(kpt.n_G, 3, seed=13)
+    ref = blk.local_apply(psi.T).T + blk.kin[None, :] * psi
+    out = kb.apply_terms(to_dev(psi[:, perm]), 3).cpu().numpy()
+    np.testing.assert_allclose(out, ref[:, perm], atol=1e-12 * np.abs(ref).max())
