@@ -151,6 +151,13 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
+    # Keep stdout clean for the single JSON line: C libraries (e.g. the NCCL version banner) write to fd 1.
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    # torchrun exports OMP_NUM_THREADS=1; cuSOLVER's heevd has host-side stages that want a few threads
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, min(16, (os.cpu_count() or 1) // max(1, world_env))))
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -331,7 +338,7 @@ def run_gpu(args):
                     block_applies_per_s=world * args.steps / (ms_total * 1e-3),
                     roofline=roofline, roofline_gemm=roofline_gemm, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches_timed,
                     clocks=clocks, setup_s=setup, **extra)
-        print(json.dumps(line), flush=True)
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
