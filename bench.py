@@ -29,6 +29,30 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+
+def effective_cpus():
+    """CPUs usable by this process (affinity and cgroup quota aware; os.cpu_count() reports the whole host)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return n
+
+
+# BLAS / OpenMP pools sized to the CPUs we may really use (must happen before numpy / torch are imported)
+_threads = max(1, effective_cpus() // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
+for _v in ("OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, str(_threads))
+if os.environ.get("OMP_NUM_THREADS") in (None, "1"):
+    os.environ["OMP_NUM_THREADS"] = str(min(16, _threads))
 import numpy as np
 
 A_SI = 10.26 / 2
@@ -122,7 +146,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = effective_cpus()
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     nb = args.cpu_bands
     t0 = time.time()
     ob, blk, psi = oracle_block(args.workload, nb, threads)
@@ -154,10 +179,8 @@ def run_gpu(args):
     # Keep stdout clean for the single JSON line: C libraries (e.g. the NCCL version banner) write to fd 1.
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
-    # torchrun exports OMP_NUM_THREADS=1; cuSOLVER's heevd has host-side stages that want a few threads
-    world_env = int(os.environ.get("WORLD_SIZE", "1"))
-    if os.environ.get("OMP_NUM_THREADS", "1") == "1":
-        os.environ["OMP_NUM_THREADS"] = str(max(1, min(16, (os.cpu_count() or 1) // max(1, world_env))))
+    # (thread pools were sized at import time: torchrun's OMP_NUM_THREADS=1 starves cuSOLVER's heevd host stages,
+    #  an unset value oversubscribes CPU-quota containers)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -299,7 +322,7 @@ def run_gpu(args):
     # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
     if rank == 0 and not args.no_cpu:
-        threads = os.cpu_count() or 1
+        threads = effective_cpus()
         nb = args.cpu_bands
         P = kb_P = None
         from oracle.terms import HamiltonianBlock
@@ -363,7 +386,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.cpu_bands <= 0:
-        args.cpu_bands = max(4, min(32, os.cpu_count() or 4))
+        args.cpu_bands = max(4, min(32, effective_cpus()))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -3,6 +3,36 @@
 The package directory is `dftk.jl_b200/`; import it as `dftk_b200` (see dftk_b200.py at the repo root).
 Names follow the reference (Model, PlaneWaveBasis, self_consistent_field, HamiltonianBlock, ...).
 """
+import os as _os
+
+
+def effective_cpus():
+    """CPUs this process may actually use: min(affinity mask, cgroup v2/v1 CPU quota, os.cpu_count())."""
+    n = _os.cpu_count() or 1
+    try:
+        n = min(n, len(_os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return n
+
+
+# cuSOLVER's Zheevd (Rayleigh-Ritz of LOBPCG) has OpenMP host stages: an unset OMP_NUM_THREADS means one thread per
+# *visible* core, which oversubscribes containers with a CPU quota by 8x and makes heevd 10x slower (measured).
+if "OMP_NUM_THREADS" not in _os.environ:
+    _os.environ["OMP_NUM_THREADS"] = str(max(1, min(16, effective_cpus() // max(1, int(_os.environ.get("LOCAL_WORLD_SIZE", "1"))))))
+
 from . import _lib
 from ._lib import DftkB200Error, LIB_PATH
 from .device import Context, FFTGrid, KBlock
