@@ -51,6 +51,7 @@ def effective_cpus():
 _threads = max(1, effective_cpus() // max(1, int(os.environ.get("WORLD_SIZE", "1"))))
 for _v in ("OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
     os.environ.setdefault(_v, str(_threads))
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # spinning OpenMP workers starve cuSOLVER's host stages (see dftk_b200/__init__.py)
 if os.environ.get("OMP_NUM_THREADS") in (None, "1"):
     os.environ["OMP_NUM_THREADS"] = str(min(16, _threads))
 import numpy as np
