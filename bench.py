@@ -311,6 +311,8 @@ def run_gpu(args):
     # ---- one LOBPCG solve at loose tolerance = the eigensolver part of the first SCF step (optional)
     if args.scf:
         X = psi.clone()
+        kb.lobpcg(X, tol=args.scf_tol, maxiter=1, n_conv_check=M - 3)   # untimed: cuSOLVER handles, 23 GB workspace
+        X.copy_(psi)
         torch.cuda.synchronize()
         t = time.perf_counter()
         res = kb.lobpcg(X, tol=args.scf_tol, maxiter=args.scf_maxiter, n_conv_check=M - 3)

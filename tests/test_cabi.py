@@ -62,6 +62,9 @@ def test_product_does_not_import_oracle():
 def test_sm100a_code_and_dmma_in_library(built):
     out = subprocess.run(["cuobjdump", "-lelf", built], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4dftk10k_zgemm_cnEPK7double2lS2_lPS0_llll", built],
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4dftk10k_zgemm_cnILi2EEEvPK7double2lS3_lPS1_lllli", built],
                           capture_output=True, text=True).stdout
     assert "DMMA" in sass and "LDGSTS" in sass      # FP64 tensor-core MMA fed by cp.async staging
+    # register two-pass FFT stage for the 192-point axis of the headline workload is in the library
+    elf = subprocess.run(["cuobjdump", "-elf", built], capture_output=True, text=True).stdout
+    assert "kr_z_applyILi12ELi16E" in elf
