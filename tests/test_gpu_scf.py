@@ -160,3 +160,20 @@ def test_iron_collinear_spin_matches_oracle():
         jk = [j for j, ok in enumerate(ob.kpoints) if ok.spin == kpt.spin and np.allclose(ok.coordinate, kpt.coordinate)][0]
         np.testing.assert_allclose(res["eigenvalues"][ik][:8], ores["eigenvalues"][jk][:8], atol=1e-6)
     assert np.linalg.norm(res["rho"].cpu().numpy() - ores["rho"]) * math.sqrt(basis.dvol) < 1e-6   # test/gpu.jl:73
+
+
+def test_supercell_identity():
+    # reference: test/supercell.jl:19-45 -- a Gamma-only 2x2x2 supercell equals the unit cell with a 2x2x2 k-grid
+    # (E_super = 8 E_unit to 1e-8 Ha per unit cell); exercises LOBPCG with 35 bands and in-order locking.
+    import dftk_b200 as dftk
+    Si = dftk.ElementPsp("Si")
+    unit = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), symmetries=False)
+    bu = dftk.PlaneWaveBasis(unit, Ecut=8, kgrid=(2, 2, 2), fft_size=(18, 18, 18))
+    ru = dftk.self_consistent_field(bu, tol=1e-9)
+    pos = [(np.asarray(p) + np.array([i, j, k])) / 2 for i in range(2) for j in range(2) for k in range(2) for p in POSITIONS]
+    sup = dftk.model_DFT(2 * LATTICE, [Si] * 16, pos, functionals=dftk.LDA(), symmetries=False)
+    bs = dftk.PlaneWaveBasis(sup, Ecut=8, kgrid=(1, 1, 1), fft_size=(36, 36, 36))
+    rs = dftk.self_consistent_field(bs, tol=1e-9)
+    assert rs["converged"] and ru["converged"]
+    assert abs(rs["energies"].total - 8 * ru["energies"].total) < 8e-8
+    assert abs(float(rs["rho"].sum() * bs.dvol) - 64.0) < 1e-9
