@@ -92,7 +92,6 @@ struct dftk_b200_ctx {
   int band_chunk = 0;     // 0 = auto
   int fft_engine = 0;     // 0 = register two-pass engine where a factor pair exists, 1 = generic Stockham (applies to grids created afterwards)
   int gemm_stages = 2;    // cp.async ring depth of the DMMA GEMMs (2 -> 4 CTAs/SM, 3 -> 2 CTAs/SM)
-  int fft_lines = 0;      // lines per CTA of the register FFT engine (0 = auto: 16, or 32 for short axes)
   int sm_count = 148;
   std::string last_error;
   dftk::DevBuf<char> solver_work;

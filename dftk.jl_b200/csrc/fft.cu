@@ -118,7 +118,6 @@ void reg_set_attributes() {
 // must match RegPair<A,B>::L (fft_reg.cuh)
 static inline int reg_L(const RegKernels* k) { return k->T >= 12 ? 8 : (k->T >= 5 ? 16 : 32); }
 static inline size_t reg_smem(const RegKernels* k) { return 2 * (size_t)k->A * k->B * (reg_L(k) + 1) * sizeof(cplx); }
-void reg_set_lines(int) {}
 static void launch_ptr(dftk_b200_ctx* ctx, const void* f, dim3 grid, int threads, size_t smem, void** args) {
   CUDA_CHECK(cudaLaunchKernel(f, grid, dim3(threads), args, smem, ctx->stream));
   ctx->launches++;

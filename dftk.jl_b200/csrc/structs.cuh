@@ -13,7 +13,6 @@ struct RegKernels {
 };
 const RegKernels* reg_kernels_for(int n);   // nullptr: use the generic Stockham engine
 void reg_set_attributes();
-void reg_set_lines(int L);
 }  // namespace dftk
 
 struct dftk_b200_grid {

@@ -55,8 +55,7 @@ def timeit(fn, n=3, warm=1):
 
 
 res = {}
-for lines in (16, 8):
-    ctx.set_option("fft_lines", lines)
+for lines in (0,):
     for chunk in (16, 51):
         ctx.set_option("band_chunk", chunk)
         nb = 153
@@ -65,7 +64,6 @@ for lines in (16, 8):
         res[f"local_kin_L{lines}_chunk{chunk}"] = dict(ms=t, us_per_band=t * 1e3 / nb, GBs_alg=bytes_alg / t / 1e6)
         print("L", lines, "chunk", chunk, res[f"local_kin_L{lines}_chunk{chunk}"], flush=True)
 ctx.set_option("band_chunk", 0)
-ctx.set_option("fft_lines", int(os.environ.get("FFT_LINES", 0)))
 for backend in (0, 2, 1):
     ctx.set_option("gemm_backend", 1 if backend == 1 else 0)
     ctx.set_option("gemm_stages", 3 if backend == 2 else 2)
