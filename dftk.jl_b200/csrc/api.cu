@@ -538,6 +538,30 @@ int dftk_b200_allgather(dftk_b200_ctx* ctx, const void* send, void* recv, int64_
   API_END(ctx)
 }
 
+// ------------------------------------------------------------------ SCF plumbing next to the hot path
+int dftk_b200_xc_evaluate(dftk_b200_ctx* ctx, int functional_mask, int n_spin, int64_t n_points, const double* rho,
+                          const double* sigma, double* e, double* vrho, double* vsigma) {
+  API_BEGIN
+  REQUIRE(ctx && rho && e && vrho && n_points >= 0, "xc_evaluate: NULL argument");
+  const bool gga = (functional_mask & (8 | 16)) != 0;
+  REQUIRE(!gga || (sigma && vsigma), "xc_evaluate: GGA functionals need sigma and vsigma");
+  REQUIRE((functional_mask & ~31) == 0 && functional_mask != 0, "xc_evaluate: unknown functional bits");
+  REQUIRE(is_device_ptr(rho) && is_device_ptr(e) && is_device_ptr(vrho), "xc_evaluate: arrays must be device memory");
+  xc_evaluate(ctx, functional_mask, n_spin, gga, n_points, rho, sigma, e, vrho, vsigma);
+  API_END(ctx)
+}
+
+int dftk_b200_symmetrize_fourier(dftk_b200_grid* grid, const void* rho_fourier_in, void* rho_fourier_out,
+                                 int n_sym, const int32_t* invS, const double* tau) {
+  dftk_b200_ctx* ctx = grid ? grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(grid && rho_fourier_in && rho_fourier_out && invS && tau && n_sym >= 1, "symmetrize_fourier: bad argument");
+  REQUIRE(rho_fourier_in != rho_fourier_out, "symmetrize_fourier: in and out must not alias");
+  REQUIRE(is_device_ptr(rho_fourier_in) && is_device_ptr(rho_fourier_out), "symmetrize_fourier: arrays must be device memory");
+  symmetrize_fourier(grid, (const cplx*)rho_fourier_in, (cplx*)rho_fourier_out, n_sym, (const int*)invS, tau);
+  API_END(ctx)
+}
+
 // ------------------------------------------------------------------ dense helpers
 int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,
                               int64_t n_cols, void* out_host) {

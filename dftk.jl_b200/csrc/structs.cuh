@@ -78,6 +78,11 @@ void kin_dots(dftk_b200_ctx* ctx, const cplx* X, int64_t ldx, const double* kin,
               int64_t n_cols, double* out_dev);
 void scale_kin_add(dftk_b200_ctx* ctx, const cplx* psi, cplx* hpsi, const double* kin, int64_t n_rows,
                    int64_t n_cols, int accumulate);
+// xc.cu
+void xc_evaluate(dftk_b200_ctx* ctx, int mask, int n_spin, bool gga, int64_t N, const double* rho,
+                 const double* sigma, double* e, double* vrho, double* vsigma);
+void symmetrize_fourier(dftk_b200_grid* g, const cplx* in, cplx* out, int n_sym, const int* invS_host,
+                        const double* tau_host);
 // lobpcg.cu
 int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter, int maxiter,
                int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host,

@@ -23,25 +23,22 @@ def compute_density(basis, psi, occupation, *, occupation_threshold=0.0):
 
 
 def symmetrize_rho(basis, rho):
-    """symmetry.jl:340-357 with do_lowpass=false: average over the basis symmetries in Fourier space."""
+    """symmetry.jl:340-357 with do_lowpass=false: average over the basis symmetries in Fourier space
+    (one fused gather kernel over all symmetry operations, dftk_b200_symmetrize_fourier)."""
+    from ._lib import check
+    from .device import _ptr
     syms = basis.symmetries
     if all(s.isone() for s in syms):
         return rho
     if not hasattr(basis, "_sym_tables"):
-        tabs = []
-        Gf = basis.G_vectors.to(torch.float64)
-        for s in syms:
-            invS = torch.as_tensor(np.rint(np.linalg.inv(s.S)), device=rho.device, dtype=torch.float64)
-            idx = basis.index_G_vectors((Gf @ invS.T).round().to(torch.int64))   # (no int64 matmul on CUDA)
-            phase = None
-            if np.any(np.abs(s.tau) > 1e-12):
-                ph = -2 * math.pi * (Gf @ torch.as_tensor(s.tau, device=rho.device))
-                phase = torch.polar(torch.ones_like(ph), ph)
-            tabs.append((idx.clamp_min(0), idx >= 0, phase))
-        basis._sym_tables = tabs
-    rf = basis.fft(rho)
-    acc = torch.zeros_like(rf)
-    for idx, ok, phase in basis._sym_tables:
-        val = torch.where(ok[None, :], rf[:, idx], torch.zeros_like(rf))
-        acc += val if phase is None else val * phase[None, :]
-    return basis.irfft(acc / len(syms))
+        invS = np.ascontiguousarray(np.stack([np.rint(np.linalg.inv(s.S)).astype(np.int32) for s in syms]))
+        tau = np.ascontiguousarray(np.stack([np.where(np.abs(s.tau) > 1e-12, s.tau, 0.0) for s in syms]))
+        basis._sym_tables = (invS, tau)
+    invS, tau = basis._sym_tables
+    rf = basis.fft(rho).contiguous()
+    out = torch.empty_like(rf)
+    ctx = basis.architecture.ctx
+    for sp in range(rho.shape[0]):
+        check(ctx.L.dftk_b200_symmetrize_fourier(basis.fft_grid.h, _ptr(rf[sp]), _ptr(out[sp]), len(syms),
+                                                 _ptr(invS), _ptr(tau)), ctx.h)
+    return basis.irfft(out)

@@ -261,7 +261,7 @@ class TermXc:
                 sigma = (grad[0] * grad[0]).sum(dim=0)[None, :]
             else:
                 sigma = torch.stack([(grad[0] * grad[0]).sum(0), (grad[0] * grad[1]).sum(0), (grad[1] * grad[1]).sum(0)])
-        e, vr, vs = xcmod.evaluate(self.functionals, rho, sigma)
+        e, vr, vs = xcmod.evaluate(basis.architecture.ctx, self.functionals, rho, sigma)
         E = float(e.sum() * basis.dvol)
         pot = vr.clone()
         if is_gga:

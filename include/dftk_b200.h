@@ -116,6 +116,19 @@ int dftk_b200_allreduce(dftk_b200_ctx* ctx, void* buf /*dev*/, int64_t count, in
 int dftk_b200_allgather(dftk_b200_ctx* ctx, const void* send /*dev*/, void* recv /*dev*/,
                         int64_t count_per_rank, int dtype);
 
+/* ---- SCF plumbing next to the hot path ----
+ * Pointwise exchange-correlation (replaces the Libxc dispatch, ext/DFTKCUDAExt.jl:17-25, src/terms/xc.jl:104-113).
+ * functional_mask: 1 lda_x | 2 lda_c_vwn | 4 lda_c_pw | 8 gga_x_pbe | 16 gga_c_pbe.  Arrays are component-major
+ * device doubles: rho[n_spin][n], sigma[1|3][n] (uu, ud, dd; GGA only), e[n] (energy per volume),
+ * vrho[n_spin][n], vsigma[1|3][n] -- the quantities libxc returns as zk*rho, vrho, vsigma. */
+int dftk_b200_xc_evaluate(dftk_b200_ctx* ctx, int functional_mask, int n_spin, int64_t n_points,
+                          const double* rho, const double* sigma, double* e, double* vrho, double* vsigma);
+/* accumulate_over_symmetries! + normalisation (src/symmetry.jl:282-327,340-357) on Fourier coefficients of the cube:
+ * out[G] = 1/n_sym * sum_s exp(-2 pi i G.tau_s) in[S_s^-1 G]  (terms outside the FFT box dropped).
+ * invS: n_sym row-major 3x3 integer matrices (host), tau: n_sym fractional translations (host). */
+int dftk_b200_symmetrize_fourier(dftk_b200_grid* grid, const void* rho_fourier_in, void* rho_fourier_out,
+                                 int n_sym, const int32_t* invS, const double* tau);
+
 /* ---- small dense helpers used by the host driver (columnwise_dots, src/common/linalg.jl:2-15) ---- */
 int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,
                               int64_t n_cols, void* out_host /*complex[n_cols]*/);

@@ -221,3 +221,26 @@ int emur_density(int nx, int ny, int nz, int64_t n_pw, const int64_t* mapping, c
   return 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// XC functionals and density symmetrisation (xc_core.cuh) on the host
+// ------------------------------------------------------------------------------------------------
+#include "../../dftk.jl_b200/csrc/xc_core.cuh"
+extern "C" {
+int emu_xc(int mask, int n_spin, int gga, int64_t N, const double* rho, const double* sigma, double* e, double* vrho,
+           double* vsigma) {
+  for (int64_t i = 0; i < N; ++i) {
+    if (n_spin == 1 && !gga) xc_eval_range<1, false>(mask, i, N, rho, sigma, e, vrho, vsigma);
+    else if (n_spin == 2 && !gga) xc_eval_range<2, false>(mask, i, N, rho, sigma, e, vrho, vsigma);
+    else if (n_spin == 1 && gga) xc_eval_range<1, true>(mask, i, N, rho, sigma, e, vrho, vsigma);
+    else if (n_spin == 2 && gga) xc_eval_range<2, true>(mask, i, N, rho, sigma, e, vrho, vsigma);
+    else return -1;
+  }
+  return 0;
+}
+int emu_symmetrize(int nx, int ny, int nz, const double* in, double* out, int n_sym, const int* invS, const double* tau) {
+  for (int64_t i = 0; i < (int64_t)nx * ny * nz; ++i)
+    symmetrize_point(i, nx, ny, nz, (const cplx*)in, (cplx*)out, n_sym, invS, tau);
+  return 0;
+}
+}

@@ -286,3 +286,47 @@ def test_unsorted_mapping_falls_back(si):
     ref = blk.local_apply(psi.T).T + blk.kin[None, :] * psi
     out = kb.apply_terms(to_dev(psi[:, perm]), 3).cpu().numpy()
     np.testing.assert_allclose(out, ref[:, perm], atol=1e-12 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n_spin", [1, 2])
+@pytest.mark.parametrize("funs", [("lda_x", "lda_c_vwn"), ("lda_x", "lda_c_pw"), ("gga_x_pbe", "gga_c_pbe")])
+def test_xc_kernel_matches_oracle(n_spin, funs):
+    from dftk_b200 import xc as pxc
+    from gpu_common import ctx, to_dev
+    from oracle import xc as oxc
+    rng = np.random.default_rng(21)
+    N = 5000
+    rho = rng.random((n_spin, N)) * 0.4 + 1e-6
+    rho[:, :5] = 0.0
+    gga = funs[0].startswith("gga")
+    sigma = None
+    if gga:
+        sigma = rng.random((1 if n_spin == 1 else 3, N)) * 0.02
+        if n_spin == 2:
+            sigma[1] = np.sqrt(sigma[0] * sigma[2]) * rng.uniform(-1, 1, N)
+    e, vr, vs = pxc.evaluate(ctx(), list(funs), to_dev(rho), None if sigma is None else to_dev(sigma))
+    ref = oxc.evaluate(list(funs), rho, sigma)
+    np.testing.assert_allclose(e.cpu().numpy(), ref["e"], rtol=1e-12, atol=1e-16)
+    np.testing.assert_allclose(vr.cpu().numpy(), ref["Vrho"], rtol=1e-11, atol=1e-14)
+    if gga:
+        np.testing.assert_allclose(vs.cpu().numpy(), ref["Vsigma"], rtol=1e-10, atol=1e-13)
+
+
+def test_symmetrize_kernel_matches_oracle():
+    """dftk_b200_symmetrize_fourier on aluminium fcc (192 operations, half of them with fractional translations)."""
+    import dftk_b200 as dftk
+    from oracle.basis import Element, Model, PlaneWaveBasis as OBasis
+    from oracle.scf import symmetrize_rho as osym
+    a = 7.65339
+    pos = [[0, 0, 0], [0, 0.5, 0.5], [0.5, 0, 0.5], [0.5, 0.5, 0]]
+    Al = dftk.ElementPsp("Al", functional="pbe")
+    model = dftk.model_DFT(a * np.eye(3), [Al] * 4, pos, functionals=dftk.PBE(), temperature=0.01)
+    basis = dftk.PlaneWaveBasis(model, Ecut=5, kgrid=(2, 2, 2))
+    om = Model(a * np.eye(3), [Element("Al", functional="pbe")] * 4, pos, functionals=("gga_x_pbe", "gga_c_pbe"),
+               temperature=0.01)
+    ob = OBasis(om, 5, kgrid=(2, 2, 2))
+    assert len(basis.symmetries) == len(ob.symmetries) == 192 and basis.fft_size == ob.fft_size
+    rng = np.random.default_rng(3)
+    rho = rng.random((1, ob.N))
+    out = dftk.symmetrize_rho(basis, torch.from_numpy(rho).to(basis.architecture.device)).cpu().numpy()
+    np.testing.assert_allclose(out, osym(ob, rho), atol=1e-13)
