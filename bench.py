@@ -254,8 +254,13 @@ def run_gpu(args):
     hbm_peak, peak_src = peaks()
     alg_bytes_band = 72.0 * N + 40.0 * n_pw
     ach = alg_bytes_band * M / (ms_local * 1e-3) / 1e9
+    # measured DRAM traffic of the group (dram__bytes_read.sum + dram__bytes_write.sum over the five kernels of one
+    # `ncu --set full` capture, profiles/ncu_full_r1.csv: 17.11 GB per 51-band launch on the 192^3 grid), scaled to the
+    # block like `achieved`; only known for the profiled workload
+    traffic = 335.49e6 * M if args.workload == "si250" else None
     roofline = dict(bound="hbm", kernel="Hpsi-local group (kr_sphere_to_x, kr_y_backward, kr_z_apply, kr_y_forward, kr_x_to_sphere)",
-                    achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=None,
+                    achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=traffic,
+                    traffic_source="profiles/ncu_full_r1.csv" if traffic else None,
                     algorithmic_bytes_per_band=alg_bytes_band, ms_per_block=ms_local, us_per_band=1e3 * ms_local / M,
                     peak_source=peak_src + " (of measured)")
     n_proj = kb.n_proj
