@@ -343,6 +343,28 @@ def run_gpu(args):
         extra["scf"] = dict(step_seconds=scf_t, lobpcg_iters_per_step=scf_it, total_s=time.perf_counter() - t,
                             energy_per_atom=res["energies"].total / len(pos), last_drho=res["history_drho"][-1],
                             note="step 1 starts from random orbitals (loose AdaptiveDiagtol tolerance), later steps from the previous orbitals")
+        # ---- Hellmann-Feynman forces of that state: local (one cube pass per atom), nonlocal (four
+        #      DMMA projections per k-block), Ewald (host)
+        try:
+            from dftk_b200 import forces as fmod
+            ft = {}
+            for name, fn in (("local", lambda: fmod.forces_local(basis, res["rho"])),
+                             ("nonlocal", lambda: fmod.forces_nonlocal(basis, res["psi"], res["occupation"]))):
+                fn()
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                f = fn()
+                torch.cuda.synchronize()
+                ft[name + "_s"] = time.perf_counter() - t
+                ft[name + "_max_abs"] = float(np.abs(np.array(f)).max())
+            t = time.perf_counter()
+            fmod.energy_forces_ewald(lat, [4.0] * len(pos), pos)
+            ft["ewald_host_s"] = time.perf_counter() - t
+            nbf = int(np.count_nonzero(res["occupation"][0]))
+            ft["nonlocal_TFLOPs"] = 4 * 8.0 * n_pw * kb.n_proj * nbf / ft["nonlocal_s"] / 1e12
+            extra["forces"] = ft
+        except Exception as e:      # never lose the headline line to the optional section
+            extra["forces"] = dict(error=repr(e))
         psi = torch.view_as_complex(torch.randn(M, n_pw, 2, generator=g, device=dev, dtype=torch.float64))
         kb.set_potential(blk.local_op.potential)     # the SCF installed its own potentials; restore the benchmark operator
 

@@ -44,6 +44,8 @@ SIGNATURES = {
     "dftk_b200_allgather": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int]),
     "dftk_b200_xc_evaluate": (c_int, [c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dftk_b200_symmetrize_fourier": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "dftk_b200_local_forces": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
+    "dftk_b200_nonlocal_force_rows": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dftk_b200_columnwise_dots": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "dftk_b200_zgemm": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp,
                                 c_vp, c_i64]),

@@ -562,6 +562,29 @@ int dftk_b200_symmetrize_fourier(dftk_b200_grid* grid, const void* rho_fourier_i
   API_END(ctx)
 }
 
+// ------------------------------------------------------------------ forces
+int dftk_b200_local_forces(dftk_b200_grid* grid, const void* w, int n_atoms, const double* positions,
+                           double* forces_host) {
+  dftk_b200_ctx* ctx = grid ? grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(grid && w && n_atoms >= 0 && (n_atoms == 0 || (positions && forces_host)), "local_forces: bad argument");
+  REQUIRE(is_device_ptr(w), "local_forces: w must be device memory");
+  REQUIRE(!is_device_ptr(forces_host), "local_forces: forces are returned in host memory");
+  local_forces(grid, (const cplx*)w, n_atoms, positions, forces_host);
+  API_END(ctx)
+}
+
+int dftk_b200_nonlocal_force_rows(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host, int64_t n_bands,
+                                  const double* gpk, double* rows_host) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && psi && occ_w_host && gpk && rows_host && n_bands >= 0, "nonlocal_force_rows: bad argument");
+  REQUIRE(is_device_ptr(gpk), "nonlocal_force_rows: gpk must be device memory");
+  const cplx* d = (const cplx*)stage_in(ctx, psi, (size_t)kb->n_pw * n_bands * sizeof(cplx), ctx->stage_in);
+  kb_nonlocal_force_rows(kb, d, occ_w_host, n_bands, gpk, rows_host);
+  API_END(ctx)
+}
+
 // ------------------------------------------------------------------ dense helpers
 int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,
                               int64_t n_cols, void* out_host) {

@@ -83,6 +83,10 @@ void xc_evaluate(dftk_b200_ctx* ctx, int mask, int n_spin, bool gga, int64_t N, 
                  const double* sigma, double* e, double* vrho, double* vsigma);
 void symmetrize_fourier(dftk_b200_grid* g, const cplx* in, cplx* out, int n_sym, const int* invS_host,
                         const double* tau_host);
+// forces.cu
+void local_forces(dftk_b200_grid* g, const cplx* w, int n_atoms, const double* pos_host, double* out_host);
+void kb_nonlocal_force_rows(dftk_b200_kblock* kb, const cplx* psi, const double* occ_w_host, int64_t n_bands,
+                            const double* gpk, double* out_host);
 // lobpcg.cu
 int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter, int maxiter,
                int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host,

@@ -129,6 +129,20 @@ int dftk_b200_xc_evaluate(dftk_b200_ctx* ctx, int functional_mask, int n_spin, i
 int dftk_b200_symmetrize_fourier(dftk_b200_grid* grid, const void* rho_fourier_in, void* rho_fourier_out,
                                  int n_sym, const int32_t* invS, const double* tau);
 
+/* ---- Hellmann-Feynman forces (compute_forces, src/postprocess/forces.jl:24-30) ----
+ * Local term (forces_local, src/terms/local.jl:152-181): for every atom of one species,
+ *   F_a,α = -Re( Σ_G -2πi G_α e^{-2πi G·r_a} w_G ),  w_G = conj(ρ_G) v_loc(|G|) / sqrt(Ω)  (device, N_fft complex),
+ * positions: 3·n_atoms fractional coordinates (host), forces_host: 3·n_atoms reduced-coordinate forces. */
+int dftk_b200_local_forces(dftk_b200_grid* grid, const void* w, int n_atoms, const double* positions,
+                           double* forces_host);
+/* Nonlocal term (compute_forces(::TermAtomicNonlocal), src/terms/nonlocal.jl:49-100) for one k-block: per projector
+ * row j and direction α the contribution  -Σ_n occ_w[n] 2 Re <ψ_n| P D (dP_j/dR_α)† |ψ_n>  with
+ * dP/dR_α = -2πi (G+k)_α P, obtained from four projections P†[ψ, p_x ψ, p_y ψ, p_z ψ] instead of the reference's
+ * 3·n_atoms full-height GEMM pairs.  gpk: 3 × n_pw reduced G+k components, component-major (device);
+ * rows_host: 3 × n_proj (α-major).  The caller sums the rows of each atom, allreduces over k and symmetrises. */
+int dftk_b200_nonlocal_force_rows(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host, int64_t n_bands,
+                                  const double* gpk, double* rows_host);
+
 /* ---- small dense helpers used by the host driver (columnwise_dots, src/common/linalg.jl:2-15) ---- */
 int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,
                               int64_t n_cols, void* out_host /*complex[n_cols]*/);

@@ -244,3 +244,31 @@ int emu_symmetrize(int nx, int ny, int nz, const double* in, double* out, int n_
   return 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Force bodies (forces_core.cuh) on the host
+// ------------------------------------------------------------------------------------------------
+#include "../../dftk.jl_b200/csrc/forces_core.cuh"
+extern "C" {
+int emu_local_forces(int nx, int ny, int nz, const double* w, int n_atoms, const double* pos, double* out) {
+  for (int a = 0; a < n_atoms; ++a) {
+    double acc[3] = {0, 0, 0};
+    for (int64_t i = 0; i < (int64_t)nx * ny * nz; ++i)
+      local_force_point(i, nx, ny, nz, (const cplx*)w, pos[3 * a], pos[3 * a + 1], pos[3 * a + 2], acc);
+    for (int c = 0; c < 3; ++c) out[3 * a + c] = -2.0 * FORCES_PI * acc[c];
+  }
+  return 0;
+}
+int emu_scale_by_momentum(int64_t n_rows, int64_t nb, const double* gpk, const double* psi, double* out) {
+  for (int a = 0; a < 3; ++a)
+    for (int64_t b = 0; b < nb; ++b)
+      for (int64_t i = 0; i < n_rows; ++i)
+        scale_by_momentum_point(i, b, a, n_rows, nb, gpk, (const cplx*)psi, n_rows, (cplx*)out);
+  return 0;
+}
+int emu_nonlocal_force_rows(int64_t np, int64_t nb, const double* dproj, const double* pa, const double* w, double* f) {
+  for (int a = 0; a < 3; ++a)
+    for (int64_t j = 0; j < np; ++j) nonlocal_force_row(j, a, np, nb, (const cplx*)dproj, (const cplx*)pa, w, f);
+  return 0;
+}
+}

@@ -154,3 +154,39 @@ def test_kpoint_comm_gloo_world2():
     occ, eF = compute_occupation(_FakeBasis(mm, [0.5, 0.5], dftk.KpointComm()), eig)
     assert out[0][1] == eF and out[1][1] == eF                      # bit-identical Fermi level on every rank
     assert out[0][2] == occ[0].tolist() and out[1][2] == occ[1].tolist()
+
+
+def test_ewald_forces_and_force_symmetrisation_match_oracle():
+    """Host-side pieces of compute_forces (ewald.jl:64-168, symmetry.jl:379-423) against the oracle."""
+    import dftk_b200 as dftk
+    from oracle import forces as oforces
+    from oracle.basis import Element, Model, PlaneWaveBasis
+    pos = [POSITIONS[0] + np.array([0.01, 0.02, -0.015]), POSITIONS[1] + np.array([0.0, -0.004, 0.003])]
+    e, f = dftk.energy_forces_ewald(LATTICE, [4, 4], pos)
+    eo, fo = oforces.energy_forces_ewald(LATTICE, [4, 4], pos)
+    assert e == pytest.approx(eo, abs=1e-12)
+    np.testing.assert_allclose(np.array(f), np.array(fo), atol=1e-12)
+    from dftk_b200.terms import energy_ewald
+    assert e == pytest.approx(energy_ewald(LATTICE, [4, 4], pos), abs=1e-12)
+    # a 3-atom, two-species cell exercises the chunked structure-factor loops
+    lat = np.diag([7.0, 8.0, 9.5])
+    p3 = [np.array([0.1, 0.2, 0.3]), np.array([0.55, 0.6, 0.1]), np.array([0.3, 0.9, 0.7])]
+    e, f = dftk.energy_forces_ewald(lat, [4, 3, 4], p3)
+    eo, fo = oforces.energy_forces_ewald(lat, [4, 3, 4], p3)
+    assert e == pytest.approx(eo, abs=1e-12)
+    np.testing.assert_allclose(np.array(f), np.array(fo), atol=1e-12)
+    assert np.abs(np.sum(np.array(f), axis=0)).max() < 1e-10            # translation invariance
+    # symmetrisation: silicon with one atom moved along [111] keeps 12 operations
+    shift = 0.003 * np.ones(3)
+    Si = dftk.ElementPsp("Si")
+    model = dftk.model_DFT(LATTICE, [Si, Si], [POSITIONS[0] + shift, POSITIONS[1]], functionals=dftk.LDA())
+    assert len(model.symmetries) == 12
+    om = Model(LATTICE, [Element("Si")] * 2, [POSITIONS[0] + shift, POSITIONS[1]])
+    ob = PlaneWaveBasis(om, 5, kgrid=(1, 1, 1), fft_size=(15, 15, 15))
+    rng = np.random.default_rng(0)
+    F = [rng.standard_normal(3), rng.standard_normal(3)]
+    got = dftk.symmetrize_forces(model, F, symmetries=model.symmetries)
+    want = oforces.symmetrize_forces(ob, F, symmetries=om.symmetries)
+    np.testing.assert_allclose(np.array(got), np.array(want), atol=1e-14)
+    np.testing.assert_allclose(got[0], got[0][0] * np.ones(3), atol=1e-14)
+    np.testing.assert_allclose(got[0], -got[1], atol=1e-14)

@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "hostemu", "libhostemu.so")
 def emu():
     src = os.path.join(HERE, "hostemu", "emu.cu")
     csrc = os.path.join(HERE, "..", "dftk.jl_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_radix_gen.cuh", "xc_core.cuh", "fft_reg_fwd.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_radix_gen.cuh", "xc_core.cuh", "forces_core.cuh", "fft_reg_fwd.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
                                "-Wno-deprecated-gpu-targets", "-o", SO, src])
@@ -153,3 +153,50 @@ def test_emulated_symmetrize_matches_oracle(emu):
     nx, ny, nz = b.fft_size
     assert emu.emu_symmetrize(nx, ny, nz, _p(rf), _p(out), len(b.symmetries), _p(invS), _p(tau)) == 0
     np.testing.assert_allclose(b.irfft_cube(out), ref, atol=1e-13)
+
+
+def test_emulated_force_bodies_match_oracle(emu):
+    """forces_core.cuh (local-potential forces; the four-projection form of the nonlocal forces) against the oracle's
+    restatement of local.jl:152-181 / nonlocal.jl:49-100 on a rattled silicon cell."""
+    import math
+    from oracle import forces as oforces
+    from oracle.psp_hgh import PspHgh
+    from oracle.terms import build_projection_vectors
+    si = Element("Si", PspHgh.from_table("Si", "lda"))
+    pos = [POSITIONS[0] + np.array([0.011, -0.007, 0.004]), POSITIONS[1] + np.array([-0.003, 0.009, 0.006])]
+    m = Model(LATTICE, [si, si], pos, symmetries=False)
+    b = PlaneWaveBasis(m, 5, fft_size=(15, 16, 18), kcoords=[[0.1, -0.2, 0.3], [0.0, 0.25, 0.5]], kweights=[0.4, 0.6])
+    rng = np.random.default_rng(11)
+    nx, ny, nz = b.fft_size
+    # local
+    rho = rng.random((1, b.N)) + 0.1
+    ref = np.array(oforces.forces_local(b, rho))
+    pn = np.sqrt(np.sum(b.G_cart ** 2, axis=1))
+    w = np.ascontiguousarray(np.conj(b.fft_cube(rho[0])) * si.psp.eval_local_fourier(pn) / math.sqrt(m.unit_cell_volume))
+    out = np.zeros((2, 3))
+    assert emu.emu_local_forces(nx, ny, nz, _p(w), 2, _p(np.ascontiguousarray(np.array(pos))), _p(out)) == 0
+    np.testing.assert_allclose(out, ref, rtol=1e-11, atol=1e-12)
+    # nonlocal
+    nb = 5
+    psi = [rng.standard_normal((k.n_G, nb)) + 1j * rng.standard_normal((k.n_G, nb)) for k in b.kpoints]
+    occ = [rng.random(nb) * 2 for _ in b.kpoints]
+    refn = np.array(oforces.forces_nonlocal(b, psi, occ))
+    F = np.zeros((2, 3))
+    for ik, kpt in enumerate(b.kpoints):
+        P, D = build_projection_vectors(b, kpt)
+        n_proj = P.shape[1]
+        gpk = np.ascontiguousarray((kpt.G_vectors + kpt.coordinate).T.astype(float))        # (3, n_G)
+        psik = np.ascontiguousarray(psi[ik].T)                                              # (nb, n_G) = column-major n_G x nb
+        scaled = np.zeros((3 * nb, kpt.n_G), dtype=complex)
+        assert emu.emu_scale_by_momentum(ctypes.c_int64(kpt.n_G), ctypes.c_int64(nb), _p(gpk), _p(psik), _p(scaled)) == 0
+        np.testing.assert_array_equal(scaled.reshape(3, nb, -1), gpk[:, None, :] * psik[None])
+        proj = P.conj().T @ psi[ik]                                                         # (n_proj, nb)
+        dproj = np.ascontiguousarray((D @ proj).T)                                          # column-major n_proj x nb
+        pa = np.ascontiguousarray((P.conj().T @ scaled.T).T)                                # column-major n_proj x 3 nb
+        rows = np.zeros((3, n_proj))
+        wts = np.ascontiguousarray(occ[ik] * b.kweights[ik])
+        assert emu.emu_nonlocal_force_rows(ctypes.c_int64(n_proj), ctypes.c_int64(nb), _p(dproj), _p(pa), _p(wts), _p(rows)) == 0
+        per_atom = n_proj // 2
+        for ia in range(2):
+            F[ia] += rows[:, ia * per_atom:(ia + 1) * per_atom].sum(axis=1)
+    np.testing.assert_allclose(F, refn, rtol=1e-11, atol=1e-12)
