@@ -36,6 +36,24 @@ _os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 if "OMP_NUM_THREADS" not in _os.environ:
     _os.environ["OMP_NUM_THREADS"] = str(max(1, min(16, effective_cpus() // max(1, int(_os.environ.get("LOCAL_WORLD_SIZE", "1"))))))
 
+
+def _limit_openmp_team():
+    """The variables above are read when libgomp is loaded -- which `import torch` already does (through libcusolver).
+    If that happened before this package was imported, at least cap the team size through the runtime API (the wait
+    policy cannot be changed any more: import dftk_b200, or set OMP_WAIT_POLICY=passive, before torch for large
+    eigenproblems)."""
+    try:
+        import ctypes
+        g = ctypes.CDLL("libgomp.so.1")
+        want = int(_os.environ["OMP_NUM_THREADS"].split(",")[0])
+        if g.omp_get_max_threads() > want:
+            g.omp_set_num_threads(want)
+    except Exception:
+        pass
+
+
+_limit_openmp_team()
+
 from . import _lib
 from ._lib import DftkB200Error, LIB_PATH
 from .device import Context, FFTGrid, KBlock

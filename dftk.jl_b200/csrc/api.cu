@@ -201,6 +201,7 @@ int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
   if (n == "gemm_backend") ctx->gemm_backend = (int)value;
   else if (n == "band_chunk") ctx->band_chunk = (int)value;
   else if (n == "gemm_stages") ctx->gemm_stages = (value == 3 ? 3 : 2);
+  else if (n == "small_dense") ctx->small_dense = (int)value;
   else if (n == "fft_engine") ctx->fft_engine = (int)value;  // 0 = register two-pass where available, 1 = generic
   else throw Error(DFTK_B200_EINVAL, "set_option: unknown option " + n);
   API_END(ctx)

@@ -92,6 +92,8 @@ struct dftk_b200_ctx {
   int band_chunk = 0;     // 0 = auto
   int fft_engine = 0;     // 0 = register two-pass engine where a factor pair exists, 1 = generic Stockham (applies to grids created afterwards)
   int gemm_stages = 2;    // cp.async ring depth of the DMMA GEMMs (2 -> 4 CTAs/SM, 3 -> 2 CTAs/SM)
+  int small_dense = 1;    // LOBPCG with <= 32 bands: fused small-matrix kernels (lobpcg_small.cuh); 0 = GEMM + cuSOLVER path
+  dftk::DevBuf<int> small_counter;   // arrival counter of k_small_gram (kept at zero between launches)
   int sm_count = 148;
   std::string last_error;
   dftk::DevBuf<char> solver_work;

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <numeric>
 #include "structs.cuh"
+#include "lobpcg_small.cuh"
 
 namespace dftk {
 
@@ -220,6 +221,54 @@ __global__ void k_compute_lambda(const cplx* __restrict__ num, const cplx* __res
   lam[i] = (a.x * b.x + a.y * b.y) / d;
 }
 
+// ------------------------------------------------------------------ fused small-matrix path (lobpcg_small.cuh)
+extern __shared__ __align__(16) unsigned char small_dyn_smem[];
+
+// one launch per block-list Gram: CTA partials, the last CTA to finish sums them in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+k_small_gram(SmallMatList A, SmallMatList B, long long rows_per_cta, long long n_rows, int upper_only, cplx* ws, cplx* C,
+             long long ldc, unsigned* counter) {
+  small_gram_cta((int)blockIdx.x, rows_per_cta, n_rows, A, B, upper_only, ws, (cplx*)small_dyn_smem);
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    small_gram_reduce((int)gridDim.x, A, B, upper_only, ws, C, ldc);
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_small_blocks_times(SmallMatList Y, const cplx* cm, long long ldcm, int ncols, cplx* out, long long ldo, long long n_rows,
+                     double alpha, double beta) {
+  cplx* cs = (cplx*)small_dyn_smem;
+  const int ny = Y.start[Y.n];
+  for (int e = threadIdx.x; e < ny * ncols; e += blockDim.x) cs[e] = cm[e % ny + ldcm * (e / ny)];
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows) small_blocks_times_row(r, Y, cs, ny, ncols, out, ldo, alpha, beta);
+}
+
+__global__ void __launch_bounds__(128)
+k_small_rmul(cplx* X, long long ld, long long n_rows, int n, const cplx* invR, long long ldr) {
+  cplx* rs = (cplx*)small_dyn_smem;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) rs[e] = invR[e % n + ldr * (e / n)];
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rows) small_rmul_row(r, X, ld, n, rs, n);
+}
+
+__global__ void __launch_bounds__(SMALL_RED)
+k_small_chol(const cplx* O, long long ldo, int n, cplx* invR, long long ldi, double* stats) {
+  __shared__ cplx As[SMALL_MAX_N * SMALL_MAX_N], Bs[SMALL_MAX_N * SMALL_MAX_N];
+  __shared__ double red[SMALL_RED];
+  __shared__ int flag[2];
+  small_chol_cta(O, ldo, n, invR, ldi, stats, As, Bs, red, flag);
+}
+
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 // Optional section timing (env DFTK_B200_PROFILE=1): stream-synchronising wall clock per LOBPCG section.
@@ -254,9 +303,41 @@ struct SectionProf {
     acc.push_back({cur, dt});
     cur.clear();
   }
+  // DFTK_B200_PROFILE=2: accumulate over all solves of the process, print once at exit (small systems: hundreds of solves)
+  struct Global {
+    std::vector<std::pair<std::string, double>> acc;
+    long iters = 0, solves = 0;
+    ~Global() {
+      if (acc.empty()) return;
+      double tot = 0;
+      for (auto& a : acc) tot += a.second;
+      fprintf(stderr, "[dftk_b200 lobpcg profile, all solves] %ld solves, %ld iterations, %.3f s in sections\n", solves, iters, tot);
+      for (auto& a : acc) fprintf(stderr, "  %-22s %9.3f s  %5.1f %%\n", a.first.c_str(), a.second, 100 * a.second / tot);
+    }
+  };
+  static Global& global() {
+    static Global g;
+    return g;
+  }
+  bool aggregate = false;
   void report(int niter) {
     if (!on) return;
     end();
+    if (aggregate) {
+      Global& g = global();
+      g.iters += niter;
+      g.solves++;
+      for (auto& a : acc) {
+        bool found = false;
+        for (auto& b : g.acc)
+          if (b.first == a.first) {
+            b.second += a.second;
+            found = true;
+          }
+        if (!found) g.acc.push_back(a);
+      }
+      return;
+    }
     double tot = 0;
     for (auto& a : acc) tot += a.second;
     fprintf(stderr, "[dftk_b200 lobpcg profile] %d iterations, %.3f s in sections\n", niter, tot);
@@ -279,6 +360,56 @@ struct Lobpcg {
   cplx *G, *cX, *cP, *Ochol, *invR, *BYX, *tmpS;
   // big scratch
   cplx* tmpN;  // N x M
+  // fused small-matrix path (M <= SMALL_MAX_N): see lobpcg_small.cuh
+  bool small = false;
+  unsigned* d_counter = nullptr;
+
+  static SmallMatList mklist(const std::vector<Mat>& v) {
+    SmallMatList L{};
+    REQUIRE(v.size() >= 1 && v.size() <= 3, "small path: block list too long");
+    L.n = (int)v.size();
+    int off = 0;
+    for (int i = 0; i < 3; ++i) {
+      L.start[i] = off;
+      if (i < L.n) {
+        L.p[i] = v[i].p;
+        L.ld[i] = v[i].ld;
+        L.cols[i] = (int)v[i].cols;
+        off += (int)v[i].cols;
+      } else {
+        L.p[i] = nullptr;
+        L.ld[i] = 0;
+        L.cols[i] = 0;
+      }
+    }
+    L.start[3] = off;
+    for (int i = L.n; i < 4; ++i) L.start[i] = off;
+    REQUIRE(off <= SMALL_MAX_COLS, "small path: too many columns");
+    return L;
+  }
+  void small_gram(const std::vector<Mat>& A, const std::vector<Mat>& B, cplx* C, int64_t ldc, bool upper_only) {
+    SmallMatList LA = mklist(A), LB = mklist(B);
+    const int nA = LA.start[LA.n], nB = LB.start[LB.n];
+    if (nA == 0 || nB == 0) return;
+    const int64_t rows = A[0].rows;
+    int64_t n_ctas = std::max<int64_t>(1, std::min<int64_t>((rows + 127) / 128, 2 * (int64_t)ctx->sm_count));
+    int64_t rpc = (rows + n_ctas - 1) / n_ctas;
+    rpc = (rpc + SMALL_TR - 1) / SMALL_TR * SMALL_TR;
+    n_ctas = std::max<int64_t>(1, (rows + rpc - 1) / rpc);
+    cplx* ws = (cplx*)ctx->gemm_ws.ensure((size_t)n_ctas * nA * nB * sizeof(cplx));
+    const size_t smem = (size_t)SMALL_TR * (nA + nB) * sizeof(cplx);
+    LAUNCH(ctx, k_small_gram, (unsigned)n_ctas, 256, smem, LA, LB, (long long)rpc, (long long)rows, upper_only ? 1 : 0, ws,
+           C, (long long)ldc, d_counter);
+  }
+  void small_blocks_times(const std::vector<Mat>& Y, const cplx* c, int64_t ldc, int64_t ncols, Mat out, double alpha,
+                          double beta) {
+    if (ncols == 0 || out.rows == 0) return;
+    REQUIRE(ncols <= SMALL_MAX_N, "small path: too many output columns");
+    SmallMatList LY = mklist(Y);
+    const int ny = LY.start[LY.n];
+    LAUNCH(ctx, k_small_blocks_times, (unsigned)((out.rows + 127) / 128), 128, (size_t)ny * ncols * sizeof(cplx), LY, c,
+           (long long)ldc, (int)ncols, out.p, (long long)out.ld, (long long)out.rows, alpha, beta);
+  }
 
   void copy2d(Mat dst, Mat src) {
     if (src.rows == 0 || src.cols == 0) return;
@@ -301,6 +432,7 @@ struct Lobpcg {
 
   // C = op(A)' * B accumulated over block lists (LazyHcat products, :90-137)
   void gram(const std::vector<Mat>& A, const std::vector<Mat>& B, cplx* C, int64_t ldc, bool upper_only) {
+    if (small) return small_gram(A, B, C, ldc, upper_only);
     const cplx one = make_double2(1, 0), zero = make_double2(0, 0);
     int64_t oc = 0;
     for (size_t ib = 0; ib < B.size(); ++ib) {
@@ -317,6 +449,7 @@ struct Lobpcg {
   // out (=|+=) alpha * [Y blocks] * c     (mul!(res, ::LazyHcat, B, α, β), :124-132)
   void blocks_times(const std::vector<Mat>& Y, const cplx* c, int64_t ldc, int64_t ncols, Mat out,
                     double alpha, double beta) {
+    if (small) return small_blocks_times(Y, c, ldc, ncols, out, alpha, beta);
     int64_t off = 0;
     for (size_t i = 0; i < Y.size(); ++i) {
       zgemm(ctx, 0, Y[i].rows, ncols, Y[i].cols, make_double2(alpha, 0), Y[i].p, Y[i].ld, c + off, ldc,
@@ -331,6 +464,27 @@ struct Lobpcg {
     const int64_t n = X.cols;
     if (n == 0) return 1.0;
     double growth = 1.0;
+    if (small) {
+      // gram -> fused safe_cholesky/inverse/normest (one CTA) -> one host sync -> X *= invR
+      for (int outer = 0; outer < 50; ++outer) {
+        gram({X}, {X}, Ochol, S3, true);
+        LAUNCH(ctx, k_small_chol, 1, SMALL_RED, 0, (const cplx*)Ochol, (long long)S3, (int)n, invR, (long long)S3, d_stats);
+        double s[4];
+        get(s, d_stats, 4 * sizeof(double));
+        const int nchol = (int)s[0];
+        if (nchol == 0) throw Error(DFTK_B200_ENUM, "ortho!: Cholesky failing badly (SVD fallback not implemented)");
+        LAUNCH(ctx, k_small_rmul, (unsigned)((X.rows + 127) / 128), 128, (size_t)n * n * sizeof(cplx), X.p, (long long)X.ld,
+               (long long)X.rows, (int)n, (const cplx*)invR, (long long)S3);
+        const double norminvR = s[1];
+        growth *= norminvR;
+        const double condR = s[2] * norminvR;
+        const double est = EPS * condR * condR;
+        n_chol_total += nchol;
+        if (nchol == 1 && est < 2 * EPS) break;
+        if (outer == 49) throw Error(DFTK_B200_ENUM, "ortho!: did not converge");
+      }
+      return growth;
+    }
     for (int outer = 0; outer < 50; ++outer) {
       gram({X}, {X}, Ochol, S3, true);
       LAUNCH(ctx, k_hermitize_upper, nblk(n * n), 256, 0, Ochol, S3, n);
@@ -440,7 +594,13 @@ struct Lobpcg {
       blocks_times(Y, BYX, ldBYX, n, X, -1.0, 1.0);  // X -= Y * BY'X
       // drop_small! :264-268
       LAUNCH(ctx, k_col_norms, (unsigned)n, 256, 0, (const cplx*)X.p, X.ld, X.rows, d_norms);
-      get(norms.data(), d_norms, n * sizeof(double));
+      // ||BY'X|| is needed below; it does not depend on the re-randomisation, so both results share one host sync
+      LAUNCH(ctx, k_matrix_stats, 1, 1024, 0, (const cplx*)BYX, ldBYX, ny, n, d_stats);
+      const size_t span = (size_t)(d_stats - d_norms) + 4;
+      std::vector<double> both(span);
+      get(both.data(), d_norms, span * sizeof(double));
+      std::copy(both.begin(), both.begin() + n, norms.begin());
+      const double* s = both.data() + (d_stats - d_norms);
       for (int64_t c = 0; c < n; ++c) {
         if (norms[c] <= tol) {
           Mat xc = X.cols_range(c, 1);
@@ -451,8 +611,6 @@ struct Lobpcg {
           blocks_times(Y, tmpS, S3, 1, xc, -1.0, 1.0);
         }
       }
-      double s[4];
-      stats(BYX, ldBYX, ny, n, s);
       if (std::sqrt(s[3]) < tol && niter > 1) break;
       double growth = ortho(X, tmp, ldtmp);
       if (growth * EPS < tol) break;
@@ -475,6 +633,7 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
 
   SectionProf prof;
   prof.on = getenv("DFTK_B200_PROFILE") != nullptr;
+  prof.aggregate = prof.on && atoi(getenv("DFTK_B200_PROFILE")) == 2;
   prof.st = ctx->stream;
   Lobpcg L;
   L.kb = kb;
@@ -507,6 +666,12 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
   L.d_meankin = dsc + 2 * M;
   L.d_w = dsc + 3 * M;
   L.d_stats = dsc + 3 * M + 3 * S3;
+  L.small = M <= SMALL_MAX_N && ctx->small_dense != 0;
+  if (L.small) {
+    unsigned* c = (unsigned*)ctx->small_counter.ensure(4);
+    CUDA_CHECK(cudaMemsetAsync(c, 0, 4 * sizeof(int), ctx->stream));   // also recovers from an aborted earlier solve
+    L.d_counter = c;
+  }
 
   Mat X{Xio, N, N, M};
   auto mat = [&](cplx* p) { return Mat{p, N, N, M}; };

@@ -1,0 +1,265 @@
+// Fused small-matrix path of the LOBPCG block algebra (M <= 32 bands, i.e. the C1/C2/C4/C5-sized problems where every
+// step is launch- and sync-latency bound).  The tensor-core GEMM + cuSOLVER sequence of the large path
+// (gram -> hermitize -> copy -> potrf -> zero_lower -> copy -> trtri -> 3x stats, five host syncs per Cholesky pass)
+// becomes gram -> k_small_chol -> k_small_rmul with ONE host sync; block-list products are one launch each.
+// Same algorithm as lobpcg.cu (reference: src/eigen/lobpcg_hyper_impl.jl:90-137 LazyHcat products, :190-210
+// safe_cholesky, :212 normest, :216-261 ortho!).  Bodies are __host__ __device__ (host emulation in tests/hostemu);
+// on the host TLOOP runs the "threads" of a CTA one after the other, which is valid because no phase between two
+// TSYNC() has dependencies between its iterations.
+#pragma once
+#include <float.h>
+#include <math.h>
+#include "fft_core.cuh"
+
+namespace dftk {
+
+#define SMALL_MAX_N 32      // columns of the block being orthogonalised / produced (= max bands of the small path)
+#define SMALL_MAX_COLS 96   // total columns of a block list [X R P]
+#define SMALL_TR 8          // rows per shared-memory tile of the Gram kernel (192 columns x 8 rows x 16 B = 24 KB)
+#define SMALL_RED 256       // logical reduction width (= CTA size of k_small_chol)
+
+struct SmallMatList {
+  const cplx* p[3];
+  long long ld[3];
+  int cols[3];
+  int start[4];   // column offsets, start[n] = total
+  int n;
+};
+HD int small_block_of(const SmallMatList& L, int col) { return col >= L.start[2] && L.n > 2 ? 2 : (col >= L.start[1] && L.n > 1 ? 1 : 0); }
+HD const cplx* small_col_ptr(const SmallMatList& L, int col) {
+  const int b = small_block_of(L, col);
+  return L.p[b] + L.ld[b] * (long long)(col - L.start[b]);
+}
+
+// ---- Gram: partial[cta][i + nA j] = sum over the CTA's rows of conj(A[r,i]) B[r,j]; (i,j) pairs with block(j) < block(i)
+//      are skipped when upper_only (Hermitian result, only the block upper triangle is consumed)
+HD void small_gram_cta(int cta, long long rows_per_cta, long long n_rows, const SmallMatList& A, const SmallMatList& B,
+                       int upper_only, cplx* __restrict__ ws, cplx* sm) {
+  const int nA = A.start[A.n], nB = B.start[B.n], total = nA * nB;
+  const long long r_begin = (long long)cta * rows_per_cta;
+  const long long r_end = r_begin + rows_per_cta < n_rows ? r_begin + rows_per_cta : n_rows;
+  cplx* As = sm;
+  cplx* Bs = sm + SMALL_TR * nA;
+  cplx* out = ws + (size_t)cta * total;
+  TLOOP(o, total) out[o] = make_double2(0.0, 0.0);
+  for (long long r0 = r_begin; r0 < r_end; r0 += SMALL_TR) {
+    const int nr = (int)(r_end - r0 < SMALL_TR ? r_end - r0 : SMALL_TR);
+    TSYNC();
+    TLOOP(e, SMALL_TR * nA) {
+      const int r = e % SMALL_TR, i = e / SMALL_TR;
+      As[r * nA + i] = r < nr ? small_col_ptr(A, i)[r0 + r] : make_double2(0.0, 0.0);
+    }
+    TLOOP(e, SMALL_TR * nB) {
+      const int r = e % SMALL_TR, j = e / SMALL_TR;
+      Bs[r * nB + j] = r < nr ? small_col_ptr(B, j)[r0 + r] : make_double2(0.0, 0.0);
+    }
+    TSYNC();
+    TLOOP(o, total) {
+      const int i = o % nA, j = o / nA;
+      if (upper_only && small_block_of(B, j) < small_block_of(A, i)) continue;
+      double ax = 0.0, ay = 0.0;
+      for (int r = 0; r < nr; ++r) {
+        const cplx a = As[r * nA + i], b = Bs[r * nB + j];
+        ax += a.x * b.x + a.y * b.y;     // conj(a) * b
+        ay += a.x * b.y - a.y * b.x;
+      }
+      out[o].x += ax;
+      out[o].y += ay;
+    }
+  }
+}
+// fixed-order sum of the CTA partials into C (run by the last CTA to finish / by the emulator)
+HD void small_gram_reduce(int n_ctas, const SmallMatList& A, const SmallMatList& B, int upper_only,
+                          const cplx* __restrict__ ws, cplx* __restrict__ C, long long ldc) {
+  const int nA = A.start[A.n], nB = B.start[B.n], total = nA * nB;
+  TLOOP(o, total) {
+    const int i = o % nA, j = o / nA;
+    if (upper_only && small_block_of(B, j) < small_block_of(A, i)) continue;
+    double sx = 0.0, sy = 0.0;
+    for (int c = 0; c < n_ctas; ++c) {
+#ifdef __CUDA_ARCH__
+      const double2 v = __ldcg(ws + (size_t)c * total + o);   // written by other CTAs: bypass L1
+#else
+      const cplx v = ws[(size_t)c * total + o];
+#endif
+      sx += v.x;
+      sy += v.y;
+    }
+    C[i + ldc * j] = make_double2(sx, sy);
+  }
+}
+
+// ---- out[r, c] = alpha * sum_l Y[r, l] cm[l, c] + beta * out[r, c]  for one row r (cm: ny x ncols, leading dim ldcm)
+HD void small_blocks_times_row(long long r, const SmallMatList& Y, const cplx* __restrict__ cm, int ldcm, int ncols,
+                               cplx* __restrict__ out, long long ldo, double alpha, double beta) {
+  double ax[SMALL_MAX_N], ay[SMALL_MAX_N];
+  for (int c = 0; c < ncols; ++c) ax[c] = ay[c] = 0.0;
+  const int ny = Y.start[Y.n];
+  for (int l = 0; l < ny; ++l) {
+    const cplx y = small_col_ptr(Y, l)[r];
+    for (int c = 0; c < ncols; ++c) {
+      const cplx m = cm[l + ldcm * c];
+      ax[c] += y.x * m.x - y.y * m.y;
+      ay[c] += y.x * m.y + y.y * m.x;
+    }
+  }
+  for (int c = 0; c < ncols; ++c) {
+    cplx o = make_double2(alpha * ax[c], alpha * ay[c]);
+    if (beta != 0.0) {
+      const cplx p = out[r + ldo * c];
+      o.x += beta * p.x;
+      o.y += beta * p.y;
+    }
+    out[r + ldo * c] = o;
+  }
+}
+
+// ---- X[r, :] <- X[r, :] * invR (upper triangular n x n, column-major with leading dimension ldr), in place
+HD void small_rmul_row(long long r, cplx* __restrict__ X, long long ld, int n, const cplx* __restrict__ Rinv, int ldr) {
+  cplx x[SMALL_MAX_N];
+  for (int l = 0; l < n; ++l) x[l] = X[r + ld * l];
+  for (int j = n - 1; j >= 0; --j) {
+    double sx = 0.0, sy = 0.0;
+    for (int l = 0; l <= j; ++l) {
+      const cplx m = Rinv[l + ldr * j];
+      sx += x[l].x * m.x - x[l].y * m.y;
+      sy += x[l].x * m.y + x[l].y * m.x;
+    }
+    X[r + ld * j] = make_double2(sx, sy);
+  }
+}
+
+// ---- safe_cholesky + inverse + normest in one CTA (n <= SMALL_MAX_N).
+// O: Hermitian, only the upper triangle (i <= j) is read.  Writes invR (n x n, zeros below the diagonal) and
+// stats[0] = number of Cholesky attempts (0: all five failed), stats[1] = normest(invR), stats[2] = normest(R),
+// stats[3] = ||O||_F.  Shared memory: As, Bs (n*n cplx each), red (SMALL_RED doubles), flag (2 ints).
+HD void small_chol_cta(const cplx* __restrict__ O, long long ldo, int n, cplx* __restrict__ invR, long long ldi,
+                       double* __restrict__ stats, cplx* As, cplx* Bs, double* red, int* flag) {
+  // Frobenius norm of the full Hermitian matrix
+  TLOOP(t, SMALL_RED) {
+    double s = 0.0;
+    for (int e = t; e < n * n; e += SMALL_RED) {
+      const int i = e % n, j = e / n;
+      const cplx v = i <= j ? O[i + ldo * j] : O[j + ldo * i];
+      s += (i == j) ? v.x * v.x : v.x * v.x + v.y * v.y;
+    }
+    red[t] = s;
+  }
+  TSYNC();
+  double onorm = 0.0;
+  for (int t = 0; t < SMALL_RED; ++t) onorm += red[t];
+  onorm = sqrt(onorm);
+  TSYNC();
+  double shift = 0.0, alpha = 100.0;
+  int nchol = 0, ok = 0;
+  while (nchol < 5 && !ok) {
+    nchol++;
+    // A = Hermitian(O) + shift I   (upper triangle only is needed)
+    TLOOP(e, n * n) {
+      const int i = e % n, j = e / n;
+      cplx v = make_double2(0.0, 0.0);
+      if (i <= j) v = O[i + ldo * j];
+      if (i == j) v = make_double2(v.x + shift, 0.0);
+      As[e] = v;
+    }
+    TLOOP(t, 1) flag[0] = 0;
+    TSYNC();
+    for (int k = 0; k < n; ++k) {
+      TLOOP(t, 1) {
+        const double d = As[k + n * k].x;
+        if (!(d > 0.0) || !isfinite(d)) flag[0] = 1;
+        else As[k + n * k] = make_double2(sqrt(d), 0.0);
+      }
+      TSYNC();
+      if (flag[0]) break;
+      const double rinv = 1.0 / As[k + n * k].x;
+      const int m = n - k - 1;
+      TLOOP(j, m) {
+        cplx v = As[k + n * (k + 1 + j)];
+        As[k + n * (k + 1 + j)] = make_double2(v.x * rinv, v.y * rinv);
+      }
+      TSYNC();
+      TLOOP(e, m * m) {
+        const int i = k + 1 + e % m, j = k + 1 + e / m;
+        if (i <= j) {
+          const cplx a = As[k + n * i], b = As[k + n * j];   // conj(R[k,i]) * R[k,j]
+          cplx v = As[i + n * j];
+          v.x -= a.x * b.x + a.y * b.y;
+          v.y -= a.x * b.y - a.y * b.x;
+          As[i + n * j] = v;
+        }
+      }
+      TSYNC();
+    }
+    int failed = flag[0];
+    TSYNC();
+    if (!failed) {
+      // invR by back substitution, one column per thread:  R x = e_j
+      TLOOP(j, n) {
+        for (int i = n - 1; i > j; --i) Bs[i + n * j] = make_double2(0.0, 0.0);
+        Bs[j + n * j] = make_double2(1.0 / As[j + n * j].x, 0.0);
+        for (int i = j - 1; i >= 0; --i) {
+          double sx = 0.0, sy = 0.0;
+          for (int l = i + 1; l <= j; ++l) {
+            const cplx a = As[i + n * l], b = Bs[l + n * j];
+            sx += a.x * b.x - a.y * b.y;
+            sy += a.x * b.y + a.y * b.x;
+          }
+          const double d = -1.0 / As[i + n * i].x;
+          Bs[i + n * j] = make_double2(sx * d, sy * d);
+        }
+      }
+      TSYNC();
+      // any non-finite entry of invR counts as a failed factorisation (@assert !any(isnan, invR), :198)
+      TLOOP(t, SMALL_RED) {
+        double bad = 0.0;
+        for (int e = t; e < n * n; e += SMALL_RED)
+          if (!isfinite(Bs[e].x) || !isfinite(Bs[e].y)) bad += 1.0;
+        red[t] = bad;
+      }
+      TSYNC();
+      double bad = 0.0;
+      for (int t = 0; t < SMALL_RED; ++t) bad += red[t];
+      TSYNC();
+      failed = bad != 0.0;
+    }
+    if (!failed) {
+      ok = 1;
+    } else {
+      // O += alpha eps ||O|| I, alpha *= 10   (:203-205)
+      shift += alpha * DBL_EPSILON * onorm;
+      alpha *= 10.0;
+    }
+  }
+  // normest(M) = max |diag| + ||M - Diag||_F  for invR (Bs) and R (As, upper triangle)
+  double out1 = 0.0, out2 = 0.0;
+  if (ok) {
+    for (int which = 0; which < 2; ++which) {
+      const cplx* Mx = which == 0 ? Bs : As;
+      TLOOP(t, SMALL_RED) {
+        double s = 0.0;
+        for (int e = t; e < n * n; e += SMALL_RED) {
+          const int i = e % n, j = e / n;
+          if (i < j) s += Mx[e].x * Mx[e].x + Mx[e].y * Mx[e].y;
+        }
+        red[t] = s;
+      }
+      TSYNC();
+      double so = 0.0, md = 0.0;
+      for (int t = 0; t < SMALL_RED; ++t) so += red[t];
+      for (int i = 0; i < n; ++i) md = fmax(md, fabs(Mx[i + n * i].x));
+      TSYNC();
+      if (which == 0) out1 = md + sqrt(so);
+      else out2 = md + sqrt(so);
+    }
+    TLOOP(e, n * n) invR[e % n + ldi * (e / n)] = Bs[e];
+  }
+  TLOOP(t, 1) {
+    stats[0] = ok ? (double)nchol : 0.0;
+    stats[1] = out1;
+    stats[2] = out2;
+    stats[3] = onorm;
+  }
+}
+
+}  // namespace dftk

@@ -52,7 +52,8 @@ int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset);
 /* tuning knobs: "gemm_backend" (0 = own DMMA kernels, 1 = cuBLAS, for A/B comparison and peak calibration only),
  * "gemm_stages" (cp.async ring depth 2|3), "band_chunk" (bands per batched-FFT launch, 0 = auto),
  * "fft_engine" (0 = register two-pass engine where a factor pair exists, 1 = generic Stockham; applies to grids
- * created afterwards) */
+ * created afterwards), "small_dense" (1 = fused small-matrix kernels for LOBPCG solves with <= 32 bands, 0 = the
+ * GEMM + cuSOLVER sequence of the large path) */
 int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value);
 
 /* ---- FFT grid (FFTGrid + build_fft_plans!, src/fft.jl:57-98,343-362) ---- */

@@ -272,3 +272,56 @@ int emu_nonlocal_force_rows(int64_t np, int64_t nb, const double* dproj, const d
   return 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Fused small-matrix LOBPCG bodies (lobpcg_small.cuh) on the host
+// ------------------------------------------------------------------------------------------------
+#include "../../dftk.jl_b200/csrc/lobpcg_small.cuh"
+#include <vector>
+static SmallMatList emu_list(int nblocks, const double* const* ptrs, const int64_t* lds, const int* cols) {
+  SmallMatList L{};
+  L.n = nblocks;
+  int off = 0;
+  for (int i = 0; i < 3; ++i) {
+    L.start[i] = off;
+    if (i < nblocks) {
+      L.p[i] = (const cplx*)ptrs[i];
+      L.ld[i] = lds[i];
+      L.cols[i] = cols[i];
+      off += cols[i];
+    }
+  }
+  L.start[3] = off;
+  for (int i = nblocks; i < 4; ++i) L.start[i] = off;
+  return L;
+}
+extern "C" {
+int emu_small_gram(int nA, const double* const* pA, const int64_t* ldA, const int* colsA, int nB, const double* const* pB,
+                   const int64_t* ldB, const int* colsB, int64_t n_rows, int64_t rows_per_cta, int upper_only, double* C,
+                   int64_t ldc) {
+  SmallMatList A = emu_list(nA, pA, ldA, colsA), B = emu_list(nB, pB, ldB, colsB);
+  const int ta = A.start[A.n], tb = B.start[B.n];
+  const int n_ctas = (int)((n_rows + rows_per_cta - 1) / rows_per_cta);
+  std::vector<cplx> ws((size_t)n_ctas * ta * tb), sm((size_t)SMALL_TR * (ta + tb));
+  for (int c = 0; c < n_ctas; ++c) small_gram_cta(c, rows_per_cta, n_rows, A, B, upper_only, ws.data(), sm.data());
+  small_gram_reduce(n_ctas, A, B, upper_only, ws.data(), (cplx*)C, ldc);
+  return 0;
+}
+int emu_small_blocks_times(int nY, const double* const* pY, const int64_t* ldY, const int* colsY, const double* cm,
+                           int ldcm, int ncols, double* out, int64_t ldo, int64_t n_rows, double alpha, double beta) {
+  SmallMatList Y = emu_list(nY, pY, ldY, colsY);
+  for (int64_t r = 0; r < n_rows; ++r) small_blocks_times_row(r, Y, (const cplx*)cm, ldcm, ncols, (cplx*)out, ldo, alpha, beta);
+  return 0;
+}
+int emu_small_rmul(double* X, int64_t ld, int64_t n_rows, int n, const double* invR, int ldr) {
+  for (int64_t r = 0; r < n_rows; ++r) small_rmul_row(r, (cplx*)X, ld, n, (const cplx*)invR, ldr);
+  return 0;
+}
+int emu_small_chol(const double* O, int64_t ldo, int n, double* invR, int64_t ldi, double* stats) {
+  std::vector<cplx> As((size_t)SMALL_MAX_N * SMALL_MAX_N), Bs((size_t)SMALL_MAX_N * SMALL_MAX_N);
+  std::vector<double> red(SMALL_RED);
+  int flag[2] = {0, 0};
+  small_chol_cta((const cplx*)O, ldo, n, (cplx*)invR, ldi, stats, As.data(), Bs.data(), red.data(), flag);
+  return 0;
+}
+}

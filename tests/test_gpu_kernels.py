@@ -120,11 +120,14 @@ def test_band_energies_and_density(si):
     np.testing.assert_allclose(rho.cpu().numpy(), ref, atol=1e-12 * ref.max())
 
 
-@pytest.mark.parametrize("backend", [0, 1])
-def test_lobpcg_matches_oracle(si, backend):
+@pytest.mark.parametrize("backend,small", [(0, 1), (1, 0), (0, 0)])
+def test_lobpcg_matches_oracle(si, backend, small):
+    # small = 1: fused small-matrix kernels (lobpcg_small.cuh, the default for <= 32 bands);
+    # small = 0: tensor-core GEMM + cuSOLVER sequence of the large path on the same problem
     from gpu_common import to_dev, ctx
     from oracle import lobpcg as olob
     ctx().set_option("gemm_backend", backend)
+    ctx().set_option("small_dense", small)
     try:
         blk, kb = si["blk"], si["kb"]
         rng = np.random.default_rng(5)
@@ -145,8 +148,16 @@ def test_lobpcg_matches_oracle(si, backend):
         X = to_dev(X0.T[:7])
         res2 = kb.lobpcg(X, tol=1e-7, maxiter=100, n_conv_check=4)
         np.testing.assert_allclose(res2["λ"][:4], ref["λ"][:4], atol=1e-6)
+        # a rank-deficient start block (two identical columns) goes through the shifted safe_cholesky retries
+        Xd = X0.T[:6].copy()
+        Xd[4] = Xd[1]
+        X = to_dev(Xd)
+        res3 = kb.lobpcg(X, tol=1e-8, maxiter=200)
+        assert res3["converged"]
+        np.testing.assert_allclose(res3["λ"], ref["λ"][:6], atol=1e-7)
     finally:
         ctx().set_option("gemm_backend", 0)
+        ctx().set_option("small_dense", 1)
 
 
 @pytest.mark.parametrize("fft_size,Ecut", [((40, 45, 48), 30), ((32, 27, 36), 14), ((33, 40, 21), 10),

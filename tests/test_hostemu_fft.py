@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "hostemu", "libhostemu.so")
 def emu():
     src = os.path.join(HERE, "hostemu", "emu.cu")
     csrc = os.path.join(HERE, "..", "dftk.jl_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_radix_gen.cuh", "xc_core.cuh", "forces_core.cuh", "fft_reg_fwd.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_radix_gen.cuh", "xc_core.cuh", "forces_core.cuh", "lobpcg_small.cuh", "fft_reg_fwd.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
                                "-Wno-deprecated-gpu-targets", "-o", SO, src])
@@ -200,3 +200,103 @@ def test_emulated_force_bodies_match_oracle(emu):
         for ia in range(2):
             F[ia] += rows[:, ia * per_atom:(ia + 1) * per_atom].sum(axis=1)
     np.testing.assert_allclose(F, refn, rtol=1e-11, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused small-matrix LOBPCG bodies (lobpcg_small.cuh): block-list Gram / update products, X*invR, safe_cholesky
+# ---------------------------------------------------------------------------------------------------------------
+def _lists(blocks):
+    """ctypes views of a list of column-major blocks given as (n_cols, n_rows) C-contiguous complex arrays."""
+    n = len(blocks)
+    ptrs = (ctypes.c_void_p * 3)(*[b.ctypes.data for b in blocks] + [None] * (3 - n))
+    lds = (ctypes.c_int64 * 3)(*[b.shape[1] for b in blocks] + [0] * (3 - n))
+    cols = (ctypes.c_int * 3)(*[b.shape[0] for b in blocks] + [0] * (3 - n))
+    return n, ptrs, lds, cols
+
+
+def _normest(M):
+    d = np.diag(M)
+    return np.max(np.abs(d)) + np.linalg.norm(M - np.diag(d))
+
+
+@pytest.mark.parametrize("rows,cols_a,cols_b", [(2114, (7, 7, 5), (7, 7, 5)), (333, (12,), (12, 3)), (21, (7,), (7,)),
+                                                (5442, (15, 15, 15), (15, 15, 15))])
+def test_emulated_small_gram_and_updates(emu, rows, cols_a, cols_b):
+    rng = np.random.default_rng(5)
+    mk = lambda c: np.ascontiguousarray(rng.standard_normal((c, rows)) + 1j * rng.standard_normal((c, rows)))
+    A, B = [mk(c) for c in cols_a], [mk(c) for c in cols_b]
+    ta, tb = sum(cols_a), sum(cols_b)
+    Afull, Bfull = np.concatenate(A, axis=0).T, np.concatenate(B, axis=0).T          # rows x cols
+    ref = Afull.conj().T @ Bfull
+    for upper in (0, 1):
+        C = np.full((tb, ta + 2), np.nan + 0j)                                            # column-major ta(+2 pad) x tb
+        for rpc in (64, 128):
+            assert emu.emu_small_gram(*_lists(A), *_lists(B), ctypes.c_int64(rows), ctypes.c_int64(rpc), upper, _p(C),
+                                      ctypes.c_int64(ta + 2)) == 0
+            got = C[:, :ta].T
+            sa = np.repeat(np.arange(len(cols_a)), cols_a)
+            sb = np.repeat(np.arange(len(cols_b)), cols_b)
+            keep = (sb[None, :] >= sa[:, None]) if upper else np.ones((ta, tb), dtype=bool)
+            np.testing.assert_allclose(got[keep], ref[keep], rtol=1e-12, atol=1e-11)
+            assert upper == 0 or np.all(np.isnan(got[~keep]))                             # skipped blocks stay untouched
+    # out = alpha * [A blocks] cm + beta * out
+    ncols = min(7, ta)
+    cm = np.ascontiguousarray(rng.standard_normal((ncols, ta + 1)) + 1j * rng.standard_normal((ncols, ta + 1)))
+    out0 = np.ascontiguousarray(rng.standard_normal((ncols, rows)) + 1j * rng.standard_normal((ncols, rows)))
+    for alpha, beta in ((1.0, 0.0), (-1.0, 1.0)):
+        out = out0.copy()
+        assert emu.emu_small_blocks_times(*_lists(A), _p(cm), ta + 1, ncols, _p(out), ctypes.c_int64(rows),
+                                          ctypes.c_int64(rows), ctypes.c_double(alpha), ctypes.c_double(beta)) == 0
+        want = alpha * (Afull @ cm[:, :ta].T) + beta * out0.T
+        np.testing.assert_allclose(out.T, want, rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.parametrize("n", [1, 7, 15, 32])
+def test_emulated_small_cholesky_qr(emu, n):
+    """k_small_chol + k_small_rmul = one pass of ortho! (lobpcg_hyper_impl.jl:216-261): X invR is orthonormal, the
+    statistics are those of safe_cholesky / normest (:190-212)."""
+    rng = np.random.default_rng(n)
+    rows = 500
+    X = rng.standard_normal((rows, n)) + 1j * rng.standard_normal((rows, n))
+    O = X.conj().T @ X
+    # column-major upper triangle; the lower one must not be read
+    Ocm = np.ascontiguousarray(np.where(np.triu(np.ones((n, n), dtype=bool)).T, np.triu(O).T, np.nan + 0j))
+    invR = np.full((n, n + 3), np.nan + 0j)
+    stats = np.zeros(4)
+    assert emu.emu_small_chol(_p(Ocm), ctypes.c_int64(n), n, _p(invR), ctypes.c_int64(n + 3), _p(stats)) == 0
+    R = np.linalg.cholesky(O).conj().T
+    got = invR[:, :n].T
+    np.testing.assert_allclose(got, np.linalg.inv(R), rtol=1e-10, atol=1e-13)
+    assert np.all(np.tril(got, -1) == 0)
+    assert stats[0] == 1
+    assert stats[1] == pytest.approx(_normest(np.linalg.inv(R)), rel=1e-10)
+    assert stats[2] == pytest.approx(_normest(R), rel=1e-10)
+    assert stats[3] == pytest.approx(np.linalg.norm(O), rel=1e-12)
+    Xcm = np.array(X.T, order="C", copy=True)
+    assert emu.emu_small_rmul(_p(Xcm), ctypes.c_int64(rows), ctypes.c_int64(rows), n, _p(np.ascontiguousarray(invR)), n + 3) == 0
+    Q = Xcm.T
+    np.testing.assert_allclose(Q, X @ np.linalg.inv(R), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(Q.conj().T @ Q, np.eye(n), atol=1e-12)
+
+
+def test_emulated_small_cholesky_failure_modes(emu):
+    """safe_cholesky (:190-210): a singular Gram matrix is shifted by alpha eps ||O|| (alpha = 100, 1000, ...) until the
+    factorisation succeeds; NaN input fails all five attempts."""
+    rng = np.random.default_rng(0)
+    n = 6
+    X = rng.standard_normal((50, n)) + 1j * rng.standard_normal((50, n))
+    X[:, 3] = X[:, 1]                                        # exactly rank deficient
+    O = X.conj().T @ X
+    Ocm = np.ascontiguousarray(O.T)
+    invR = np.zeros((n, n), dtype=complex)
+    stats = np.zeros(4)
+    assert emu.emu_small_chol(_p(Ocm), ctypes.c_int64(n), n, _p(invR), ctypes.c_int64(n), _p(stats)) == 0
+    assert stats[0] >= 1
+    nchol = int(stats[0])
+    shift = sum(100.0 * 10 ** a for a in range(nchol - 1)) * np.finfo(float).eps * np.linalg.norm(O)
+    Rg = np.linalg.inv(invR.T)                               # the factor that was inverted (ill-conditioned: compare R'R)
+    np.testing.assert_allclose(Rg.conj().T @ Rg, O + shift * np.eye(n), atol=1e-9 * np.linalg.norm(O))
+    assert stats[1] > 1e3                                     # huge growth factor: the caller loops again
+    Ocm[2, 2] = np.nan
+    assert emu.emu_small_chol(_p(Ocm), ctypes.c_int64(n), n, _p(invR), ctypes.c_int64(n), _p(stats)) == 0
+    assert stats[0] == 0
