@@ -23,7 +23,6 @@ print(f"{os.environ['PROBE_NAME']:42s} eigh 1509: min {min(ts)*1e3:7.1f} ms  med
 '''
 cases = [("pkg_first (env set before libgomp)", "pkg_first", {}),
          ("torch_first (runtime team cap only)", "torch_first", {}),
-         ("torch_first + OMP_WAIT_POLICY=passive env", "torch_first", {"OMP_WAIT_POLICY": "passive"}),
          ("torch only, OMP_NUM_THREADS=1", "none", {"OMP_NUM_THREADS": "1"}),
          ("torch only, defaults", "none", {})]
 for name, order, extra in cases:
