@@ -166,6 +166,7 @@ int dftk_b200_ctx_destroy(dftk_b200_ctx* ctx) {
   }
   if (ctx->nccl) ncclCommDestroy(ctx->nccl);
   if (ctx->cublas) cublasDestroy(ctx->cublas);
+  if (ctx->solver_params) cusolverDnDestroyParams(ctx->solver_params);
   if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
   delete ctx;
   return DFTK_B200_OK;

@@ -85,6 +85,8 @@ struct dftk_b200_ctx {
   cudaStream_t stream = 0;
   cublasHandle_t cublas = nullptr;
   cusolverDnHandle_t cusolver = nullptr;
+  cusolverDnParams_t solver_params = nullptr;
+  std::vector<char> solver_host_work;
   ncclComm_t nccl = nullptr;
   int rank = 0, nranks = 1;
   int64_t launches = 0;

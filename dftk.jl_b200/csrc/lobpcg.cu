@@ -564,14 +564,19 @@ struct Lobpcg {
   }
   // eigen(Hermitian(G)) upper triangle; eigenvectors overwrite G, eigenvalues -> d_w (ascending)
   void heevd(cplx* A, int64_t n) {
-    int lwork = 0;
-    CUSOLVER_CHECK(cusolverDnZheevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR,
-                                               CUBLAS_FILL_MODE_UPPER, (int)n, (cuDoubleComplex*)A, (int)S3,
-                                               d_w, &lwork));
-    char* w = ctx->solver_work.ensure((size_t)lwork * sizeof(cuDoubleComplex) + 16);
+    // 64-bit generic API: unlike the legacy cusolverDnZheevd it has no OpenMP host stage whose speed depends on the
+    // process' OMP_* environment (measured: 26 ms for n = 1509 under every setting vs 30-700 ms for Zheevd)
+    if (!ctx->solver_params) CUSOLVER_CHECK(cusolverDnCreateParams(&ctx->solver_params));
+    size_t wd = 0, wh = 0;
+    CUSOLVER_CHECK(cusolverDnXsyevd_bufferSize(ctx->cusolver, ctx->solver_params, CUSOLVER_EIG_MODE_VECTOR,
+                                               CUBLAS_FILL_MODE_UPPER, n, CUDA_C_64F, A, S3, CUDA_R_64F, d_w, CUDA_C_64F,
+                                               &wd, &wh));
+    char* w = ctx->solver_work.ensure(wd + 16);
+    if (ctx->solver_host_work.size() < wh + 16) ctx->solver_host_work.resize(wh + 16);
     int* dinfo = ctx->dev_info.ensure(4);
-    CUSOLVER_CHECK(cusolverDnZheevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, (int)n,
-                                    (cuDoubleComplex*)A, (int)S3, d_w, (cuDoubleComplex*)w, lwork, dinfo));
+    CUSOLVER_CHECK(cusolverDnXsyevd(ctx->cusolver, ctx->solver_params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_UPPER, n,
+                                    CUDA_C_64F, A, S3, CUDA_R_64F, d_w, CUDA_C_64F, w, wd, ctx->solver_host_work.data(), wh,
+                                    dinfo));
     ctx->launches++;
     int info = 0;
     get(&info, dinfo, sizeof(int));
