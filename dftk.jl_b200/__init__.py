@@ -28,8 +28,9 @@ def effective_cpus():
     return n
 
 
-# cuSOLVER's Zheevd (Rayleigh-Ritz of LOBPCG) has OpenMP host stages: an unset OMP_NUM_THREADS means one thread per
-# *visible* core, which oversubscribes containers with a CPU quota by 8x and makes heevd 10x slower (measured).
+# cuSOLVER's legacy dense routines have OpenMP host stages: an unset OMP_NUM_THREADS means one thread per *visible*
+# core, which oversubscribes containers with a CPU quota by 8x (measured: Zheevd 10x slower; the Rayleigh-Ritz of
+# LOBPCG now uses cusolverDnXsyevd, which does not depend on these settings, but potrf/trtri and NumPy still do).
 # Spinning OpenMP workers (the libgomp default) fight the CUDA-synchronising host thread for a quota-limited CPU
 # budget: measured 0.03 s (passive) vs 0.25-3.7 s (active) per 1509x1509 heevd.
 _os.environ.setdefault("OMP_WAIT_POLICY", "passive")
