@@ -16,7 +16,7 @@ class Energies(dict):
 
 
 class DftHamiltonianBlock:
-    def __init__(self, basis, ik, operators):
+    def __init__(self, basis, ik, operators, pot_cache=None):
         self.basis, self.ik, self.kpoint = basis, ik, basis.kpoints[ik]
         self.operators = operators
         ops = [o for o in operators if not isinstance(o, NoopOperator)]
@@ -31,10 +31,17 @@ class DftHamiltonianBlock:
         # optimize_operators (operators.jl:213-222): sum all real-space multiplications
         self.local_op = None
         if real:
-            pot = real[0].potential
-            for o in real[1:]:
-                pot = pot + o.potential
-            self.local_op = RealSpaceMultiplication(basis, self.kpoint, pot.contiguous())
+            # all k-blocks of one spin share the same term potentials: sum them once (keyed by the storage they view)
+            key = tuple((o.potential.data_ptr(), o.potential.numel()) for o in real)
+            pot = pot_cache.get(key) if pot_cache is not None else None
+            if pot is None:
+                pot = real[0].potential
+                for o in real[1:]:
+                    pot = pot + o.potential
+                pot = pot.contiguous()
+                if pot_cache is not None:
+                    pot_cache[key] = pot
+            self.local_op = RealSpaceMultiplication(basis, self.kpoint, pot)
         self.kblock = basis.kblocks[ik]
         self.kblock.set_potential(self.local_op.potential if self.local_op is not None else None)
 
@@ -65,17 +72,27 @@ class Hamiltonian:
 def energy_hamiltonian(basis, psi, occupation, *, rho, eigenvalues=None, eF=None, **kw):
     """Hamiltonian.jl:200-227: energies of every term + the per-k Hamiltonian blocks."""
     energies, per_term_ops = Energies(), []
-    for name, term in zip(basis.model.term_types, basis.terms):
-        E, ops = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF)
-        energies[name] = E
-        per_term_ops.append(ops)
-    blocks = [DftHamiltonianBlock(basis, ik, [ops[ik] for ops in per_term_ops]) for ik in range(len(basis.kpoints))]
+    basis._be_cache = {}
+    try:
+        for name, term in zip(basis.model.term_types, basis.terms):
+            E, ops = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF)
+            energies[name] = E
+            per_term_ops.append(ops)
+    finally:
+        basis._be_cache = None
+    pot_cache = {}
+    blocks = [DftHamiltonianBlock(basis, ik, [ops[ik] for ops in per_term_ops], pot_cache)
+              for ik in range(len(basis.kpoints))]
     return energies, Hamiltonian(basis, blocks)
 
 
 def energy(basis, psi, occupation, *, rho, eigenvalues=None, eF=None, **kw):
     """Hamiltonian.jl:232-236 (energies only)."""
     energies = Energies()
-    for name, term in zip(basis.model.term_types, basis.terms):
-        energies[name] = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF)[0]
+    basis._be_cache = {}
+    try:
+        for name, term in zip(basis.model.term_types, basis.terms):
+            energies[name] = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF)[0]
+    finally:
+        basis._be_cache = None
     return energies

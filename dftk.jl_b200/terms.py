@@ -58,7 +58,8 @@ class TermKinetic:
             return math.inf, ops
         E = 0.0
         for ik, kb in enumerate(basis.kblocks):
-            ek, _ = _band_energies(kb, psi[ik], want_nl=False)
+            both = _band_energies_shared(basis, ik, psi[ik])
+            ek = both[0] if both is not None else _band_energies(kb, psi[ik], want_nl=False)[0]
             E += basis.kweights[ik] * float(np.sum(np.asarray(occupation[ik]) * ek))
         return basis.comm_kpts.sum(E), ops
 
@@ -72,6 +73,17 @@ def _band_energies(kb, psik, want_nl=True, want_kin=True):
     en = np.zeros(nb) if want_nl else None
     check(kb.ctx.L.dftk_b200_band_energies(kb.h, _ptr(psik), nb, _ptr(ek), _ptr(en)), kb.ctx.h)
     return ek, en
+
+
+def _band_energies_shared(basis, ik, psik):
+    """Within one energy evaluation (energy_hamiltonian / energy set `basis._be_cache`) the kinetic and the nonlocal term
+    need per-band energies of the same orbitals: one dftk_b200_band_energies call per k-block serves both."""
+    cache = getattr(basis, "_be_cache", None)
+    if cache is None or basis.term("Kinetic") is None or basis.term("AtomicNonlocal") is None:
+        return None
+    if ik not in cache:
+        cache[ik] = _band_energies(basis.kblocks[ik], psik)
+    return cache[ik]
 
 
 class TermAtomicLocal:
@@ -163,7 +175,8 @@ class TermAtomicNonlocal:
             return math.inf, self.ops
         E = 0.0
         for ik, kb in enumerate(basis.kblocks):
-            _, en = _band_energies(kb, psi[ik], want_kin=False)
+            both = _band_energies_shared(basis, ik, psi[ik])
+            en = both[1] if both is not None else _band_energies(kb, psi[ik], want_kin=False)[1]
             E += basis.kweights[ik] * float(np.sum(en * np.asarray(occupation[ik])))
         return basis.comm_kpts.sum(E), self.ops
 
