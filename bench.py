@@ -346,6 +346,8 @@ def run_gpu(args):
         # ---- Hellmann-Feynman forces of that state: local (one cube pass per atom), nonlocal (four
         #      DMMA projections per k-block), Ewald (host)
         try:
+            if world > 1:
+                raise RuntimeError("measured at N=1 only")
             from dftk_b200 import forces as fmod
             ft = {}
             for name, fn in (("local", lambda: fmod.forces_local(basis, res["rho"])),
