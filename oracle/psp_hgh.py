@@ -13,6 +13,15 @@ PSP_TABLE = {
     ("Si", "lda"): dict(Z=14, n_elec=[2, 2], rloc=0.44, cloc=[-7.33610297],
                         proj=[(0.42273813, [[5.90692831, -1.26189397], [3.25819622]]),
                               (0.48427842, [[2.72701346]])]),
+    ("Si", "pbe"): dict(Z=14, n_elec=[2, 2], rloc=0.44, cloc=[-6.26928833],
+                        proj=[(0.43563383, [[8.95174150, -2.70627082], [3.49378060]]),
+                              (0.49794218, [[2.43127673]])]),
+    # Fe GTH-PADE-q8 (large core; the pseudopotential of the reference's iron tests, test/testcases.jl:129)
+    ("Fe", "lda-q8"): dict(Z=26, n_elec=[2, 0, 6], rloc=0.61, cloc=[],
+                           proj=[(0.45448200, [[3.01664046, -1.00040646, 0.79478164], [2.58303836, -2.05211737],
+                                               [3.25763534]]),
+                                 (0.63890282, [[1.49964199, -0.13812935], [0.32687369]]),
+                                 (0.30873177, [[-9.14535371]])]),
     ("Al", "lda"): dict(Z=13, n_elec=[2, 1], rloc=0.45, cloc=[-8.49135116],
                         proj=[(0.46010427, [[5.08833953, -1.03784325], [2.67969975]]),
                               (0.53674439, [[2.19343827]])]),

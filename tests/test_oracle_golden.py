@@ -173,6 +173,82 @@ def test_silicon_lda_scf_vs_abinit():
         np.testing.assert_allclose(res["eigenvalues"][ik][:8], ref[ik], atol=1e-5)
 
 
+def test_silicon_pbe_scf_vs_abinit():
+    # reference: test/silicon_pbe.jl:6-41,57-61 ("Silicon PBE (large, Float64)": Ecut 25, fft 33, ABINIT eigenvalues and
+    # E_tot, test_tol 1e-5) -- the absolute pin of gga_x_pbe + gga_c_pbe and of the GGA potential term
+    m = Model(LATTICE, [Element("Si", functional="pbe")] * 2, POSITIONS, functionals=("gga_x_pbe", "gga_c_pbe"))
+    b = PlaneWaveBasis(m, 25, fft_size=(33, 33, 33), kcoords=KCOORDS, kweights=KWEIGHTS)
+    ref = [[-0.181210259413818, 0.258840553222639, 0.258840553225549, 0.258840553228459, 0.351692348652324,
+            0.351692348656259, 0.351692348660193, 0.380606400669216, 0.540705881744348, 0.540705883460555],
+           [-0.130553299114991, 0.062256443775155, 0.221871391287580, 0.221871391290802, 0.322398722411882,
+            0.386194327436667, 0.386194327439986, 0.546859898649217, 0.550571701390781, 0.550571701394327],
+           [-0.111170738096744, 0.074494899973125, 0.169461730083372, 0.169461730088140, 0.284305392082236,
+            0.330468937070505, 0.524509288492752, 0.524509288496625, 0.616964090764029, 0.619623658242765],
+           [-0.061054203629684, 0.009700769243041, 0.095769985640881, 0.180784778430457, 0.315000287382235,
+            0.471042322838057, 0.495281775946584, 0.517469860611792, 0.530124341745161, 0.539044739392045]]
+
+    def conv(info):
+        h = info["history_Etot"]
+        return len(h) > 1 and abs(h[-1] - h[-2]) < 1e-8
+    res = scf.self_consistent_field(b, nbandsalg=scf.AdaptiveBands(m, n_bands_converge=10), is_converged=conv)
+    assert res["energies"]["total"] == pytest.approx(-7.854477356672080, abs=1e-5)       # observed: 2e-8
+    for ik in range(4):
+        np.testing.assert_allclose(res["eigenvalues"][ik][:10], ref[ik], atol=1e-5)       # observed: 7e-7
+
+
+def test_iron_pbe_collinear_scf_vs_abinit():
+    # reference: test/iron_pbe.jl:6-70 (bcc Fe, GTH-PADE-q8, PBE, collinear spin, Fermi-Dirac T = 0.01, Ecut 20,
+    # fft 20, shifted 4x4x4 k-grid; ABINIT eigenvalues 5e-6, E_tot, magnetisation 5e-5) -- pins the spin-polarised
+    # GGA path, smearing / Fermi level, Kerker mixing and the d-channel projectors
+    from oracle.terms import guess_density as guess
+    ref = [[0.0603597727989307, 0.1964963273638626, 0.196496327424440, 0.279192222553112, 0.2791922225741613,
+            0.3415221335998876, 0.837882559419754, 0.883850560591423, 0.8838505606211768, 1.3135367355436536],
+           [0.1384929268069029, 0.1847168453364975, 0.223179759800174, 0.320070899985990, 0.3500724891746176,
+            0.4685757607370267, 0.541752194212558, 0.751365680734661, 0.8039132927796911, 1.3939297677405071],
+           [-0.017996603976028, 0.2383855826934185, 0.238385582734711, 0.248204676138927, 0.2509395500598295,
+            0.2776437400588896, 1.069915401940919, 1.088217176897224, 1.094997859335961, 1.0949978593466851],
+           [0.1102557166995405, 0.2077201723056727, 0.220685303120809, 0.289884460857327, 0.3490062808992303,
+            0.3571047250832524, 0.664551132243957, 0.890354172420178, 0.939822681382406, 1.2259972985258636],
+           [0.1723514110126840, 0.1723514110181127, 0.189598224957126, 0.315084007273243, 0.3150840073174671,
+            0.5487559496577702, 0.548755949657792, 0.571153866844390, 1.0611134432316718, 1.1887518709297569],
+           [0.1360541296075938, 0.1413608406233668, 0.337616953214017, 0.337616953257584, 0.3463728840905585,
+            0.4304010493995122, 0.688627292839765, 0.688627292852315, 0.885008380770321, 0.9722786718518246],
+           [0.0802990962833626, 0.3488798033726516, 0.348879803416372, 0.533263624117060, 0.560354114948579,
+            0.5603541149670136, 0.923281827089562, 0.967838872125574, 0.9678388721641925, 1.300215418446228],
+           [0.2341496631160049, 0.2737567834221212, 0.320646675118266, 0.590600827614029, 0.6440928824646408,
+            0.6458637753212415, 0.678343515679297, 0.838647690182280, 0.8763210347583158, 1.4092936521531203],
+           [-0.002234753604747, 0.4096246186291687, 0.409624618662776, 0.434260327970128, 0.5068101375084778,
+            0.5757957165012942, 1.137207834311533, 1.137826252874365, 1.170363096833071, 1.170363096849632],
+           [0.1518900787487526, 0.3293780680641614, 0.376401550325491, 0.512562269331525, 0.5557310122303195,
+            0.6261449425921871, 0.794097184155989, 0.967295197092196, 1.0000550921659532, 1.2999173820510477],
+           [0.2873355363445261, 0.2873355363447599, 0.319313192152575, 0.537629072823137, 0.5376290728591641,
+            0.6802062250711767, 0.704199805731151, 0.704199805731498, 1.1322730987840155, 1.255912074880981],
+           [0.2512356397409882, 0.315293666807424, 0.491297439253523, 0.4912974392811193, 0.5558649368408816,
+            0.556692128645629, 0.777563890322163, 0.7775638903489546, 0.9998569230219644, 1.1313796020728688]]
+    lat = 2.71176 * np.array([[-1, 1, 1], [1, -1, 1], [1, 1, -1]], dtype=float)
+    fe = Element("Fe", PspHgh.from_table("Fe", "lda-q8"))
+    m = Model(lat, [fe], [np.zeros(3)], functionals=("gga_x_pbe", "gga_c_pbe"), temperature=0.01, magnetic_moments=[4.0])
+    b = PlaneWaveBasis(m, 20, kgrid=(4, 4, 4), kshift=(0.5, 0.5, 0.5), fft_size=(20, 20, 20))
+    assert len(b.kpoints) == 12 and m.n_electrons == 8        # 6 irreducible k-points x 2 spins
+
+    def conv(info):
+        h = info["history_Etot"]
+        return len(h) > 1 and abs(h[-1] - h[-2]) < 1e-10
+    res = scf.self_consistent_field(b, rho=guess(b, [4.0]), mixing="kerker",
+                                    nbandsalg=scf.AdaptiveBands(m, n_bands_converge=10), is_converged=conv)
+    assert res["energies"]["total"] == pytest.approx(-18.21465922614397, abs=5e-6)       # observed: 1.1e-7
+    mag = float((res["rho"][0] - res["rho"][1]).sum() * b.dvol)
+    assert mag == pytest.approx(2.98199463, abs=5e-5)                                     # observed: 2.2e-5
+    # the irreducible k-points come from an orbit search, not spglib: match blocks to ABINIT's by their spectra
+    used = set()
+    for ik, kpt in enumerate(b.kpoints):
+        d = [np.abs(np.array(res["eigenvalues"][ik][:10]) - np.array(r)).max() for r in ref]
+        j = int(np.argmin(d))
+        assert d[j] < 5e-6 and (j < 6) == (kpt.spin == 0)                                # observed: 2.9e-6
+        used.add(j)
+    assert used == set(range(12))
+
+
 def test_oracle_matches_committed_fixture():
     # the oracle is frozen by tests/golden/si_block_fixture.npz (made by tests/golden/make_fixtures.py)
     import os
