@@ -325,3 +325,51 @@ int emu_small_chol(const double* O, int64_t ldo, int n, double* invR, int64_t ld
   return 0;
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// INT8-emulated FP64 GEMM bodies (i8emu_core.cuh) on the host
+// ------------------------------------------------------------------------------------------------
+#include "../../dftk.jl_b200/csrc/i8emu_core.cuh"
+extern "C" {
+// tables: q[n_mod], w[n_mod*4], P[4], returns operand bits
+int emu_i8_tables(int n_mod, int64_t K, int* q, double* w, double* P) {
+  I8Tables T = i8_make_tables(n_mod, K);
+  for (int t = 0; t < n_mod; ++t) {
+    q[t] = T.q[t];
+    for (int j = 0; j < I8_LIMBS; ++j) w[t * I8_LIMBS + j] = T.w[t][j];
+  }
+  for (int j = 0; j < I8_LIMBS; ++j) P[j] = T.P[j];
+  return T.bits;
+}
+// C (m x n complex, column-major) = A^H B for A (k x m), B (k x n) complex column-major, through int8 residues
+int emu_i8_zgemm_cn(int n_mod, int64_t m, int64_t n, int64_t k, const double* A, const double* B, double* C) {
+  I8Tables T = i8_make_tables(n_mod, 2 * k);
+  const cplx* a = (const cplx*)A;
+  const cplx* b = (const cplx*)B;
+  std::vector<int> ea(m), eb(n);
+  std::vector<signed char> ra((size_t)n_mod * 2 * m * k), rb((size_t)n_mod * 2 * n * k);
+  for (int64_t i = 0; i < m; ++i) {
+    double mx = 0.0;
+    for (int64_t r = 0; r < k; ++r) mx = fmax(mx, fmax(fabs(a[r + k * i].x), fabs(a[r + k * i].y)));
+    ea[i] = i8_scale_exponent(mx, T.bits);
+    for (int64_t r = 0; r < k; ++r) i8_residues_entry(a[r + k * i], ea[i], n_mod, ra.data() + (r + k * i), (long long)m * k);
+  }
+  for (int64_t j = 0; j < n; ++j) {
+    double mx = 0.0;
+    for (int64_t r = 0; r < k; ++r) mx = fmax(mx, fmax(fabs(b[r + k * j].x), fabs(b[r + k * j].y)));
+    eb[j] = i8_scale_exponent(mx, T.bits);
+    for (int64_t r = 0; r < k; ++r) i8_residues_entry(b[r + k * j], eb[j], n_mod, rb.data() + (r + k * j), (long long)n * k);
+  }
+  cplx* c = (cplx*)C;
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t i = 0; i < m; ++i) {
+      int rre[I8_MAX_MODULI], rim[I8_MAX_MODULI];
+      for (int t = 0; t < n_mod; ++t)
+        i8_dot_conj(ra.data() + (size_t)(2 * t) * m * k + k * i, ra.data() + (size_t)(2 * t + 1) * m * k + k * i,
+                    rb.data() + (size_t)(2 * t) * n * k + k * j, rb.data() + (size_t)(2 * t + 1) * n * k + k * j, k,
+                    i8_modulus(t), &rre[t], &rim[t]);
+      c[i + m * j] = make_double2(ldexp(i8_crt(rre, T), -(ea[i] + eb[j])), ldexp(i8_crt(rim, T), -(ea[i] + eb[j])));
+    }
+  return T.bits;
+}
+}

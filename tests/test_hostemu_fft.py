@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "hostemu", "libhostemu.so")
 def emu():
     src = os.path.join(HERE, "hostemu", "emu.cu")
     csrc = os.path.join(HERE, "..", "dftk.jl_b200", "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_radix_gen.cuh", "xc_core.cuh", "forces_core.cuh", "lobpcg_small.cuh", "fft_reg_fwd.cuh")]
+    deps = [src] + [os.path.join(csrc, f) for f in ("fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_radix_gen.cuh", "xc_core.cuh", "forces_core.cuh", "lobpcg_small.cuh", "i8emu_core.cuh", "fft_reg_fwd.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
                                "-Wno-deprecated-gpu-targets", "-o", SO, src])
@@ -300,3 +300,59 @@ def test_emulated_small_cholesky_failure_modes(emu):
     Ocm[2, 2] = np.nan
     assert emu.emu_small_chol(_p(Ocm), ctypes.c_int64(n), n, _p(invR), ctypes.c_int64(n), _p(stats)) == 0
     assert stats[0] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# INT8-emulated FP64 GEMM (i8emu_core.cuh; groundwork for a tcgen05 kind::i8 path, not on the default path)
+# ---------------------------------------------------------------------------------------------------------------
+I8_MODULI = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191, 181, 179, 173]
+
+
+@pytest.mark.parametrize("n_mod,K", [(12, 1000), (16, 17116), (17, 529718), (20, 4096)])
+def test_emulated_i8_crt_tables(emu, n_mod, K):
+    import math
+    q = (ctypes.c_int * n_mod)()
+    w = (ctypes.c_double * (4 * n_mod))()
+    Pl = (ctypes.c_double * 4)()
+    bits = emu.emu_i8_tables(n_mod, ctypes.c_int64(K), q, w, Pl)
+    p = I8_MODULI[:n_mod]
+    assert all(math.gcd(a, b) == 1 for i, a in enumerate(p) for b in p[i + 1:])
+    P = math.prod(p)
+    assert sum(int(Pl[j]) << (40 * j) for j in range(4)) == P
+    for t, pt in enumerate(p):
+        W = P // pt
+        assert sum(int(w[4 * t + j]) << (40 * j) for j in range(4)) == W
+        assert (W * q[t]) % pt == 1
+    assert K * 4 ** bits <= P // 4                                 # the exact product cannot wrap
+    assert bits == 61 or P // 4 < K * 4 ** (bits + 2)              # and the budget is the largest such (cap: int64)
+
+
+@pytest.mark.parametrize("n_mod", [12, 14, 16, 18])
+def test_emulated_i8_zgemm_matches_exact(emu, n_mod):
+    """A^H B through int8 residues / int32 accumulation / CRT against exact rational arithmetic on the same FP64 inputs;
+    inputs with the dynamic range of projector tables and orbital coefficients (17 orders of magnitude)."""
+    import math
+    rng = np.random.default_rng(n_mod)
+    k, m, n = 3000, 5, 4
+    decay = np.exp(-np.linspace(0, 38, k))[:, None]
+    A = (rng.standard_normal((k, m)) + 1j * rng.standard_normal((k, m))) * decay * rng.uniform(1e-3, 1e3, (1, m))
+    B = (rng.standard_normal((k, n)) + 1j * rng.standard_normal((k, n))) * np.sqrt(decay) * rng.uniform(1e-2, 1e2, (1, n))
+    Acm, Bcm = np.ascontiguousarray(A.T), np.ascontiguousarray(B.T)
+    C = np.zeros((n, m), dtype=complex)
+    bits = emu.emu_i8_zgemm_cn(n_mod, ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(k), _p(Acm), _p(Bcm), _p(C))
+    from fractions import Fraction
+    fr = lambda x: Fraction(float(x))
+    exact = np.zeros((m, n), dtype=complex)
+    bound = np.zeros((m, n))
+    for i in range(m):
+        for j in range(n):
+            re = sum(fr(A[r, i].real) * fr(B[r, j].real) + fr(A[r, i].imag) * fr(B[r, j].imag) for r in range(k))
+            im = sum(fr(A[r, i].real) * fr(B[r, j].imag) - fr(A[r, i].imag) * fr(B[r, j].real) for r in range(k))
+            exact[i, j] = complex(float(re), float(im))
+            # truncation of both operands to `bits` bits relative to their column maxima
+            bound[i, j] = 2 * k * 2.0 ** (1 - bits) * np.abs(A[:, i]).max() * np.abs(B[:, j]).max() * 2
+    err = np.abs(C.T - exact)
+    assert np.all(err <= bound + 1e-300), (bits, (err / bound).max())
+    if n_mod >= 16:      # as accurate as an FP64 GEMM on these inputs
+        ref = A.conj().T @ B
+        assert err.max() <= 4 * np.abs(ref - exact).max() + 1e-18 * np.abs(exact).max()
