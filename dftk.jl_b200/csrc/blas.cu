@@ -387,6 +387,11 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
     ctx->launches++;
     return;
   }
+  if (ctx->gemm_backend == 2 && transA == 2 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.x == 0.0 && beta.y == 0.0) {
+    // experimental: FP64 by INT8 residues + CRT (i8emu.cu; reference pipeline, groundwork for a tcgen05 kind::i8 kernel)
+    zgemm_i8_cn(ctx, m, n, k, A, lda, B, ldb, C, ldc);
+    return;
+  }
   if (k == 0) {
     // C = beta C
     LAUNCH(ctx, k_reduce_partials, (unsigned)((m * n + 255) / 256), 256, 0, (const cplx*)nullptr, 0, m, n,

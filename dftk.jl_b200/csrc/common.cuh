@@ -90,7 +90,7 @@ struct dftk_b200_ctx {
   ncclComm_t nccl = nullptr;
   int rank = 0, nranks = 1;
   int64_t launches = 0;
-  int gemm_backend = 0;   // 0 = own DMMA kernels, 1 = cuBLAS (A/B comparison only)
+  int gemm_backend = 0;   // 0 = own DMMA kernels, 1 = cuBLAS (A/B comparison only), 2 = experimental INT8-residue emulation (i8emu.cu)
   int band_chunk = 0;     // 0 = auto
   int fft_engine = 0;     // 0 = register two-pass engine where a factor pair exists, 1 = generic Stockham (applies to grids created afterwards)
   int gemm_stages = 2;    // cp.async ring depth of the DMMA GEMMs (2 -> 4 CTAs/SM, 3 -> 2 CTAs/SM)

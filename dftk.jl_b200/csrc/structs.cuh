@@ -83,6 +83,9 @@ void xc_evaluate(dftk_b200_ctx* ctx, int mask, int n_spin, bool gga, int64_t N, 
                  const double* sigma, double* e, double* vrho, double* vsigma);
 void symmetrize_fourier(dftk_b200_grid* g, const cplx* in, cplx* out, int n_sym, const int* invS_host,
                         const double* tau_host);
+// i8emu.cu (experimental, option gemm_backend = 2)
+void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                 cplx* C, int64_t ldc);
 // forces.cu
 void local_forces(dftk_b200_grid* g, const cplx* w, int n_atoms, const double* pos_host, double* out_host);
 void kb_nonlocal_force_rows(dftk_b200_kblock* kb, const cplx* psi, const double* occ_w_host, int64_t n_bands,

@@ -120,6 +120,28 @@ def test_band_energies_and_density(si):
     np.testing.assert_allclose(rho.cpu().numpy(), ref, atol=1e-12 * ref.max())
 
 
+@pytest.mark.skip(reason="round-2 groundwork: the INT8-residue reference pipeline (gemm_backend = 2) has only been "
+                         "validated in host emulation (tests/test_hostemu_fft.py), not on hardware yet")
+@pytest.mark.parametrize("shape", [(3000, 7, 5), (70000, 20, 9)])
+def test_i8_emulated_gemm_matches_fp64(shape):
+    from gpu_common import ctx
+    K, m, n = shape
+    c = ctx()
+    g = torch.Generator(device="cpu").manual_seed(1)
+    decay = torch.exp(-torch.linspace(0, 30, K, dtype=torch.float64))
+    A = (torch.view_as_complex(torch.randn(m, K, 2, generator=g, dtype=torch.float64)) * decay).to(c.device)
+    B = (torch.view_as_complex(torch.randn(n, K, 2, generator=g, dtype=torch.float64)) * decay.sqrt()).to(c.device)
+    ref = torch.zeros((n, m), dtype=torch.complex128, device=c.device)
+    c.zgemm("C", A, B, ref)
+    c.set_option("gemm_backend", 2)
+    try:
+        C = torch.zeros_like(ref)
+        c.zgemm("C", A, B, C)
+    finally:
+        c.set_option("gemm_backend", 0)
+    assert (C - ref).abs().max().item() < 1e-14 * ref.abs().max().item() * K ** 0.5
+
+
 @pytest.mark.parametrize("backend,small", [(0, 1), (1, 0), (0, 0)])
 def test_lobpcg_matches_oracle(si, backend, small):
     # small = 1: fused small-matrix kernels (lobpcg_small.cuh, the default for <= 32 bands);
