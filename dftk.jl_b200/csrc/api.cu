@@ -118,6 +118,7 @@ static int ctx_create_common(int device, dftk_b200_ctx** out) {
   fft_set_attributes();
   reg_set_attributes();
   blas_set_attributes();
+  i8tc_set_attributes();
   *out = c;
   return 0;
 }

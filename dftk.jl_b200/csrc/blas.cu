@@ -387,9 +387,9 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
     ctx->launches++;
     return;
   }
-  if (ctx->gemm_backend == 2 && transA == 2 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.x == 0.0 && beta.y == 0.0) {
+  if ((ctx->gemm_backend == 2 || ctx->gemm_backend == 3) && transA == 2 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.x == 0.0 && beta.y == 0.0) {
     // experimental: FP64 by INT8 residues + CRT (i8emu.cu; reference pipeline, groundwork for a tcgen05 kind::i8 kernel)
-    zgemm_i8_cn(ctx, m, n, k, A, lda, B, ldb, C, ldc);
+    zgemm_i8_cn(ctx, m, n, k, A, lda, B, ldb, C, ldc, ctx->gemm_backend == 3);
     return;
   }
   if (k == 0) {

@@ -37,6 +37,16 @@ k_i8_residues(const cplx* __restrict__ X, int64_t ld, int64_t n_rows, int64_t n_
   i8_residues_entry(X[r + ld * col], e[col], n_mod, planes + (r + n_rows * col), (long long)n_rows * n_cols);
 }
 
+// same with a padded leading dimension (tensor-core path: rows 16-byte aligned, K padded with zeros to the stage size)
+__global__ void __launch_bounds__(256)
+k_i8_residues_ld(const cplx* __restrict__ X, int64_t ld, int64_t n_rows, int64_t n_cols, int64_t ldk, const int* __restrict__ e,
+                 int n_mod, signed char* __restrict__ planes) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t col = blockIdx.y;
+  if (r >= n_rows) return;
+  i8_residues_entry(X[r + ld * col], e[col], n_mod, planes + (r + ldk * col), (long long)ldk * n_cols);
+}
+
 // one warp per (i, j, t): residues of conj(a_i) . b_j modulo p_t;  res[(2 t + part)][j][i]
 __global__ void __launch_bounds__(256)
 k_i8_dot_ref(const signed char* __restrict__ ra, const signed char* __restrict__ rb, int64_t m, int64_t n, int64_t k,
@@ -99,28 +109,42 @@ static I8Tables tables_for(int64_t K) {
   return i8_make_tables(I8_MAX_MODULI, K);
 }
 
-// C (m x n) = A^H B,  A: k x m, B: k x n (column-major, complex)
+// C (m x n) = A^H B,  A: k x m, B: k x n (column-major, complex).  tensor_cores: integer products by k_i8_gemm_tc (i8tc.cu)
 void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
-                 cplx* C, int64_t ldc) {
+                 cplx* C, int64_t ldc, bool tensor_cores) {
   if (m == 0 || n == 0) return;
   REQUIRE(k >= 1 && m <= 65535 && n <= 65535, "zgemm_i8: unsupported shape");
   const I8Tables T = tables_for(2 * k);
-  const size_t plane_a = (size_t)m * k, plane_b = (size_t)n * k;
-  const size_t bytes = 2 * (size_t)T.n_mod * (plane_a + plane_b) + (size_t)(m + n) * sizeof(int) + 64 +
-                       2 * (size_t)T.n_mod * m * n * sizeof(int);
+  const int64_t ldk = tensor_cores ? (k + 127) / 128 * 128 : k;
+  const int n_chunks = (int)((ldk + I8_K_CHUNK - 1) / I8_K_CHUNK);
+  const size_t plane_a = (size_t)m * ldk, plane_b = (size_t)n * ldk;
+  const size_t n_res = 2 * (size_t)T.n_mod * m * n;
+  const size_t bytes = (size_t)(m + n) * sizeof(int) + 64 + n_res * sizeof(int) + 2 * (size_t)T.n_mod * (plane_a + plane_b) + 256 +
+                       (tensor_cores ? n_res * n_chunks * sizeof(short) : 0);
   char* ws = (char*)ctx->gemm_ws.ensure(bytes);
   int* ea = (int*)ws;
   int* eb = ea + m;
   int* res = eb + n;
-  signed char* ra = (signed char*)(res + 2 * (size_t)T.n_mod * m * n);
+  signed char* ra = (signed char*)(res + n_res);
+  ra += (16 - ((uintptr_t)ra & 15)) & 15;                       // cp.async needs 16-byte aligned rows
   signed char* rb = ra + 2 * (size_t)T.n_mod * plane_a;
+  short* part = (short*)(rb + 2 * (size_t)T.n_mod * plane_b);
   LAUNCH(ctx, k_i8_col_exponent, (unsigned)m, 256, 0, A, lda, k, T.bits, ea);
   LAUNCH(ctx, k_i8_col_exponent, (unsigned)n, 256, 0, B, ldb, k, T.bits, eb);
-  LAUNCH(ctx, k_i8_residues, dim3((unsigned)((k + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, (const int*)ea, T.n_mod, ra);
-  LAUNCH(ctx, k_i8_residues, dim3((unsigned)((k + 255) / 256), (unsigned)n), 256, 0, B, ldb, k, n, (const int*)eb, T.n_mod, rb);
-  const int64_t warps = m * n * T.n_mod;
-  LAUNCH(ctx, k_i8_dot_ref, (unsigned)((warps * 32 + 255) / 256), 256, 0, (const signed char*)ra, (const signed char*)rb, m, n, k,
-         T.n_mod, res);
+  if (tensor_cores) {
+    CUDA_CHECK(cudaMemsetAsync(ra, 0, 2 * (size_t)T.n_mod * (plane_a + plane_b), ctx->stream));      // zero K padding
+    LAUNCH(ctx, k_i8_residues_ld, dim3((unsigned)((k + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, ldk, (const int*)ea,
+           T.n_mod, ra);
+    LAUNCH(ctx, k_i8_residues_ld, dim3((unsigned)((k + 255) / 256), (unsigned)n), 256, 0, B, ldb, k, n, ldk, (const int*)eb,
+           T.n_mod, rb);
+    i8tc_products(ctx, ra, rb, m, n, ldk, T.n_mod, part, res);
+  } else {
+    LAUNCH(ctx, k_i8_residues, dim3((unsigned)((k + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, (const int*)ea, T.n_mod, ra);
+    LAUNCH(ctx, k_i8_residues, dim3((unsigned)((k + 255) / 256), (unsigned)n), 256, 0, B, ldb, k, n, (const int*)eb, T.n_mod, rb);
+    const int64_t warps = m * n * T.n_mod;
+    LAUNCH(ctx, k_i8_dot_ref, (unsigned)((warps * 32 + 255) / 256), 256, 0, (const signed char*)ra, (const signed char*)rb, m, n,
+           k, T.n_mod, res);
+  }
   LAUNCH(ctx, k_i8_crt, (unsigned)((m * n + 127) / 128), 128, 0, (const int*)res, m, n, T, (const int*)ea, (const int*)eb, C, ldc);
 }
 

@@ -50,7 +50,8 @@ int dftk_b200_mem_info(dftk_b200_ctx* ctx, int64_t* free_bytes, int64_t* total_b
 /* number of kernel launches issued by this library on the context since creation / last reset */
 int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset);
 /* tuning knobs: "gemm_backend" (0 = own DMMA kernels, 1 = cuBLAS, for A/B comparison and peak calibration only,
- * 2 = experimental INT8-residue emulation of C = A'B, a reference pipeline that is not validated on hardware yet),
+ * 2 / 3 = experimental INT8-residue emulation of C = A'B with the integer products on CUDA cores / on the tensor cores
+ * (tcgen05.mma.kind::i8); groundwork that has not been validated on hardware yet),
  * "gemm_stages" (cp.async ring depth 2|3), "band_chunk" (bands per batched-FFT launch, 0 = auto),
  * "fft_engine" (0 = register two-pass engine where a factor pair exists, 1 = generic Stockham; applies to grids
  * created afterwards), "small_dense" (1 = fused small-matrix kernels for LOBPCG solves with <= 32 bands, 0 = the

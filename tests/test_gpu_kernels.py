@@ -122,8 +122,9 @@ def test_band_energies_and_density(si):
 
 @pytest.mark.skip(reason="round-2 groundwork: the INT8-residue reference pipeline (gemm_backend = 2) has only been "
                          "validated in host emulation (tests/test_hostemu_fft.py), not on hardware yet")
-@pytest.mark.parametrize("shape", [(3000, 7, 5), (70000, 20, 9)])
-def test_i8_emulated_gemm_matches_fp64(shape):
+@pytest.mark.parametrize("backend", [2, 3])      # 2: integer products on CUDA cores, 3: tcgen05.mma.kind::i8 (i8tc.cu)
+@pytest.mark.parametrize("shape", [(3000, 7, 5), (70000, 20, 9), (140000, 150, 130)])
+def test_i8_emulated_gemm_matches_fp64(shape, backend):
     from gpu_common import ctx
     K, m, n = shape
     c = ctx()
@@ -133,7 +134,7 @@ def test_i8_emulated_gemm_matches_fp64(shape):
     B = (torch.view_as_complex(torch.randn(n, K, 2, generator=g, dtype=torch.float64)) * decay.sqrt()).to(c.device)
     ref = torch.zeros((n, m), dtype=torch.complex128, device=c.device)
     c.zgemm("C", A, B, ref)
-    c.set_option("gemm_backend", 2)
+    c.set_option("gemm_backend", backend)
     try:
         C = torch.zeros_like(ref)
         c.zgemm("C", A, B, C)
