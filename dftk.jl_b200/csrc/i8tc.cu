@@ -220,7 +220,8 @@ __global__ void k_i8_sum_chunks(const short* __restrict__ part, int n_chunks, in
 }
 
 void i8tc_set_attributes() {
-  cudaFuncSetAttribute(k_i8_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  // experimental kernel: never let a failure here leak into the error state of the product path
+  if (cudaFuncSetAttribute(k_i8_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM) != cudaSuccess) cudaGetLastError();
 }
 
 // integer stage of C = A^H B on the tensor cores; ra / rb: padded residue planes, res: int residues [(2 t + part)][j][i]
