@@ -79,7 +79,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
 // part[(chunk)][(2 t + part)][j][i] int16: residues of this chunk (summed modulo p by k_i8_sum_chunks)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_i8_gemm_tc(const signed char* __restrict__ ra, const signed char* __restrict__ rb, int64_t m, int64_t n, int64_t ldk,
-             int n_mod, int n_chunks, int64_t chunk_len, short* __restrict__ part) {
+             int n_mod, int n_chunks, int64_t chunk_len, short* __restrict__ part, int swap_lbo_sbo, int simple) {
   extern __shared__ unsigned char tc_raw[];
   unsigned char* sm = (unsigned char*)(((uintptr_t)tc_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
@@ -117,6 +117,23 @@ k_i8_gemm_tc(const signed char* __restrict__ ra, const signed char* __restrict__
     src[1] = ra + ((size_t)(2 * t + 1) * m) * ldk;
     src[2] = rb + ((size_t)(2 * t) * n) * ldk;
     src[3] = rb + ((size_t)(2 * t + 1) * n) * ldk;
+    if (simple) {
+      // bring-up mode: one stage, plain 16-byte loads/stores, a full CTA barrier per K block (no cp.async, no overlap)
+      for (int it = 0; it < n_iters; ++it) {
+        if (it > 0) tc_mbar_wait(&empty_bar[0], (uint32_t)((it - 1) & 1));
+        const int64_t kb = k_begin + (int64_t)it * TC_BK;
+        for (int q = tid; q < 4096; q += 128) {
+          const int tile = q >> 10, r = (q >> 3) & 127, c16 = q & 7;
+          const int64_t rows = tile < 2 ? m : n;
+          int64_t row = (tile < 2 ? i0 : j0) + r;
+          if (row >= rows) row = rows - 1;
+          const uint4 v = *reinterpret_cast<const uint4*>(src[tile] + (size_t)row * ldk + kb + c16 * 16);
+          *reinterpret_cast<uint4*>(sm + tile * TC_TILE_BYTES + c16 * (TC_M * 16) + (r >> 3) * 128 + (r & 7) * 16) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_mbar_arrive(&full_bar[0]);
+      }
+    } else
     for (int it = 0; it < n_iters + TC_STAGES - 1; ++it) {
       if (it < n_iters) {
         const int s = it % TC_STAGES;
@@ -176,11 +193,12 @@ k_i8_gemm_tc(const signed char* __restrict__ ra, const signed char* __restrict__
     // ---------------- MMA issuer
     // instruction descriptor: D = s32, A = B = s8, both K-major, N = 128, M = 128  (cute::UMMA::InstrDescriptor)
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-    const uint32_t lbo = I8TC_SWAP_LBO_SBO ? 128u : (uint32_t)(TC_M * 16);
-    const uint32_t sbo = I8TC_SWAP_LBO_SBO ? (uint32_t)(TC_M * 16) : 128u;
+    const bool swp = (I8TC_SWAP_LBO_SBO != 0) != (swap_lbo_sbo != 0);
+    const uint32_t lbo = swp ? 128u : (uint32_t)(TC_M * 16);
+    const uint32_t sbo = swp ? (uint32_t)(TC_M * 16) : 128u;
     for (int it = 0; it < n_iters; ++it) {
-      const int s = it % TC_STAGES;
-      tc_mbar_wait(&full_bar[s], (uint32_t)((it / TC_STAGES) & 1));
+      const int s = simple ? 0 : it % TC_STAGES;
+      tc_mbar_wait(&full_bar[s], (uint32_t)((simple ? it : it / TC_STAGES) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         const uint32_t base = tc_smem_u32(sm + (size_t)s * TC_STAGE_BYTES);
@@ -230,7 +248,11 @@ void i8tc_products(dftk_b200_ctx* ctx, const signed char* ra, const signed char*
   const int64_t chunk_len = I8_K_CHUNK;                         // multiple of TC_BK
   const int n_chunks = (int)((ldk + chunk_len - 1) / chunk_len);
   dim3 grid((unsigned)((m + TC_M - 1) / TC_M), (unsigned)((n + TC_N - 1) / TC_N), (unsigned)(n_mod * n_chunks));
-  LAUNCH(ctx, k_i8_gemm_tc, grid, TC_THREADS, TC_SMEM, ra, rb, m, n, ldk, n_mod, n_chunks, chunk_len, part);
+  // bring-up switches (see scripts/next_round_first_call.sh): descriptor convention and the unpipelined variant
+  const char* e1 = getenv("DFTK_B200_I8TC_SWAP");
+  const char* e2 = getenv("DFTK_B200_I8TC_SIMPLE");
+  LAUNCH(ctx, k_i8_gemm_tc, grid, TC_THREADS, TC_SMEM, ra, rb, m, n, ldk, n_mod, n_chunks, chunk_len, part,
+         e1 && e1[0] == '1' ? 1 : 0, e2 && e2[0] == '1' ? 1 : 0);
   const int64_t tot = 2 * (int64_t)n_mod * m * n;
   LAUNCH(ctx, k_i8_sum_chunks, (unsigned)((tot + 255) / 256), 256, 0, (const short*)part, n_chunks, n_mod, m * n, res);
 }
