@@ -39,11 +39,18 @@ __device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(tc_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\tTC_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra TC_DONE;\n\tbra TC_WAIT;\n\tTC_DONE:\n\t}\n"
-      :: "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+  // bounded wait (bring-up): a protocol error traps after ~2 s instead of hanging the GPU
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok) : "r"(tc_smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tc_smem_u32(bar)) : "memory");
