@@ -202,19 +202,21 @@ static int run_variant(int variant) {
   return bad == 0;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  // usage: i8probe <variant 0..3>   one descriptor convention (separate processes: a faulting kernel poisons the context)
+  //        i8probe rate             issue-rate measurement
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s, sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   if (prop.major < 10) { printf("needs sm_100a\n"); return 1; }
-  printf("(1) single tcgen05.mma.kind::i8 128 x N x 32 against the CPU:\n");
-  int ok = 0;
-  for (int v = 0; v < 4; ++v) {
-    int r = run_variant<64>(v);
-    if (r < 0) { printf("  (a failed launch poisons the context: rerun with fewer variants)\n"); return 2; }
-    ok |= r << v;
+  if (argc < 2) { printf("usage: %s <0|1|2|3|rate>\n", argv[0]); return 1; }
+  if (argv[1][0] != 'r') {
+    const int v = atoi(argv[1]);
+    printf("(1) single tcgen05.mma.kind::i8 128 x N x 32 against the CPU, descriptor variant %d:\n", v);
+    const int r = run_variant<64>(v);
+    if (r > 0) run_variant<256>(v);
+    return r > 0 ? 0 : 3;
   }
-  for (int v = 0; v < 4; ++v) if ((ok >> v) & 1) run_variant<256>(v);
   printf("(2) issue rate, 128 x 256 x 32 MMAs on resident operands, one CTA per SM:\n");
   const int iters = 4096;
   long long* dc;
