@@ -95,6 +95,28 @@ HD void i8_dot_conj(const signed char* __restrict__ ar, const signed char* __res
   *im = i8_sym(sim, p);
 }
 
+// same for a . b without conjugation (update-type products C = A B: rows of A against columns of B), strided operands:
+// returns (Ar.Br - Ai.Bi) mod p and (Ar.Bi + Ai.Br) mod p
+HD void i8_dot_plain(const signed char* __restrict__ ar, const signed char* __restrict__ ai, long long sa,
+                     const signed char* __restrict__ br, const signed char* __restrict__ bi, long long sb, long long K, int p,
+                     int* re, int* im) {
+  int sre = 0, sim = 0;
+  for (long long k0 = 0; k0 < K; k0 += I8_K_CHUNK) {
+    const long long k1 = k0 + I8_K_CHUNK < K ? k0 + I8_K_CHUNK : K;
+    int x1 = 0, x2 = 0, x3 = 0, x4 = 0;
+    for (long long k = k0; k < k1; ++k) {
+      x1 += (int)ar[k * sa] * (int)br[k * sb];
+      x2 += (int)ai[k * sa] * (int)bi[k * sb];
+      x3 += (int)ar[k * sa] * (int)bi[k * sb];
+      x4 += (int)ai[k * sa] * (int)br[k * sb];
+    }
+    sre = (sre + x1 % p - x2 % p) % p;
+    sim = (sim + x3 % p + x4 % p) % p;
+  }
+  *re = i8_sym(sre, p);
+  *im = i8_sym(sim, p);
+}
+
 // CRT: residues r[t] (any representatives) of the integer C' (|C'| <= P/4)  ->  C' as a double (faithfully rounded)
 HD double i8_crt(const int* __restrict__ r, const I8Tables& T) {
   const double B40 = 1099511627776.0;    // 2^40

@@ -373,3 +373,36 @@ int emu_i8_zgemm_cn(int n_mod, int64_t m, int64_t n, int64_t k, const double* A,
   return T.bits;
 }
 }
+extern "C" {
+// C (m x n) = A B for A (m x k), B (k x n) complex column-major: scales per ROW of A and per column of B
+int emu_i8_zgemm_nn(int n_mod, int64_t m, int64_t n, int64_t k, const double* A, const double* B, double* C) {
+  I8Tables T = i8_make_tables(n_mod, 2 * k);
+  const cplx* a = (const cplx*)A;
+  const cplx* b = (const cplx*)B;
+  std::vector<int> ea(m), eb(n);
+  std::vector<signed char> ra((size_t)n_mod * 2 * m * k), rb((size_t)n_mod * 2 * n * k);   // A planes keep A's layout (m fastest)
+  for (int64_t i = 0; i < m; ++i) {
+    double mx = 0.0;
+    for (int64_t r = 0; r < k; ++r) mx = fmax(mx, fmax(fabs(a[i + m * r].x), fabs(a[i + m * r].y)));
+    ea[i] = i8_scale_exponent(mx, T.bits);
+    for (int64_t r = 0; r < k; ++r) i8_residues_entry(a[i + m * r], ea[i], n_mod, ra.data() + (i + m * r), (long long)m * k);
+  }
+  for (int64_t j = 0; j < n; ++j) {
+    double mx = 0.0;
+    for (int64_t r = 0; r < k; ++r) mx = fmax(mx, fmax(fabs(b[r + k * j].x), fabs(b[r + k * j].y)));
+    eb[j] = i8_scale_exponent(mx, T.bits);
+    for (int64_t r = 0; r < k; ++r) i8_residues_entry(b[r + k * j], eb[j], n_mod, rb.data() + (r + k * j), (long long)n * k);
+  }
+  cplx* c = (cplx*)C;
+  for (int64_t j = 0; j < n; ++j)
+    for (int64_t i = 0; i < m; ++i) {
+      int rre[I8_MAX_MODULI], rim[I8_MAX_MODULI];
+      for (int t = 0; t < n_mod; ++t)
+        i8_dot_plain(ra.data() + (size_t)(2 * t) * m * k + i, ra.data() + (size_t)(2 * t + 1) * m * k + i, m,
+                     rb.data() + (size_t)(2 * t) * n * k + k * j, rb.data() + (size_t)(2 * t + 1) * n * k + k * j, 1, k,
+                     i8_modulus(t), &rre[t], &rim[t]);
+      c[i + m * j] = make_double2(ldexp(i8_crt(rre, T), -(ea[i] + eb[j])), ldexp(i8_crt(rim, T), -(ea[i] + eb[j])));
+    }
+  return T.bits;
+}
+}

@@ -356,3 +356,26 @@ def test_emulated_i8_zgemm_matches_exact(emu, n_mod):
     if n_mod >= 16:      # as accurate as an FP64 GEMM on these inputs
         ref = A.conj().T @ B
         assert err.max() <= 4 * np.abs(ref - exact).max() + 1e-18 * np.abs(exact).max()
+
+
+def test_emulated_i8_update_product_matches_exact(emu):
+    """C = A B (update type: the P (D P' psi) half of the nonlocal term, K = n_proj) through int8 residues with one scale
+    per row of A and per column of B, against exact rational arithmetic."""
+    from fractions import Fraction
+    rng = np.random.default_rng(3)
+    m, k, n = 40, 130, 6
+    A = (rng.standard_normal((m, k)) + 1j * rng.standard_normal((m, k))) * np.exp(-np.linspace(0, 25, m))[:, None]
+    B = (rng.standard_normal((k, n)) + 1j * rng.standard_normal((k, n))) * rng.uniform(1e-4, 1e2, (1, n))
+    Acm, Bcm = np.ascontiguousarray(A.T), np.ascontiguousarray(B.T)         # column-major m x k and k x n
+    C = np.zeros((n, m), dtype=complex)
+    bits = emu.emu_i8_zgemm_nn(16, ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(k), _p(Acm), _p(Bcm), _p(C))
+    assert bits >= 55
+    fr = lambda x: Fraction(float(x))
+    for i in range(0, m, 7):
+        for j in range(n):
+            re = sum(fr(A[i, r].real) * fr(B[r, j].real) - fr(A[i, r].imag) * fr(B[r, j].imag) for r in range(k))
+            im = sum(fr(A[i, r].real) * fr(B[r, j].imag) + fr(A[i, r].imag) * fr(B[r, j].real) for r in range(k))
+            ex = complex(float(re), float(im))
+            tol = 4 * k * 2.0 ** (1 - bits) * np.abs(A[i]).max() * np.abs(B[:, j]).max()
+            assert abs(C[j, i] - ex) <= tol
+            assert abs(C[j, i] - ex) <= 4 * abs((A @ B)[i, j] - ex) + 1e-17 * np.abs(A[i]).max() * np.abs(B[:, j]).max() * k
