@@ -3,7 +3,7 @@
 #   gpurun --timeout 1200 -- 'bash scripts/next_round_first_call.sh > gpurun_out/i8_bringup.log 2>&1'
 set -x
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/i8probe scripts/tcgen05_i8_probe.cu
-for v in 0 1 2 3 rate; do timeout 60 /tmp/i8probe $v; done
+for v in 0 1 2 3 mn0 mn1 rate; do timeout 60 /tmp/i8probe $v; done
 export DFTK_B200_EXPERIMENTAL=1
 # reference pipeline (backend 2: integer products on CUDA cores) against the FP64 DMMA GEMM
 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -x -k "i8_emulated and -2]"

@@ -126,6 +126,92 @@ __global__ void __launch_bounds__(128) probe_mma(const int8_t* __restrict__ A, c
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(N_ < 32 ? 32 : N_) : "memory");
 }
 
+// A in MN-major form (the update-type products: output rows contiguous in the stored residue planes).  Canonical no-swizzle
+// MN-major layout (cute: ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)), T = 16 bytes): core matrix = 8 K-rows of 16 M-contiguous bytes;
+// element (m, k) at (m / 16) * sbo + (k / 8) * lbo + (k % 8) * 16 + m % 16.   variant bit 1 swaps the two descriptor fields.
+__global__ void __launch_bounds__(128) probe_mma_mn(const int8_t* __restrict__ A_km, const int8_t* __restrict__ B, int32_t* __restrict__ D,
+                                                   int variant) {
+  constexpr int N_ = 64;
+  __shared__ __align__(1024) int8_t sA[M_ * K_];
+  __shared__ __align__(1024) int8_t sB[N_ * K_];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t lboA = 128, sboA = (K_ / 8) * 128;                 // core matrices ordered [m / 16][k / 8]
+  const uint32_t sboB = 128, lboB = (N_ / 8) * 128;
+  for (int e = tid; e < M_ * K_; e += 128) {                        // A_km: K x M, M contiguous
+    const int k = e / M_, m = e % M_;
+    sA[(m / 16) * sboA + (k / 8) * lboA + (k % 8) * 16 + m % 16] = A_km[e];
+  }
+  for (int e = tid; e < N_ * K_; e += 128) sB[tile_off(e / K_, e % K_, lboB, sboB)] = B[e];
+  if (tid == 0) mbar_init(&bar, 1);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base)), "r"(N_) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const bool swap = variant & 1;
+    const uint64_t da = make_desc(smem_u32(sA), swap ? sboA : lboA, swap ? lboA : sboA, 1);
+    const uint64_t db = make_desc(smem_u32(sB), lboB, sboB, 1);      // use the K-major convention that passed (edit if variant 1 won)
+    mma_i8(tmem, da, db, make_idesc(M_, N_, 1, 0), 0u);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int c0 = 0; c0 < N_; c0 += 32) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * N_ + c0 + j] = (int32_t)v[j];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(N_) : "memory");
+}
+
+static int run_mn(int variant) {
+  constexpr int N_ = 64;
+  std::vector<int8_t> A(M_ * K_), B(N_ * K_);
+  srand(99);
+  for (auto& x : A) x = (int8_t)(rand() % 256 - 128);              // A_km[k * M + m]
+  for (auto& x : B) x = (int8_t)(rand() % 256 - 128);
+  std::vector<int32_t> ref(M_ * N_), got(M_ * N_);
+  for (int i = 0; i < M_; ++i)
+    for (int j = 0; j < N_; ++j) {
+      int s = 0;
+      for (int k = 0; k < K_; ++k) s += (int)A[k * M_ + i] * (int)B[j * K_ + k];
+      ref[i * N_ + j] = s;
+    }
+  int8_t *dA, *dB;
+  int32_t* dD;
+  CK(cudaMalloc(&dA, A.size())); CK(cudaMalloc(&dB, B.size())); CK(cudaMalloc(&dD, got.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0x7f, got.size() * 4));
+  probe_mma_mn<<<1, 128>>>(dA, dB, dD, variant);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  MN-major A, variant %d: kernel failed: %s\n", variant, cudaGetErrorString(e)); return -1; }
+  CK(cudaMemcpy(got.data(), dD, got.size() * 4, cudaMemcpyDeviceToHost));
+  long bad = 0;
+  for (size_t i = 0; i < ref.size(); ++i) bad += ref[i] != got[i];
+  printf("  MN-major A, variant %d (%s): %ld of %zu entries differ%s\n", variant,
+         (variant & 1) ? "fields swapped" : "LBO = 8-K-row stride, SBO = 16-M-byte block stride", bad, ref.size(), bad ? "" : "   <-- MATCH");
+  return bad == 0;
+}
+
 // issue-rate probe: `iters` x 4 MMAs of 128 x 256 x 32 per CTA on resident (arbitrary) operands, one CTA per SM
 __global__ void __launch_bounds__(128) probe_rate(int iters, long long* cycles) {
   extern __shared__ __align__(1024) int8_t sm[];
@@ -209,7 +295,8 @@ int main(int argc, char** argv) {
   CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s, sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
   if (prop.major < 10) { printf("needs sm_100a\n"); return 1; }
-  if (argc < 2) { printf("usage: %s <0|1|2|3|rate>\n", argv[0]); return 1; }
+  if (argc < 2) { printf("usage: %s <0|1|2|3|mn0|mn1|rate>\n", argv[0]); return 1; }
+  if (argv[1][0] == 'm') return run_mn(argv[1][2] - '0') > 0 ? 0 : 3;
   if (argv[1][0] != 'r') {
     const int v = atoi(argv[1]);
     printf("(1) single tcgen05.mma.kind::i8 128 x N x 32 against the CPU, descriptor variant %d:\n", v);
