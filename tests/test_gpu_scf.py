@@ -1,6 +1,7 @@
 """End-to-end GPU parity: the product's Model / PlaneWaveBasis / self_consistent_field path (all orbital
 work inside libdftk_b200) against (a) the reference's own golden numbers and (b) the CPU oracle."""
 import math
+import os
 import numpy as np
 import pytest
 import torch
@@ -82,6 +83,65 @@ def test_silicon_lda_vs_abinit():
     assert res["energies"].total == pytest.approx(-7.911817522631488, abs=1e-5)
     for ik in range(4):
         np.testing.assert_allclose(res["eigenvalues"][ik][:8], ref[ik], atol=1e-5)
+
+
+_OPT_IN = pytest.mark.skipif(os.environ.get("DFTK_B200_EXPERIMENTAL") != "1",
+                             reason="written after the last GPU minutes of the round were spent: the oracle reproduces these ABINIT "
+                                    "values (tests/test_oracle_golden.py) and the product matches the oracle on reduced versions "
+                                    "of the same systems; set DFTK_B200_EXPERIMENTAL=1 to run the product against ABINIT directly")
+
+
+@_OPT_IN
+def test_silicon_pbe_vs_abinit():
+    # reference: test/silicon_pbe.jl:6-41,57-61 (Ecut 25, fft 33; eigenvalues and E_tot to 1e-5)
+    import dftk_b200 as dftk
+    Si = dftk.ElementPsp("Si", functional="pbe")
+    model = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.PBE())
+    basis = dftk.PlaneWaveBasis(model, Ecut=25, kgrid=dftk.ExplicitKpoints(KCOORDS, KWEIGHTS), fft_size=(33, 33, 33))
+    ref = [[-0.181210259413818, 0.258840553222639, 0.258840553225549, 0.258840553228459, 0.351692348652324,
+            0.351692348656259, 0.351692348660193, 0.380606400669216, 0.540705881744348, 0.540705883460555],
+           [-0.130553299114991, 0.062256443775155, 0.221871391287580, 0.221871391290802, 0.322398722411882,
+            0.386194327436667, 0.386194327439986, 0.546859898649217, 0.550571701390781, 0.550571701394327],
+           [-0.111170738096744, 0.074494899973125, 0.169461730083372, 0.169461730088140, 0.284305392082236,
+            0.330468937070505, 0.524509288492752, 0.524509288496625, 0.616964090764029, 0.619623658242765],
+           [-0.061054203629684, 0.009700769243041, 0.095769985640881, 0.180784778430457, 0.315000287382235,
+            0.471042322838057, 0.495281775946584, 0.517469860611792, 0.530124341745161, 0.539044739392045]]
+    res = dftk.self_consistent_field(basis, is_converged=dftk.ScfConvergenceEnergy(1e-8),
+                                     nbandsalg=dftk.AdaptiveBands(model, n_bands_converge=10))
+    assert res["energies"].total == pytest.approx(-7.854477356672080, abs=1e-5)
+    for ik in range(4):
+        np.testing.assert_allclose(res["eigenvalues"][ik][:10], ref[ik], atol=1e-5)
+
+
+@_OPT_IN
+def test_iron_pbe_collinear_vs_abinit():
+    # reference: test/iron_pbe.jl:6-70 (GTH-PADE-q8, PBE, collinear spin, T = 0.01, Ecut 20, fft 20, shifted 4x4x4 grid)
+    import dftk_b200 as dftk
+    fe_q8 = ("Fe GTH-PADE-q8 GTH-LDA-q8\n    2    0    6\n     0.61000000    0\n    3\n"
+             "     0.45448200    3     3.01664046    -1.00040646     0.79478164\n"
+             "                                        2.58303836    -2.05211737\n"
+             "                                                       3.25763534\n"
+             "     0.63890282    2     1.49964199    -0.13812935\n"
+             "                                        0.32687369\n"
+             "     0.30873177    1    -9.14535371\n")
+    Fe = dftk.ElementPsp("Fe", psp=dftk.parse_hgh(fe_q8, identifier="hgh/lda/fe-q8"))
+    assert Fe.psp.Zion == 8 and Fe.psp.count_n_proj() == 14
+    lat = 2.71176 * np.array([[-1, 1, 1], [1, -1, 1], [1, 1, -1]], dtype=float)
+    model = dftk.model_DFT(lat, [Fe], [[0, 0, 0]], functionals=dftk.PBE(), temperature=0.01, magnetic_moments=[4.0])
+    basis = dftk.PlaneWaveBasis(model, Ecut=20, kgrid=dftk.MonkhorstPack((4, 4, 4), kshift=(0.5, 0.5, 0.5)), fft_size=(20, 20, 20))
+    assert len(basis.kpoints) == 12
+    res = dftk.self_consistent_field(basis, rho=dftk.guess_density(basis, [4.0]), mixing=dftk.KerkerMixing(),
+                                     is_converged=dftk.ScfConvergenceEnergy(1e-10),
+                                     nbandsalg=dftk.AdaptiveBands(model, n_bands_converge=10))
+    assert res["energies"].total == pytest.approx(-18.21465922614397, abs=5e-6)
+    mag = float((res["rho"][0] - res["rho"][1]).sum() * basis.dvol)
+    assert mag == pytest.approx(2.98199463, abs=5e-5)
+    # spot values of the ABINIT spectra (first and last irreducible k-point of each spin channel are matched by value)
+    lowest = sorted(float(e[0]) for e in res["eigenvalues"])
+    ref_lowest = sorted([0.0603597727989307, 0.1384929268069029, -0.017996603976028, 0.1102557166995405, 0.1723514110126840,
+                         0.1360541296075938, 0.0802990962833626, 0.2341496631160049, -0.002234753604747, 0.1518900787487526,
+                         0.2873355363445261, 0.2512356397409882])
+    np.testing.assert_allclose(lowest, ref_lowest, atol=5e-6)
 
 
 def test_hamiltonian_consistency():
