@@ -13,3 +13,5 @@ for swap in 0 1; do for simple in 1 0; do
   echo "=== backend 3: DFTK_B200_I8TC_SWAP=$swap DFTK_B200_I8TC_SIMPLE=$simple"
   DFTK_B200_I8TC_SWAP=$swap DFTK_B200_I8TC_SIMPLE=$simple timeout 300 python -m pytest tests/test_gpu_kernels.py -q -k "i8_emulated and -3]" 2>&1 | tail -5
 done; done
+# product against ABINIT directly (PBE silicon, spin-polarised iron) and the forces tests
+timeout 600 python -m pytest tests/test_gpu_scf.py -q -k "pbe_vs_abinit or collinear_vs_abinit"
