@@ -5,14 +5,14 @@
 //
 // Scheme (integer modular technique, Ozaki / Uchino / Imamura 2025):
 //   1. every column of an operand (a vector along the contraction index) gets a power-of-two scale 2^e such that
-//      a' = trunc(a 2^e) is an integer of at most `bits` bits, with  K 2^(2 bits) <= P / 4,  P = prod of the moduli;
+//      a' = round(a 2^e) is an integer of at most `bits` bits, with  K 2^(2 bits) <= P / 4,  P = prod of the moduli;
 //   2. a' is reduced modulo N pairwise coprime moduli p_t <= 256 to symmetric residues in [-128, 127]  (int8 planes);
 //   3. per modulus the residues are multiplied exactly: int8 x int8 products, int32 accumulation over at most 2^17 terms,
 //      partial sums reduced mod p_t;
 //   4. the Chinese remainder theorem recombines the N residues of every output element into the exact integer
 //      C' = sum a' b'  (|C'| <= P/4), evaluated with 40-bit limbs held in FP64 (all limb operations are exact);
 //   5. C = C' 2^-(e_a + e_b).
-// The only errors are the truncations of step 1: with N = 16 (55 bits per operand at K = 8.5k) the result is as accurate as
+// The only errors are the roundings of step 1: with N = 16 (55 bits per operand at K = 8.5k) the result is as accurate as
 // an FP64 GEMM; N = 17 covers K = 2 x 264 859.
 // Bodies are __host__ __device__ (host emulation in tests/hostemu).
 #pragma once
@@ -66,7 +66,8 @@ HD int i8_scale_exponent(double amax, int bits) {
 
 // residues of one complex entry: out[(t * 2 + part) * plane_stride] for part = 0 (re), 1 (im)
 HD void i8_residues_entry(cplx x, int e, int n_mod, signed char* __restrict__ out, long long plane_stride) {
-  const double ar = trunc(ldexp(x.x, e)), ai = trunc(ldexp(x.y, e));
+  // round to nearest: unbiased operand errors (truncation would bias e.g. the diagonal of a Gram matrix low)
+  const double ar = rint(ldexp(x.x, e)), ai = rint(ldexp(x.y, e));
   for (int t = 0; t < n_mod; ++t) {
     const int p = i8_modulus(t);
     out[(long long)(2 * t) * plane_stride] = (signed char)i8_residue(ar, p);

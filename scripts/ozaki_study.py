@@ -43,11 +43,6 @@ def exact_product(At, B):
     return C, Ea + Eb      # value = C * 2^(Ea+Eb)
 
 
-def to_float(Cint, e):
-    return np.vectorize(lambda c: float(c) if abs(c) < 2 ** 1000 else math.ldexp(float(c >> 200), 200), otypes=[float])(Cint) * 2.0 ** e \
-        if False else np.array([[math.ldexp(c, e) if isinstance(c, int) and abs(c) < 2 ** 1020 else float(c) * 2.0 ** e for c in row] for row in Cint])
-
-
 def scheme_slices(At, B, s, bits):
     """Scheme I.  Rows of At / columns of B share one power-of-two scale; slice q holds bits [q*bits, (q+1)*bits)."""
     sa = 2.0 ** np.ceil(np.log2(np.abs(At).max(axis=1, keepdims=True)))      # |a| / sa < 1
@@ -74,7 +69,7 @@ MODULI = [256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 
 
 
 def scheme_modular(At, B, n_mod):
-    """Scheme II.  Integer operands A' = trunc(mu A), B' = trunc(B nu) with k max|a'| max|b'| < P/2; residues in
+    """Scheme II.  Integer operands A' = round(mu A), B' = round(B nu) with k max|a'| max|b'| < P/2; residues in
     [-128, 127]; int32 accumulation over chunks of k <= 2^17; CRT recombination (Python integers here -- the device
     version uses 40-bit FP64 pieces, exact as well)."""
     p = MODULI[:n_mod]
@@ -84,7 +79,7 @@ def scheme_modular(At, B, n_mod):
     budget = math.floor(math.log2(P // 2 // k) / 2)                           # bits per operand
     mu = 2.0 ** (budget - np.ceil(np.log2(np.abs(At).max(axis=1, keepdims=True))))
     nu = 2.0 ** (budget - np.ceil(np.log2(np.abs(B).max(axis=0, keepdims=True))))
-    Ai, Bi = np.trunc(At * mu), np.trunc(B * nu)                              # exact integers held in FP64
+    Ai, Bi = np.rint(At * mu), np.rint(B * nu)                                # exact integers held in FP64
     res = []
     for pt in p:
         a = np.fmod(Ai, pt); a = np.where(a > pt // 2 - (pt % 2 == 0), a - pt, a); a = np.where(a < -(pt // 2), a + pt, a)
