@@ -13,6 +13,9 @@
 // left when it was written.  It is reachable only through option gemm_backend = 3 and is checked against the CUDA-core
 // reference pipeline (gemm_backend = 2) by a GPU test that is committed but skipped.  scripts/tcgen05_i8_probe.cu settles
 // the descriptor convention (I8TC_SWAP_LBO_SBO) on the first GPU call of the next round.
+#include <algorithm>
+#include <string>
+#include <vector>
 #include "structs.cuh"
 #include "i8emu_core.cuh"
 
@@ -86,7 +89,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
 // part[(chunk)][(2 t + part)][j][i] int16: residues of this chunk (summed modulo p by k_i8_sum_chunks)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_i8_gemm_tc(const signed char* __restrict__ ra, const signed char* __restrict__ rb, int64_t m, int64_t n, int64_t ldk,
-             int n_mod, int n_chunks, int64_t chunk_len, short* __restrict__ part, int swap_lbo_sbo, int simple) {
+             int n_mod, int n_chunks, int64_t chunk_len, short* __restrict__ part, int swap_lbo_sbo, int simple,
+             int* __restrict__ dbg) {
   extern __shared__ unsigned char tc_raw[];
   unsigned char* sm = (unsigned char*)(((uintptr_t)tc_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
@@ -182,6 +186,15 @@ k_i8_gemm_tc(const signed char* __restrict__ ra, const signed char* __restrict__
       tc_ld32(lane_base + 2 * TC_N, x3);
       tc_ld32(lane_base + 3 * TC_N, x4);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        // bring-up dump: dbg[x][row][col] raw s32 accumulators of the first tile (x = 0..3 for X1..X4)
+        for (int c = 0; c < 32; ++c) {
+          dbg[(0 * TC_M + tid) * TC_N + c0 + c] = (int)x1[c];
+          dbg[(1 * TC_M + tid) * TC_N + c0 + c] = (int)x2[c];
+          dbg[(2 * TC_M + tid) * TC_N + c0 + c] = (int)x3[c];
+          dbg[(3 * TC_M + tid) * TC_N + c0 + c] = (int)x4[c];
+        }
+      }
       if (i < m) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -258,8 +271,50 @@ void i8tc_products(dftk_b200_ctx* ctx, const signed char* ra, const signed char*
   // bring-up switches (see scripts/next_round_first_call.sh): descriptor convention and the unpipelined variant
   const char* e1 = getenv("DFTK_B200_I8TC_SWAP");
   const char* e2 = getenv("DFTK_B200_I8TC_SIMPLE");
+  // DFTK_B200_I8TC_DUMP=<prefix>: write the raw accumulators of the first tile (modulus 0, chunk 0) and the operand rows
+  // that produced them to <prefix>.x / .a / .b for scripts/i8tc_debug.py
+  const char* e3 = getenv("DFTK_B200_I8TC_DUMP");
+  int* dbg = nullptr;
+  if (e3 && e3[0]) {
+    CUDA_CHECK(cudaMalloc((void**)&dbg, (size_t)4 * TC_M * TC_N * sizeof(int)));
+    CUDA_CHECK(cudaMemsetAsync(dbg, 0x7f, (size_t)4 * TC_M * TC_N * sizeof(int), ctx->stream));
+  }
   LAUNCH(ctx, k_i8_gemm_tc, grid, TC_THREADS, TC_SMEM, ra, rb, m, n, ldk, n_mod, n_chunks, chunk_len, part,
-         e1 && e1[0] == '1' ? 1 : 0, e2 && e2[0] == '1' ? 1 : 0);
+         e1 && e1[0] == '1' ? 1 : 0, e2 && e2[0] == '1' ? 1 : 0, dbg);
+  if (dbg) {
+    cudaError_t err = cudaStreamSynchronize(ctx->stream);
+    const int64_t kc = std::min<int64_t>(chunk_len, ldk);
+    std::vector<int> hx((size_t)4 * TC_M * TC_N);
+    auto dump = [&](const char* ext, const void* host, size_t bytes) {
+      std::string path = std::string(e3) + ext;
+      if (FILE* f = fopen(path.c_str(), "wb")) {
+        fwrite(host, 1, bytes, f);
+        fclose(f);
+      }
+    };
+    if (err == cudaSuccess) {
+      cudaMemcpy(hx.data(), dbg, hx.size() * sizeof(int), cudaMemcpyDeviceToHost);
+      dump(".x", hx.data(), hx.size() * sizeof(int));
+      // operand rows of the first tile: [part][row][k] for modulus 0, first chunk (rows beyond m / n clamp like the kernel)
+      for (int which = 0; which < 2; ++which) {
+        const int64_t rows = which == 0 ? m : n;
+        const signed char* src = which == 0 ? ra : rb;
+        std::vector<signed char> h((size_t)2 * TC_M * kc);
+        for (int part_i = 0; part_i < 2; ++part_i)
+          for (int r = 0; r < TC_M; ++r) {
+            const int64_t row = std::min<int64_t>(r, rows - 1);
+            cudaMemcpy(h.data() + ((size_t)part_i * TC_M + r) * kc, src + ((size_t)part_i * rows + row) * ldk, (size_t)kc,
+                       cudaMemcpyDeviceToHost);
+          }
+        dump(which == 0 ? ".a" : ".b", h.data(), h.size());
+      }
+      fprintf(stderr, "[i8tc] dumped first-tile accumulators and operands to %s.{x,a,b} (k = %lld)\n", e3, (long long)kc);
+    } else {
+      fprintf(stderr, "[i8tc] kernel failed before the dump: %s\n", cudaGetErrorString(err));
+    }
+    cudaFree(dbg);
+    CUDA_CHECK(err);
+  }
   const int64_t tot = 2 * (int64_t)n_mod * m * n;
   LAUNCH(ctx, k_i8_sum_chunks, (unsigned)((tot + 255) / 256), 256, 0, (const short*)part, n_chunks, n_mod, m * n, res);
 }

@@ -15,3 +15,5 @@ for swap in 0 1; do for simple in 1 0; do
 done; done
 # product against ABINIT directly (PBE silicon, spin-polarised iron) and the forces tests
 timeout 600 python -m pytest tests/test_gpu_scf.py -q -k "pbe_vs_abinit or collinear_vs_abinit"
+# if backend 3 failed above: first-tile dump + diagnosis (add DFTK_B200_I8TC_SWAP / _SIMPLE as needed)
+DFTK_B200_I8TC_DUMP=/tmp/i8tc DFTK_B200_I8TC_SIMPLE=1 timeout 120 python scripts/i8tc_debug.py 512 40 24
