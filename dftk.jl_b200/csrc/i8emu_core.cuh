@@ -49,6 +49,16 @@ HD int i8_residue(double a, int p) {
   if (r < -(p / 2)) r += p;
   return r;
 }
+// the same residue with six FP64 operations instead of a 64-bit integer division: a - p rint(a / p) evaluated with FMAs
+// (both remainders are small integers, hence exact); a is an integer-valued double with at most 53 significant bits
+HD int i8_residue_fast(double a, int p) {
+  const double dp = (double)p, ip = 1.0 / dp;
+  const double r0 = fma(-dp, rint(a * ip), a);       // |r0| <= p (1/2 + 2^-52 |a| / p ... ) : a few hundred at most
+  double r = fma(-dp, rint(r0 * ip), r0);            // in [-p/2, p/2]
+  if (r > (double)((p - 1) / 2)) r -= dp;            // even p: +p/2 -> -p/2
+  if (r < -(double)(p / 2)) r += dp;
+  return (int)r;
+}
 HD int i8_sym(int r, int p) {            // symmetric representative of any int
   r %= p;
   if (r > (p - 1) / 2) r -= p;
@@ -70,8 +80,8 @@ HD void i8_residues_entry(cplx x, int e, int n_mod, signed char* __restrict__ ou
   const double ar = rint(ldexp(x.x, e)), ai = rint(ldexp(x.y, e));
   for (int t = 0; t < n_mod; ++t) {
     const int p = i8_modulus(t);
-    out[(long long)(2 * t) * plane_stride] = (signed char)i8_residue(ar, p);
-    out[(long long)(2 * t + 1) * plane_stride] = (signed char)i8_residue(ai, p);
+    out[(long long)(2 * t) * plane_stride] = (signed char)i8_residue_fast(ar, p);
+    out[(long long)(2 * t + 1) * plane_stride] = (signed char)i8_residue_fast(ai, p);
   }
 }
 

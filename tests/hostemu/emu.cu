@@ -406,3 +406,12 @@ int emu_i8_zgemm_nn(int n_mod, int64_t m, int64_t n, int64_t k, const double* A,
   return T.bits;
 }
 }
+extern "C" {
+// residues of integer-valued doubles: division-free variant against the 64-bit integer remainder; returns #mismatches
+int64_t emu_i8_residue_compare(int64_t n, const double* a) {
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; ++i)
+    for (int t = 0; t < I8_MAX_MODULI; ++t) bad += i8_residue(a[i], i8_modulus(t)) != i8_residue_fast(a[i], i8_modulus(t));
+  return bad;
+}
+}

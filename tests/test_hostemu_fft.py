@@ -379,3 +379,22 @@ def test_emulated_i8_update_product_matches_exact(emu):
             tol = 4 * k * 2.0 ** (1 - bits) * np.abs(A[i]).max() * np.abs(B[:, j]).max()
             assert abs(C[j, i] - ex) <= tol
             assert abs(C[j, i] - ex) <= 4 * abs((A @ B)[i, j] - ex) + 1e-17 * np.abs(A[i]).max() * np.abs(B[:, j]).max() * k
+
+
+def test_emulated_i8_residue_fast_equals_integer_remainder(emu):
+    """a - p rint(a / p) by FMAs == symmetric 64-bit integer remainder, for integer-valued doubles up to 2^61 (53 significant
+    bits), including values at +-p/2 and multiples of the moduli."""
+    rng = np.random.default_rng(0)
+    vals = []
+    for bits in (8, 20, 40, 52, 53, 57, 61):
+        mant = rng.integers(-(1 << min(bits, 53)), 1 << min(bits, 53), size=4000).astype(np.float64)
+        vals.append(mant * 2.0 ** max(0, bits - 53))
+    edge = []
+    for p in I8_MODULI:
+        for mult in (1, 2, 3, 12345, 1 << 30, (1 << 52) // p):
+            base = float(p) * mult
+            edge += [base, base + p // 2, base - p // 2, base + (p - 1) // 2, -base, -base - p // 2, -base + p // 2, base + 1, base - 1]
+    a = np.ascontiguousarray(np.concatenate(vals + [np.array(edge)]))
+    assert np.all(a == np.rint(a))
+    emu.emu_i8_residue_compare.restype = ctypes.c_int64
+    assert emu.emu_i8_residue_compare(ctypes.c_int64(a.size), _p(a)) == 0
