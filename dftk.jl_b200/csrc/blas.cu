@@ -392,6 +392,10 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
     zgemm_i8_cn(ctx, m, n, k, A, lda, B, ldb, C, ldc, ctx->gemm_backend == 3);
     return;
   }
+  if (ctx->gemm_backend == 2 && transA == 0 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.y == 0.0 &&
+      (beta.x == 0.0 || beta.x == 1.0) && !upper_only) {
+    if (zgemm_i8_nn(ctx, m, n, k, A, lda, B, ldb, C, ldc, beta.x == 1.0)) return;     // too large: DMMA kernel below
+  }
   if (k == 0) {
     // C = beta C
     LAUNCH(ctx, k_reduce_partials, (unsigned)((m * n + 255) / 256), 256, 0, (const cplx*)nullptr, 0, m, n,

@@ -87,7 +87,7 @@ k_i8_dot_ref(const signed char* __restrict__ ra, const signed char* __restrict__
 
 __global__ void __launch_bounds__(128)
 k_i8_crt(const int* __restrict__ res, int64_t m, int64_t n, I8Tables T, const int* __restrict__ ea, const int* __restrict__ eb,
-         cplx* __restrict__ C, int64_t ldc) {
+         cplx* __restrict__ C, int64_t ldc, int accumulate) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m * n) return;
   const int64_t i = idx % m, j = idx / m;
@@ -97,7 +97,50 @@ k_i8_crt(const int* __restrict__ res, int64_t m, int64_t n, I8Tables T, const in
     rim[t] = res[((size_t)(2 * t + 1) * n + j) * m + i];
   }
   const int sh = -(ea[i] + eb[j]);
-  C[i + ldc * j] = make_double2(ldexp(i8_crt(rre, T), sh), ldexp(i8_crt(rim, T), sh));
+  cplx v = make_double2(ldexp(i8_crt(rre, T), sh), ldexp(i8_crt(rim, T), sh));
+  if (accumulate) {
+    const cplx o = C[i + ldc * j];
+    v.x += o.x;
+    v.y += o.y;
+  }
+  C[i + ldc * j] = v;
+}
+
+// ---- update-type products C (m x n) (+)= A B, A: m x k (rows scaled), B: k x n (columns scaled) ----
+// e[row] = scale exponent of row `row` of A (largest |re|, |im| over the k columns)
+__global__ void __launch_bounds__(256)
+k_i8_row_exponent(const cplx* __restrict__ A, int64_t lda, int64_t m, int64_t k, int bits, int* __restrict__ e) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  double mx = 0.0;
+  for (int64_t c = 0; c < k; ++c) {
+    const cplx v = A[i + lda * c];
+    mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+  }
+  e[i] = i8_scale_exponent(mx, bits);
+}
+// planes[(2 t + part)][c][i] (i fastest, like A itself), plane stride = m * k
+__global__ void __launch_bounds__(256)
+k_i8_residues_rows(const cplx* __restrict__ A, int64_t lda, int64_t m, int64_t k, const int* __restrict__ e, int n_mod,
+                   signed char* __restrict__ planes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = blockIdx.y;
+  if (i >= m) return;
+  i8_residues_entry(A[i + lda * c], e[i], n_mod, planes + (i + m * c), (long long)m * k);
+}
+// one thread per (i, j, t);  res[(2 t + part)][j][i]
+__global__ void __launch_bounds__(256)
+k_i8_dot_plain_ref(const signed char* __restrict__ ra, const signed char* __restrict__ rb, int64_t m, int64_t n, int64_t k,
+                   int n_mod, int* __restrict__ res) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= m * n * n_mod) return;
+  const int64_t i = w % m, j = (w / m) % n;
+  const int t = (int)(w / (m * n));
+  int re, im;
+  i8_dot_plain(ra + (size_t)(2 * t) * m * k + i, ra + (size_t)(2 * t + 1) * m * k + i, m,
+               rb + (size_t)(2 * t) * n * k + k * j, rb + (size_t)(2 * t + 1) * n * k + k * j, 1, k, i8_modulus(t), &re, &im);
+  res[((size_t)(2 * t) * n + j) * m + i] = re;
+  res[((size_t)(2 * t + 1) * n + j) * m + i] = im;
 }
 
 // number of moduli for FP64-level accuracy at contraction length K (55 bits per operand, scripts/ozaki_study.py)
@@ -145,7 +188,34 @@ void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx
     LAUNCH(ctx, k_i8_dot_ref, (unsigned)((warps * 32 + 255) / 256), 256, 0, (const signed char*)ra, (const signed char*)rb, m, n,
            k, T.n_mod, res);
   }
-  LAUNCH(ctx, k_i8_crt, (unsigned)((m * n + 127) / 128), 128, 0, (const int*)res, m, n, T, (const int*)ea, (const int*)eb, C, ldc);
+  LAUNCH(ctx, k_i8_crt, (unsigned)((m * n + 127) / 128), 128, 0, (const int*)res, m, n, T, (const int*)ea, (const int*)eb, C, ldc, 0);
+}
+
+// C (m x n) = A B (+ C if accumulate): reference pipeline only (integer products on CUDA cores); returns false when the
+// residue planes would not fit the workspace budget (the caller then uses the DMMA kernel)
+bool zgemm_i8_nn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                 cplx* C, int64_t ldc, bool accumulate) {
+  if (m == 0 || n == 0 || k == 0) return true;
+  const I8Tables T = tables_for(2 * k);
+  const size_t n_res = 2 * (size_t)T.n_mod * m * n;
+  const size_t bytes = (size_t)(m + n) * sizeof(int) + 64 + n_res * sizeof(int) + 2 * (size_t)T.n_mod * (size_t)k * (m + n) + 64;
+  if (bytes > ((size_t)8 << 30) || k > 65535 || m * n * T.n_mod > (int64_t)1 << 40) return false;
+  char* ws = (char*)ctx->gemm_ws.ensure(bytes);
+  int* ea = (int*)ws;
+  int* eb = ea + m;
+  int* res = eb + n;
+  signed char* ra = (signed char*)(res + n_res);
+  signed char* rb = ra + 2 * (size_t)T.n_mod * m * k;
+  LAUNCH(ctx, k_i8_row_exponent, (unsigned)((m + 255) / 256), 256, 0, A, lda, m, k, T.bits, ea);
+  LAUNCH(ctx, k_i8_col_exponent, (unsigned)n, 256, 0, B, ldb, k, T.bits, eb);
+  LAUNCH(ctx, k_i8_residues_rows, dim3((unsigned)((m + 255) / 256), (unsigned)k), 256, 0, A, lda, m, k, (const int*)ea, T.n_mod, ra);
+  LAUNCH(ctx, k_i8_residues, dim3((unsigned)((k + 255) / 256), (unsigned)n), 256, 0, B, ldb, k, n, (const int*)eb, T.n_mod, rb);
+  const int64_t threads = m * n * T.n_mod;
+  LAUNCH(ctx, k_i8_dot_plain_ref, (unsigned)((threads + 255) / 256), 256, 0, (const signed char*)ra, (const signed char*)rb, m, n,
+         k, T.n_mod, res);
+  LAUNCH(ctx, k_i8_crt, (unsigned)((m * n + 127) / 128), 128, 0, (const int*)res, m, n, T, (const int*)ea, (const int*)eb, C, ldc,
+         accumulate ? 1 : 0);
+  return true;
 }
 
 }  // namespace dftk

@@ -86,6 +86,8 @@ void symmetrize_fourier(dftk_b200_grid* g, const cplx* in, cplx* out, int n_sym,
 // i8emu.cu (experimental, option gemm_backend = 2)
 void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
                  cplx* C, int64_t ldc, bool tensor_cores);
+bool zgemm_i8_nn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
+                 cplx* C, int64_t ldc, bool accumulate);
 // i8tc.cu (experimental, option gemm_backend = 3): tcgen05.mma.kind::i8 kernel of the integer products
 void i8tc_products(dftk_b200_ctx* ctx, const signed char* ra, const signed char* rb, int64_t m, int64_t n, int64_t ldk,
                    int n_mod, short* part, int* res);

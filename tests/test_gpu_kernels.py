@@ -144,6 +144,23 @@ def test_i8_emulated_gemm_matches_fp64(shape, backend):
     finally:
         c.set_option("gemm_backend", 0)
     assert (C - ref).abs().max().item() < 1e-14 * ref.abs().max().item() * K ** 0.5
+    if backend == 2 and m * K < 3_000_000:
+        # update type: X (K x n) = A (K x m) S (m x n), and the accumulating form, through the reference pipeline
+        S = torch.view_as_complex(torch.randn(n, m, 2, generator=g, dtype=torch.float64)).to(c.device)
+        X0 = torch.view_as_complex(torch.randn(n, K, 2, generator=g, dtype=torch.float64)).to(c.device)
+        want = torch.zeros_like(X0)
+        c.zgemm("N", A, S, want)
+        c.set_option("gemm_backend", 2)
+        try:
+            X = torch.zeros_like(X0)
+            c.zgemm("N", A, S, X)
+            Xa = X0.clone()
+            c.zgemm("N", A, S, Xa, 1.0, 1.0)
+        finally:
+            c.set_option("gemm_backend", 0)
+        scale = (A.abs().max(dim=0).values[:, None] * S.abs().max()).max().item() * m
+        assert (X - want).abs().max().item() < 1e-14 * scale
+        assert (Xa - X0 - want).abs().max().item() < 1e-14 * scale
 
 
 @pytest.mark.parametrize("backend,small", [(0, 1), (1, 0), (0, 0)])
