@@ -168,6 +168,13 @@ def test_ewald_forces_and_force_symmetrisation_match_oracle():
     np.testing.assert_allclose(np.array(f), np.array(fo), atol=1e-12)
     from dftk_b200.terms import energy_ewald
     assert e == pytest.approx(energy_ewald(LATTICE, [4, 4], pos), abs=1e-12)
+    # the reference's own golden Ewald energies (test/ewald.jl:1-52) through the product's host code
+    for lat_g, ch, pos_g, ref, tol in [(16 * np.eye(3), [1], [[0, 0, 0]], -0.088665545, 1e-8),
+                                        (LATTICE, [14, 14], POSITIONS, -102.8741963352893, 1e-8),
+                                        (16 * np.eye(3), [5, 5], [[0, 0, 0], [0.14763485355139283, 0, 0]], 1.790634595, 1e-7)]:
+        pg = [np.array(q, dtype=float) for q in pos_g]
+        assert energy_ewald(lat_g, ch, pg) == pytest.approx(ref, abs=tol)
+        assert dftk.energy_forces_ewald(lat_g, ch, pg)[0] == pytest.approx(ref, abs=tol)
     # a 3-atom, two-species cell exercises the chunked structure-factor loops
     lat = np.diag([7.0, 8.0, 9.5])
     p3 = [np.array([0.1, 0.2, 0.3]), np.array([0.55, 0.6, 0.1]), np.array([0.3, 0.9, 0.7])]

@@ -62,6 +62,20 @@ def test_energy_nuclear():
     assert energy_psp_correction(m) == pytest.approx(-0.294622067023269, abs=1e-10)
 
 
+def test_ewald_golden():
+    # reference: test/ewald.jl:1-52 (hydrogen atom, silicon diamond with Z = 14, boron and hydrogen molecules in a 16 bohr box)
+    from oracle.forces import energy_forces_ewald
+    A = 5.131570667152971
+    cases = [(16 * np.eye(3), [1], [[0, 0, 0]], -0.088665545, 1e-8),
+             (np.array([[0, A, A], [A, 0, A], [A, A, 0]]), [14, 14], [np.ones(3) / 8, -np.ones(3) / 8], -102.8741963352893, 1e-8),
+             (16 * np.eye(3), [5, 5], [[0, 0, 0], [0.14763485355139283, 0, 0]], 1.790634595, 1e-7),
+             (16 * np.eye(3), [1, 1], [[0.45312500031210007, 0.5, 0.5], [0.5468749996028622, 0.5, 0.5]], 0.31316999, 1e-7)]
+    for lat, charges, pos, ref, tol in cases:
+        pos = [np.array(p, dtype=float) for p in pos]
+        assert energy_ewald(lat, charges, pos) == pytest.approx(ref, abs=tol)
+        assert energy_forces_ewald(lat, charges, pos)[0] == pytest.approx(ref, abs=tol)
+
+
 def test_G_index():
     # reference: test/PlaneWaveBasis.jl:92-96 -- index of G=[-2,-3,-1] at k=[1/3,1/3,0], fft (7,9,11), Ecut 3
     m = Model(LATTICE, [Element("Si")] * 2, POSITIONS, symmetries=False)
