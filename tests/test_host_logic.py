@@ -197,3 +197,22 @@ def test_ewald_forces_and_force_symmetrisation_match_oracle():
     np.testing.assert_allclose(np.array(got), np.array(want), atol=1e-14)
     np.testing.assert_allclose(got[0], got[0][0] * np.ones(3), atol=1e-14)
     np.testing.assert_allclose(got[0], -got[1], atol=1e-14)
+
+
+def test_smearing_functions_satisfy_reference_identities():
+    """test/occupation.jl:17-34 ("Smearing functions"): f(-inf) = 1, f(inf) = 0 and the entropy identity s'(x) = x f'(x),
+    for the product's host functions and the oracle's."""
+    from dftk_b200.terms import smearing_occupation as pf, smearing_entropy as ps
+    from oracle.terms import smearing_occupation as of, smearing_entropy as os_
+    eps = 1e-6
+    for f, s in ((pf, ps), (of, os_)):
+        for kind in ("FermiDirac", "Gaussian"):
+            assert float(f(kind, np.array([-np.inf]))[0]) == 1.0 and float(f(kind, np.array([np.inf]))[0]) == 0.0
+            for x in (0.04, -0.7, 1.3):
+                sp = (s(kind, np.array([x + eps]))[0] - s(kind, np.array([x - eps]))[0]) / (2 * eps)
+                fp = (f(kind, np.array([x + eps]))[0] - f(kind, np.array([x - eps]))[0]) / (2 * eps)
+                assert abs(sp - x * fp) < 1e-6, (kind, x)
+    x = np.linspace(-30, 30, 41)
+    for kind in ("FermiDirac", "Gaussian", "None"):
+        np.testing.assert_allclose(pf(kind, x), of(kind, x), atol=1e-16)
+        np.testing.assert_allclose(ps(kind, x), os_(kind, x), atol=1e-16)
