@@ -207,7 +207,7 @@ def run_gpu(args):
     rho0 = dftk.guess_density(basis)
     energies0, ham = dftk.energy_hamiltonian(basis, None, None, rho=rho0)
     blk = ham[0]
-    kb = blk.kblock
+    kb = blk.bind()
     n_pw, N = kb.n_pw, basis.N
     M = args.bands or n_bands_for(len(pos))
     setup = time.time() - t0

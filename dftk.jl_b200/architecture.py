@@ -21,17 +21,29 @@ class B200(AbstractArchitecture):
     """GPU{B200Array} analogue.  One instance per process (= per GPU / rank)."""
     _contexts = {}
 
-    def __init__(self, device=0, comm=None):
+    def __init__(self, device=None, comm=None):
+        if device is None:
+            # one process per GPU: a multi-rank run must not pile every rank onto cuda:0
+            if comm is not None and comm.nranks > 1:
+                import os
+                device = int(os.environ["LOCAL_RANK"]) if "LOCAL_RANK" in os.environ else torch.cuda.current_device()
+            else:
+                device = 0
         self.device_index = device
         self.comm = comm  # a dftk_b200.parallel.KpointComm or None
-        key = (device, None if comm is None else id(comm))
+        dist = comm is not None and comm.nranks > 1
+        key = (device, comm.rank, comm.nranks, comm.nccl_id) if dist else (device, 0, 1, None)
         if key not in B200._contexts:
-            if comm is not None and comm.nranks > 1:
+            if dist:
+                if comm.nccl_id is None:
+                    raise ValueError("multi-rank KpointComm without an NCCL id (use KpointComm.from_torch_distributed())")
                 B200._contexts[key] = Context(device, comm.nccl_id, comm.rank, comm.nranks)
             else:
                 B200._contexts[key] = Context(device)
         self.ctx = B200._contexts[key]
         self.device = self.ctx.device
+        if dist:
+            comm.attach(self.ctx)
 
     # to_device / to_cpu / synchronize_device / memory_usage  (architecture.jl:18-48)
     def to_device(self, x):

@@ -8,7 +8,7 @@ import torch
 
 from .model import SymOp, SYMMETRY_TOLERANCE
 from .device import FFTGrid, KBlock
-from .parallel import KpointComm, split_evenly, pad_kpoints_for_ranks
+from .parallel import KpointComm, BlockLayout, pad_kpoints_for_ranks
 
 
 # ------------------------------------------------------------------ grid sizes (fft.jl:231-337)
@@ -170,36 +170,45 @@ class PlaneWaveBasis:
         else:
             kcoords, kweights = irreducible_kcoords(self.kgrid, [SymOp(np.eye(3), np.zeros(3))])
         self.n_irreducible_kpoints = len(kcoords)
-        # k-point sharding (PlaneWaveBasis.jl:184-229): contiguous chunks, both spins on the same rank
+        # (k, spin) block sharding.  The reference splits the k-points into contiguous chunks and keeps both spins of a
+        # k-point on one rank (PlaneWaveBasis.jl:184-229); here the blocks b = ik + spin * n_kpt are flattened and dealt
+        # to the ranks longest-first by cost ~ n_pw, so spin x k fills all 8 GPUs of a box.
         comm = self.comm_kpts
-        kcoords, kweights = pad_kpoints_for_ranks(kcoords, kweights, comm.nranks)
+        n_spin = model.n_spin_components
+        kcoords, kweights = pad_kpoints_for_ranks(kcoords, kweights, comm.nranks, n_spin)
         self.kcoords_global = [np.array(k, dtype=float) for k in kcoords]
         self.kweights_global = list(kweights)
         n_kpt = len(kcoords)
-        self.krange_allprocs = split_evenly(range(n_kpt), comm.nranks)
-        mine = self.krange_allprocs[comm.rank]
-        n_spin = model.n_spin_components
-        self.krange_thisproc_allspin = [i + s * n_kpt for s in range(n_spin) for i in mine]
         # device grid tables
         self.fft_grid = FFTGrid(self.architecture.ctx, self.fft_size, model.unit_cell_volume)
         gx, gy, gz = (torch.as_tensor(G_axis(n), device=dev) for n in self.fft_size)
         Z, Y, X = torch.meshgrid(gz, gy, gx, indexing="ij")
         self.G_vectors = torch.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], dim=1)     # (N,3) int64
         self._recip = torch.as_tensor(model.recip_lattice, device=dev)
-        self.G_vectors_cart = self.G_vectors.to(torch.float64) @ self._recip.T
-        # k-points of this rank (Kpoint.jl:20-41: sphere membership over the whole cube)
+        Gf = self.G_vectors.to(torch.float64)
+        self.G_vectors_cart = Gf @ self._recip.T
+
+        def sphere(kcoord):          # Kpoint.jl:20-41: sphere membership over the whole cube
+            p = (Gf + torch.as_tensor(kcoord, device=dev)) @ self._recip.T
+            return (p * p).sum(dim=1) / 2 <= self.Ecut
+
+        costs = [1.0] * (n_kpt * n_spin)
+        if comm.nranks > 1:          # every rank counts every sphere: the block -> rank map is identical everywhere
+            npw = [float(sphere(k).sum().item()) for k in self.kcoords_global]
+            costs = [npw[b % n_kpt] for b in range(n_kpt * n_spin)]
+        self.layout = BlockLayout(n_kpt, n_spin, self.kweights_global, costs, comm.nranks, comm.rank)
+        self.krange_thisproc_allspin = list(self.layout.mine)
+        # k-blocks of this rank, spin-major then k
         self.kpoints, self.kweights = [], []
         base = {}
-        for spin in range(n_spin):
-            for i in mine:
-                if i not in base:
-                    k = torch.as_tensor(self.kcoords_global[i], device=dev)
-                    p = (self.G_vectors.to(torch.float64) + k) @ self._recip.T
-                    mapping = torch.nonzero((p * p).sum(dim=1) / 2 <= self.Ecut).reshape(-1)
-                    base[i] = (mapping, self.G_vectors[mapping])
-                mapping, Gk = base[i]
-                self.kpoints.append(Kpoint(spin, self.kcoords_global[i], mapping, Gk))
-                self.kweights.append(self.kweights_global[i])
+        for b in self.layout.mine:
+            i, spin = b % n_kpt, b // n_kpt
+            if i not in base:
+                mapping = torch.nonzero(sphere(self.kcoords_global[i])).reshape(-1)
+                base[i] = (mapping, self.G_vectors[mapping])
+            mapping, Gk = base[i]
+            self.kpoints.append(Kpoint(spin, self.kcoords_global[i], mapping, Gk))
+            self.kweights.append(self.kweights_global[i])
         total_w = comm.sum(sum(self.kweights))
         assert abs(total_w - n_spin) < 1e-10
         # instantiate terms (PlaneWaveBasis.jl:256-259), then the device k-blocks

@@ -262,4 +262,139 @@ HD void small_chol_cta(const cplx* __restrict__ O, long long ldo, int n, cplx* _
   }
 }
 
+// ---- Hermitian eigensolver of the Rayleigh-Ritz step (eigen(Hermitian(XAX)), lobpcg_hyper_impl.jl:141-171) for n <=
+// SMALL_MAX_COLS in one CTA: cyclic two-sided Jacobi with a round-robin ("chess tournament") ordering, n/2 disjoint
+// rotations per step.  A rotation of the pair (p, q) with A[p,q] = |b| e^{i phi} is J = diag(1, e^{-i phi}) R(c, s);
+// one step applies A <- J^H (A J) for all pairs at once (column phase, then row phase) and V <- V J.
+// G: n x n Hermitian, only the upper triangle (i <= j) is read; on return G holds the eigenvectors (columns, ascending
+// eigenvalues) and w the eigenvalues.  As: n*n cplx (shared), V: n*n cplx scratch (global, leading dimension n),
+// rot: 2*(n/2+1) cplx (shared; {c, s} and the phase of each pair), red: SMALL_RED doubles, iwork: 2*(n/2+1) ints (shared).
+// stats[0] = sweeps used (0: no convergence within the cap), stats[1] = final off-diagonal Frobenius norm.
+HD void small_heev_cta(cplx* __restrict__ G, long long ldg, int n, double* __restrict__ w, cplx* As, cplx* __restrict__ V,
+                       cplx* rot, double* red, int* iwork, double* __restrict__ stats) {
+  const int m = (n + 1) & ~1, half = m / 2;
+  int* pp = iwork;
+  int* qq = iwork + half;
+  TLOOP(e, n * n) {
+    const int i = e % n, j = e / n;
+    cplx v = i <= j ? G[i + ldg * j] : G[j + ldg * i];
+    if (i > j) v.y = -v.y;
+    if (i == j) v.y = 0.0;
+    As[e] = v;
+    V[e] = make_double2(i == j ? 1.0 : 0.0, 0.0);
+  }
+  TSYNC();
+  TLOOP(t, SMALL_RED) {
+    double s = 0.0;
+    for (int e = t; e < n * n; e += SMALL_RED) s += As[e].x * As[e].x + As[e].y * As[e].y;
+    red[t] = s;
+  }
+  TSYNC();
+  double normA = 0.0;
+  for (int t = 0; t < SMALL_RED; ++t) normA += red[t];
+  normA = sqrt(normA);
+  TSYNC();
+  const double tiny = 1.1102230246251565e-16 * 0.0078125 * normA;   // rotations below eps/128 ||A|| are skipped
+  // converged: off-diagonal norm at the rounding floor of the updates (or stagnating just above it)
+  const double off_tol = 2.0 * sqrt((double)n) * DBL_EPSILON * normA;
+  int sweeps = 0;
+  double off = 0.0, off_prev = -1.0;
+  bool done = (n <= 1) || !(normA > 0.0);
+  const int max_sweeps = 60;
+  while (!done && sweeps < max_sweeps) {
+    sweeps++;
+    for (int r = 0; r < m - 1; ++r) {
+      // pairs of this step: (m-1, r) and ((r+k) mod (m-1), (r-k) mod (m-1)), k = 1 .. m/2-1; indices >= n are byes
+      TLOOP(k, half) {
+        int a = k == 0 ? m - 1 : (r + k) % (m - 1);
+        int b = k == 0 ? r : (r - k + (m - 1)) % (m - 1);
+        int p = a < b ? a : b, q = a < b ? b : a;
+        cplx cs = make_double2(1.0, 0.0), ph = make_double2(1.0, 0.0);
+        if (q >= n) {
+          p = q = -1;
+        } else {
+          const cplx bq = As[p + n * q];
+          const double ab = sqrt(bq.x * bq.x + bq.y * bq.y);
+          if (ab > tiny) {
+            const double tau = (As[q + n * q].x - As[p + n * p].x) / (2.0 * ab);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            const double c = 1.0 / sqrt(1.0 + t * t);
+            cs = make_double2(c, t * c);
+            ph = make_double2(bq.x / ab, -bq.y / ab);     // e^{-i phi}
+          } else {
+            p = q = -1;
+          }
+        }
+        pp[k] = p;
+        qq[k] = q;
+        rot[k] = cs;
+        rot[half + k] = ph;
+      }
+      TSYNC();
+      // columns: [a_p a_q] <- [c a_p - s e^{-i phi} a_q,  s a_p + c e^{-i phi} a_q], same for V
+      TLOOP(e, half * n) {
+        const int k = e / n, i = e % n;
+        const int p = pp[k], q = qq[k];
+        if (p >= 0) {
+          const double c = rot[k].x, s = rot[k].y;
+          const cplx ph = rot[half + k];
+          const cplx ap = As[i + n * p], aq = cmul(ph, As[i + n * q]);
+          As[i + n * p] = make_double2(c * ap.x - s * aq.x, c * ap.y - s * aq.y);
+          As[i + n * q] = make_double2(s * ap.x + c * aq.x, s * ap.y + c * aq.y);
+          const cplx vp = V[i + n * p], vq = cmul(ph, V[i + n * q]);
+          V[i + n * p] = make_double2(c * vp.x - s * vq.x, c * vp.y - s * vq.y);
+          V[i + n * q] = make_double2(s * vp.x + c * vq.x, s * vp.y + c * vq.y);
+        }
+      }
+      TSYNC();
+      // rows: [a_p; a_q] <- [c a_p - s e^{+i phi} a_q;  s a_p + c e^{+i phi} a_q]
+      TLOOP(e, half * n) {
+        const int k = e / n, j = e % n;
+        const int p = pp[k], q = qq[k];
+        if (p >= 0) {
+          const double c = rot[k].x, s = rot[k].y;
+          const cplx ph = make_double2(rot[half + k].x, -rot[half + k].y);
+          const cplx ap = As[p + n * j], aq = cmul(ph, As[q + n * j]);
+          As[p + n * j] = make_double2(c * ap.x - s * aq.x, c * ap.y - s * aq.y);
+          As[q + n * j] = make_double2(s * ap.x + c * aq.x, s * ap.y + c * aq.y);
+        }
+      }
+      TSYNC();
+    }
+    TLOOP(t, SMALL_RED) {
+      double s = 0.0;
+      for (int e = t; e < n * n; e += SMALL_RED)
+        if (e % n != e / n) s += As[e].x * As[e].x + As[e].y * As[e].y;
+      red[t] = s;
+    }
+    TSYNC();
+    off = 0.0;
+    for (int t = 0; t < SMALL_RED; ++t) off += red[t];
+    off = sqrt(off);
+    TSYNC();
+    done = off <= off_tol || (off_prev >= 0.0 && off <= 1e-12 * normA && off >= 0.25 * off_prev);
+    off_prev = off;
+  }
+  // ascending order by rank counting (ties keep their index order); eigenvectors into G
+  TLOOP(i, n) {
+    const double li = As[i + n * i].x;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const double lj = As[j + n * j].x;
+      rank += (lj < li) || (lj == li && j < i);
+    }
+    iwork[i] = rank;     // pp/qq are dead by now (2*half >= n)
+    w[rank] = li;
+  }
+  TSYNC();
+  TLOOP(e, n * n) {
+    const int i = e % n, j = e / n;
+    G[i + ldg * iwork[j]] = V[i + n * j];
+  }
+  TLOOP(t, 1) {
+    stats[0] = done ? (double)(sweeps > 0 ? sweeps : 1) : 0.0;
+    stats[1] = off;
+  }
+}
+
 }  // namespace dftk

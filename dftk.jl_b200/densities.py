@@ -6,10 +6,16 @@ import numpy as np
 import torch
 
 
-def compute_density(basis, psi, occupation, *, occupation_threshold=0.0):
+def compute_density(basis, psi, occupation, *, occupation_threshold=0.0, packed_sums=None):
+    """`packed_sums`: a few host scalars (this rank's partial sums of the k-summed energies) that ride behind the density
+    in the SAME allreduce; the call then returns (rho, summed scalars)."""
     n_spin = basis.model.n_spin_components
     dev = basis.architecture.device
-    rho = torch.zeros((n_spin, basis.N), dtype=torch.float64, device=dev)
+    n_tail = 0 if packed_sums is None else len(packed_sums)
+    flat = torch.zeros(n_spin * basis.N + n_tail, dtype=torch.float64, device=dev)
+    rho = flat[:n_spin * basis.N].view(n_spin, basis.N)
+    if n_tail:
+        flat[n_spin * basis.N:] = torch.as_tensor(np.asarray(packed_sums, dtype=np.float64), device=dev)
     for ik, kb in enumerate(basis.kblocks):
         occ = np.asarray(occupation[ik], dtype=float)
         w = np.where(np.abs(occ) >= occupation_threshold, occ * basis.kweights[ik], 0.0)
@@ -17,9 +23,11 @@ def compute_density(basis, psi, occupation, *, occupation_threshold=0.0):
         if nb:
             kb.density_accumulate(psi[ik][:nb], w[:nb], rho[basis.kpoints[ik].spin])
     if basis.comm_kpts.nranks > 1:
-        basis.architecture.ctx.allreduce(rho, "sum")
+        basis.comm_kpts.n_collectives += 1
+        basis.architecture.ctx.allreduce(flat, "sum")          # mpi_sum!(ρ) of densities.jl:46 + the packed scalars
+    sums = flat[n_spin * basis.N:].cpu().numpy() if n_tail else None
     rho = symmetrize_rho(basis, rho)
-    return rho
+    return rho if packed_sums is None else (rho, sums)
 
 
 def symmetrize_rho(basis, rho):

@@ -145,6 +145,14 @@ class KBlock:
         self.h = h
 
     def set_potential(self, V):
+        """Install the total local potential.  Re-installing the very tensor the block already holds (same object,
+        not modified in place since) is free: Hamiltonian blocks bind their potential before every device call."""
+        if isinstance(V, torch.Tensor):
+            if V is getattr(self, "_pot_ref", None) and V._version == self._pot_version:
+                return
+            self._pot_ref, self._pot_version = V, V._version
+        else:
+            self._pot_ref = None
         check(self.ctx.L.dftk_b200_kblock_set_potential(self.h, _ptr(V)), self.ctx.h)
 
     def _new(self, nb):

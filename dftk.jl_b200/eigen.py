@@ -18,7 +18,7 @@ def lobpcg_hyper(A, X0, *, prec=True, tol=None, maxiter=100, miniter=1, n_conv_c
     returns (; λ, X, residual_norms, n_iter, converged, n_matvec).  X0 is consumed (updated in place)."""
     if tol is None:
         tol = 20 * A.shape[1] * np.finfo(float).eps
-    return A.kblock.lobpcg(X0, tol=tol, miniter=miniter, maxiter=maxiter, n_conv_check=n_conv_check,
+    return A.bind().lobpcg(X0, tol=tol, miniter=miniter, maxiter=maxiter, n_conv_check=n_conv_check,
                            prec=bool(prec))
 
 

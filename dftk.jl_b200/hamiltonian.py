@@ -2,6 +2,7 @@
 src/terms/Hamiltonian.jl:22-57,137-236).  `mul!(Hψ, H::DftHamiltonianBlock, ψ)` is one C-ABI call
 (dftk_b200_apply_h) that runs the batched FFT pipeline + fused kinetic/local scalings + nonlocal GEMMs."""
 import math
+import numpy as np
 import torch
 
 from .terms import (RealSpaceMultiplication, FourierMultiplication, NonlocalOperator, NoopOperator)
@@ -43,7 +44,14 @@ class DftHamiltonianBlock:
                     pot_cache[key] = pot
             self.local_op = RealSpaceMultiplication(basis, self.kpoint, pot)
         self.kblock = basis.kblocks[ik]
+
+    def bind(self):
+        """Install this block's local potential on the shared device k-block.  A Hamiltonian is a value in the
+        reference: several may be alive at once (scfres.ham, info.ham of a callback, ham(ρ1) vs ham(ρ2)), so the
+        potential travels with the block and is (re)installed before every device call; the k-block skips the copy
+        when it already holds this very tensor."""
         self.kblock.set_potential(self.local_op.potential if self.local_op is not None else None)
+        return self.kblock
 
     @property
     def shape(self):
@@ -51,7 +59,7 @@ class DftHamiltonianBlock:
 
     def mul(self, psi, out=None):
         """Hψ for a block of bands; psi: (n_bands, n_G) complex128 on the device."""
-        return self.kblock.apply_h(psi, out)
+        return self.bind().apply_h(psi, out)
 
     __matmul__ = mul
 
@@ -69,17 +77,43 @@ class Hamiltonian:
     __matmul__ = mul
 
 
+KSUM_TERMS = ("Kinetic", "AtomicNonlocal", "Entropy")     # energies that are sums over the (k, spin) blocks
+
+
+def ksum_energy_partials(basis, psi, occupation, eigenvalues, eF):
+    """This rank's partial sums of the k-summed energy terms (kinetic.jl:54, nonlocal.jl:44, entropy.jl:39 before their
+    mpi_sum): next_density packs them behind the density so that one allreduce serves compute_density and the energies."""
+    names = [n for n in KSUM_TERMS if basis.term(n) is not None]
+    basis._be_cache = {}
+    try:
+        vals = [basis.term(n).local_energy(basis, psi, occupation, eigenvalues=eigenvalues, eF=eF) for n in names]
+    finally:
+        basis._be_cache = None
+    return names, np.array(vals, dtype=np.float64)
+
+
+def _ksum_totals(basis, psi, occupation, eigenvalues, eF):
+    """Totals over all ranks of the k-summed terms: taken from the step's packed allreduce when (psi, occupation) are the
+    objects next_density produced, otherwise one packed allreduce here."""
+    if psi is None or occupation is None:
+        return {}
+    c = getattr(basis, "_ksum_cache", None)
+    if c is not None and c["psi"] is psi and c["occupation"] is occupation and c["eF"] == eF:
+        return c["totals"]
+    names, vals = ksum_energy_partials(basis, psi, occupation, eigenvalues, eF)
+    if not np.all(np.isfinite(vals)):
+        return dict(zip(names, vals))
+    return dict(zip(names, basis.comm_kpts.allreduce(vals, "sum")))
+
+
 def energy_hamiltonian(basis, psi, occupation, *, rho, eigenvalues=None, eF=None, **kw):
     """Hamiltonian.jl:200-227: energies of every term + the per-k Hamiltonian blocks."""
     energies, per_term_ops = Energies(), []
-    basis._be_cache = {}
-    try:
-        for name, term in zip(basis.model.term_types, basis.terms):
-            E, ops = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF)
-            energies[name] = E
-            per_term_ops.append(ops)
-    finally:
-        basis._be_cache = None
+    totals = _ksum_totals(basis, psi, occupation, eigenvalues, eF)
+    for name, term in zip(basis.model.term_types, basis.terms):
+        E, ops = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF, ksum_total=totals.get(name))
+        energies[name] = E
+        per_term_ops.append(ops)
     pot_cache = {}
     blocks = [DftHamiltonianBlock(basis, ik, [ops[ik] for ops in per_term_ops], pot_cache)
               for ik in range(len(basis.kpoints))]
@@ -89,10 +123,8 @@ def energy_hamiltonian(basis, psi, occupation, *, rho, eigenvalues=None, eF=None
 def energy(basis, psi, occupation, *, rho, eigenvalues=None, eF=None, **kw):
     """Hamiltonian.jl:232-236 (energies only)."""
     energies = Energies()
-    basis._be_cache = {}
-    try:
-        for name, term in zip(basis.model.term_types, basis.terms):
-            energies[name] = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF)[0]
-    finally:
-        basis._be_cache = None
+    totals = _ksum_totals(basis, psi, occupation, eigenvalues, eF)
+    for name, term in zip(basis.model.term_types, basis.terms):
+        energies[name] = term.ene_ops(basis, psi, occupation, rho=rho, eigenvalues=eigenvalues, eF=eF,
+                                      ksum_total=totals.get(name))[0]
     return energies

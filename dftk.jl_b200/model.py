@@ -84,6 +84,9 @@ class Model:
             raise ValueError("temperature must be non-negative")
         self.temperature = float(temperature)
         self.smearing = smearing or ("FermiDirac" if temperature > 0 else "None")
+        if self.smearing not in ("None", "FermiDirac", "Gaussian"):
+            # the Fermi-level search of dftk_b200.occupation covers monotone smearing functions only (no FermiTwoStage)
+            raise NotImplementedError(f"smearing {self.smearing!r}: only 'None', 'FermiDirac' and 'Gaussian' are supported")
         self.magnetic_moments = [float(m) for m in magnetic_moments]
         if self.magnetic_moments and len(self.magnetic_moments) != len(self.atoms):
             raise ValueError("Length of atoms and magnetic_moments vectors need to agree.")

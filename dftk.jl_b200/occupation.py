@@ -5,16 +5,29 @@ import numpy as np
 from .terms import smearing_occupation
 
 
-def _gather(basis, eigenvalues):
+def gather_eigenvalues(basis, eigenvalues, stats=()):
+    """ONE fixed-size allgather per SCF step: the eigenvalues of every rank's blocks (all blocks carry the same number
+    of bands) with a few per-rank solver statistics behind them.  Returns (eigenvalues of all blocks in global block
+    order b = ik + spin * n_kpt, their k-weights, stats[rank, :])."""
     comm = basis.comm_kpts
+    layout = getattr(basis, "layout", None)
+    stats = np.asarray(stats, dtype=np.float64).reshape(-1)
     if comm.nranks == 1:
-        return [np.asarray(e) for e in eigenvalues], list(basis.kweights)
-    pieces = comm.allgather_object(([np.asarray(e) for e in eigenvalues], list(basis.kweights)))
-    ev, w = [], []
-    for e, ww in pieces:
-        ev += e
-        w += ww
-    return ev, w
+        w = list(layout.weights) if layout is not None else list(basis.kweights)
+        return [np.asarray(e, dtype=np.float64) for e in eigenvalues], w, stats[None, :]
+    nb = len(eigenvalues[0])
+    if any(len(e) != nb for e in eigenvalues):
+        raise ValueError("all blocks must carry the same number of bands")
+    buf = np.zeros(layout.max_local * nb + len(stats))
+    for j, e in enumerate(eigenvalues):
+        buf[j * nb:(j + 1) * nb] = e
+    buf[layout.max_local * nb:] = stats
+    got = comm.allgather(buf)
+    ev = [None] * layout.n_blocks
+    for r in range(comm.nranks):
+        for j, b in enumerate(layout.blocks_of_rank[r]):
+            ev[b] = got[r, j * nb:(j + 1) * nb].copy()
+    return ev, list(layout.weights), got[:, layout.max_local * nb:]
 
 
 def _occ(model, eigs, eF):
@@ -23,14 +36,19 @@ def _occ(model, eigs, eF):
     return [model.filled_occupation * smearing_occupation(model.smearing, (e - eF) / model.temperature) for e in eigs]
 
 
-def compute_occupation(basis, eigenvalues, *, tol_n_elec=1e-6):
-    """Returns (occupation of the local k-points, εF)."""
+def compute_occupation(basis, eigenvalues, *, tol_n_elec=1e-6, gathered=None, return_global=False):
+    """Returns (occupation of the local blocks, εF).  `gathered` = (eigenvalues of all blocks, weights) when the caller
+    already did the allgather (next_density packs solver statistics into the same collective)."""
     model = basis.model
     for ek in eigenvalues:
         if not np.all(np.diff(ek) >= -np.finfo(float).eps):
             raise ValueError("Eigenvalues should be monotonically increasing.")
-    ev, w = _gather(basis, eigenvalues)
+    ev, w = gathered if gathered is not None else gather_eigenvalues(basis, eigenvalues)[:2]
     filled = model.filled_occupation
+    if model.n_electrons == 0:
+        eF = min(e.min() for e in ev) - 1.0
+        occ = [np.zeros(len(e)) for e in eigenvalues]
+        return (occ, eF, [np.zeros(len(e)) for e in ev]) if return_global else (occ, eF)
 
     def excess(eF):
         return sum(wk * o.sum() for wk, o in zip(w, _occ(model, ev, eF))) - model.n_electrons
@@ -52,6 +70,8 @@ def compute_occupation(basis, eigenvalues, *, tol_n_elec=1e-6):
         ex = excess(eF)
         if abs(ex) >= tol_n_elec / 10:
             lo, hi = (eF, max(e.max() for e in ev) + 1) if ex < 0 else (min(e.min() for e in ev) - 1, eF)
+            if not (excess(lo) <= 0 <= excess(hi)):      # occupation.jl:100-103 (@assert on the bracket)
+                raise RuntimeError("compute_occupation: the Fermi level is not bracketed by the eigenvalue range")
             for _ in range(200):      # Roots.Bisection to atol = eps
                 mid = (lo + hi) / 2
                 if mid == lo or mid == hi:
@@ -64,4 +84,5 @@ def compute_occupation(basis, eigenvalues, *, tol_n_elec=1e-6):
             if abs(excess(eF)) > tol_n_elec:
                 import warnings
                 warnings.warn("Large deviation of electron count in compute_occupation.")
-    return _occ(model, [np.asarray(e) for e in eigenvalues], eF), eF
+    occ = _occ(model, [np.asarray(e) for e in eigenvalues], eF)
+    return (occ, eF, _occ(model, ev, eF)) if return_global else (occ, eF)

@@ -8,9 +8,9 @@ import time
 import numpy as np
 import torch
 
-from .hamiltonian import energy_hamiltonian, energy
+from .hamiltonian import energy_hamiltonian, energy, ksum_energy_partials
 from .eigen import lobpcg_hyper, diagonalize_all_kblocks
-from .occupation import compute_occupation
+from .occupation import compute_occupation, gather_eigenvalues
 from .densities import compute_density
 from .terms import guess_density
 
@@ -155,21 +155,32 @@ class AndersonAcceleration:
 
 def next_density(ham, nbandsalg, *, eigensolver=lobpcg_hyper, psi=None, eigenvalues=None, occupation=None,
                  tol=1e-6, miniter=1, maxiter=100, generator=None):
-    """self_consistent_field.jl:80-129."""
+    """self_consistent_field.jl:80-129.  `eigenvalues` / `occupation` drive the band-count heuristics: pass the lists
+    over ALL (k, spin) blocks (the `*_global` entries of the previous result) so that every rank takes the same
+    decision without the mpi_max of self_consistent_field.jl:98.
+
+    Collectives of the sharded path: one allgather (eigenvalues + solver statistics) and one allreduce (density with
+    the k-summed band-energy partials packed behind it)."""
     basis = ham.basis
     nconv, ncomp = nbandsalg.determine_n_bands(occupation, eigenvalues, psi)
     if psi is not None:
         ncomp = max(ncomp, max(p.shape[0] for p in psi))
-    ncomp = int(basis.comm_kpts.max(ncomp))
     eig = diagonalize_all_kblocks(eigensolver, ham, ncomp, psiguess=psi, n_conv_check=nconv, tol=tol,
                                   miniter=miniter, maxiter=maxiter, generator=generator)
+    ev_g, w_g, stats = gather_eigenvalues(basis, eig["λ"], stats=[eig["n_matvec"], 1.0 if eig["converged"] else 0.0])
+    eig["converged"] = bool(np.all(stats[:, 1] > 0.5))
     if not eig["converged"]:
         import warnings
         warnings.warn(f"Eigensolver not converged, n_iter={eig['n_iter']}")
-    occ, eF = compute_occupation(basis, eig["λ"], tol_n_elec=nbandsalg.occupation_threshold)
-    rho = compute_density(basis, eig["X"], occ, occupation_threshold=nbandsalg.occupation_threshold)
+    occ, eF, occ_g = compute_occupation(basis, eig["λ"], tol_n_elec=nbandsalg.occupation_threshold,
+                                        gathered=(ev_g, w_g), return_global=True)
+    names, partials = ksum_energy_partials(basis, eig["X"], occ, eig["λ"], eF)
+    rho, totals = compute_density(basis, eig["X"], occ, occupation_threshold=nbandsalg.occupation_threshold,
+                                  packed_sums=partials)
+    basis._ksum_cache = dict(psi=eig["X"], occupation=occ, eF=eF, totals=dict(zip(names, totals)))
     return dict(psi=eig["X"], eigenvalues=eig["λ"], occupation=occ, eF=eF, rho=rho, diagonalization=eig,
-                n_bands_converge=nconv, n_matvec=int(basis.comm_kpts.sum(eig["n_matvec"])))
+                n_bands_converge=nconv, n_matvec=int(round(float(np.sum(stats[:, 0])))),
+                eigenvalues_global=ev_g, occupation_global=occ_g)
 
 
 def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=None, maxiter=100,
@@ -180,23 +191,30 @@ def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=N
     rho = guess_density(basis) if rho is None else rho
     mixing = mixing or SimpleMixing()      # reference default LdosMixing degenerates to SimpleMixing at T = 0
     nbandsalg = nbandsalg or AdaptiveBands(model)
-    diagtolalg = diagtolalg or AdaptiveDiagtol()
+    if diagtolalg is None:       # default_diagtolalg, scf_callbacks.jl:220-229
+        nonlinear = any(t in model.term_types for t in ("Hartree", "Xc"))
+        diagtolalg = AdaptiveDiagtol() if nonlinear else AdaptiveDiagtol(diagtol_first=tol / 5)
     is_converged = is_converged or ScfConvergenceDensity(tol)
     gen = torch.Generator(device=basis.architecture.device)
-    gen.manual_seed(int(basis.comm_kpts.bcast_object(seed if seed is not None else 0)) + 7919 * basis.comm_kpts.rank)
+    gen.manual_seed(int(seed if seed is not None else 0) + 7919 * basis.comm_kpts.rank)   # same `seed` on every rank
     info = dict(basis=basis, rho=rho, psi=psi, occupation=None, eigenvalues=None, eF=None, n_iter=0, n_matvec=0,
+                eigenvalues_global=None, occupation_global=None,
                 converged=False, history_Etot=[], history_drho=[], stage="iterate", algorithm="SCF")
     acc = AndersonAcceleration(m=anderson_m)
 
     def fixpoint_map(rho_in):
+        # the reference hands the info of the PREVIOUS step to determine_diagtol (self_consistent_field.jl:198-203):
+        # its n_iter is 0 and 1 for the first two steps, which therefore both run at diagtol_first
+        diagtol = diagtolalg.determine_diagtol(info)
         info["n_iter"] += 1
         t0 = time.time()
         _, ham = energy_hamiltonian(basis, info["psi"], info["occupation"], rho=rho_in,
                                     eigenvalues=info["eigenvalues"], eF=info["eF"])
-        nxt = next_density(ham, nbandsalg, eigensolver=eigensolver, psi=info["psi"], eigenvalues=info["eigenvalues"],
-                           occupation=info["occupation"], miniter=1, tol=diagtolalg.determine_diagtol(info),
-                           generator=gen)
+        nxt = next_density(ham, nbandsalg, eigensolver=eigensolver, psi=info["psi"],
+                           eigenvalues=info["eigenvalues_global"], occupation=info["occupation_global"], miniter=1,
+                           tol=diagtol, generator=gen)
         info.update(ham=ham, rho_in=rho_in, psi=nxt["psi"], eigenvalues=nxt["eigenvalues"], occupation=nxt["occupation"],
+                    eigenvalues_global=nxt["eigenvalues_global"], occupation_global=nxt["occupation_global"],
                     eF=nxt["eF"], rho_out=nxt["rho"], diagonalization=nxt["diagonalization"],
                     n_bands_converge=nxt["n_bands_converge"], n_matvec=info["n_matvec"] + nxt["n_matvec"])
         if compute_consistent_energies:
@@ -209,7 +227,7 @@ def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=N
         info["history_Etot"].append(energies.total)
         info["history_drho"].append(float(drho.norm()) * math.sqrt(basis.dvol))
         nxt_rho = rho_in + mixing.mix_density(basis, drho)
-        info["converged"] = bool(basis.comm_kpts.bcast_object(is_converged(info)))
+        info["converged"] = basis.comm_kpts.all_true(is_converged(info))
         info["time_step"] = time.time() - t0
         if callback:
             callback(info)
@@ -226,6 +244,7 @@ def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=N
                                        eigenvalues=info["eigenvalues"], eF=info["eF"])
     return dict(ham=ham, basis=basis, energies=energies, converged=info["converged"], rho=rho_f,
                 eigenvalues=info["eigenvalues"], occupation=info["occupation"], eF=info["eF"], psi=info["psi"],
+                eigenvalues_global=info["eigenvalues_global"], occupation_global=info["occupation_global"],
                 n_iter=info["n_iter"], n_matvec=info["n_matvec"], history_Etot=info["history_Etot"],
                 history_drho=info["history_drho"], diagonalization=info["diagonalization"],
                 n_bands_converge=info["n_bands_converge"], runtime_s=time.time() - start, stage="finalize",

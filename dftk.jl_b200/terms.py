@@ -52,16 +52,22 @@ class TermKinetic:
             p = basis.Gplusk_vectors_cart(kpt)
             self.kinetic_energies.append((scaling_factor * (p * p).sum(dim=1) / 2).contiguous())
 
-    def ene_ops(self, basis, psi, occupation, **kw):
-        ops = [FourierMultiplication(basis, k, self.kinetic_energies[ik]) for ik, k in enumerate(basis.kpoints)]
-        if psi is None or occupation is None:
-            return math.inf, ops
+    def local_energy(self, basis, psi, occupation, **kw):
+        """Σ over this rank's blocks (the mpi_sum of kinetic.jl:54 is done by the caller, packed with the other sums)."""
         E = 0.0
         for ik, kb in enumerate(basis.kblocks):
             both = _band_energies_shared(basis, ik, psi[ik])
             ek = both[0] if both is not None else _band_energies(kb, psi[ik], want_nl=False)[0]
             E += basis.kweights[ik] * float(np.sum(np.asarray(occupation[ik]) * ek))
-        return basis.comm_kpts.sum(E), ops
+        return E
+
+    def ene_ops(self, basis, psi, occupation, ksum_total=None, **kw):
+        ops = [FourierMultiplication(basis, k, self.kinetic_energies[ik]) for ik, k in enumerate(basis.kpoints)]
+        if psi is None or occupation is None:
+            return math.inf, ops
+        if ksum_total is None:
+            ksum_total = basis.comm_kpts.sum(self.local_energy(basis, psi, occupation))
+        return float(ksum_total), ops
 
 
 def _band_energies(kb, psik, want_nl=True, want_kin=True):
@@ -170,15 +176,20 @@ class TermAtomicNonlocal:
             P, D = cache[key]
             self.ops.append(NonlocalOperator(basis, kpt, P, D))
 
-    def ene_ops(self, basis, psi, occupation, **kw):
-        if psi is None or occupation is None:
-            return math.inf, self.ops
+    def local_energy(self, basis, psi, occupation, **kw):
         E = 0.0
         for ik, kb in enumerate(basis.kblocks):
             both = _band_energies_shared(basis, ik, psi[ik])
             en = both[1] if both is not None else _band_energies(kb, psi[ik], want_kin=False)[1]
             E += basis.kweights[ik] * float(np.sum(en * np.asarray(occupation[ik])))
-        return basis.comm_kpts.sum(E), self.ops
+        return E
+
+    def ene_ops(self, basis, psi, occupation, ksum_total=None, **kw):
+        if psi is None or occupation is None:
+            return math.inf, self.ops
+        if ksum_total is None:
+            ksum_total = basis.comm_kpts.sum(self.local_energy(basis, psi, occupation))
+        return float(ksum_total), self.ops
 
 
 def energy_ewald(lattice, charges, positions, eta=None):
@@ -326,19 +337,29 @@ class TermEntropy:
     def __init__(self, basis):
         pass
 
-    def ene_ops(self, basis, psi, occupation, eigenvalues=None, eF=None, **kw):
+    def local_energy(self, basis, psi, occupation, eigenvalues=None, eF=None, **kw):
+        m = basis.model
+        if m.temperature == 0:
+            return 0.0
+        if eigenvalues is None or eF is None:
+            return math.inf
+        E = 0.0
+        for ik in range(len(basis.kpoints)):
+            nb = psi[ik].shape[0]
+            E -= (m.temperature * basis.kweights[ik] * m.filled_occupation
+                  * float(np.sum(smearing_entropy(m.smearing, (np.asarray(eigenvalues[ik])[:nb] - eF) / m.temperature))))
+        return E
+
+    def ene_ops(self, basis, psi, occupation, eigenvalues=None, eF=None, ksum_total=None, **kw):
         ops = [NoopOperator(basis, k) for k in basis.kpoints]
         m = basis.model
         if m.temperature == 0:
             return 0.0, ops
         if psi is None or occupation is None or eigenvalues is None or eF is None:
             return math.inf, ops
-        E = 0.0
-        for ik in range(len(basis.kpoints)):
-            nb = psi[ik].shape[0]
-            E -= (m.temperature * basis.kweights[ik] * m.filled_occupation
-                  * float(np.sum(smearing_entropy(m.smearing, (np.asarray(eigenvalues[ik])[:nb] - eF) / m.temperature))))
-        return basis.comm_kpts.sum(E), ops
+        if ksum_total is None:
+            ksum_total = basis.comm_kpts.sum(self.local_energy(basis, psi, occupation, eigenvalues=eigenvalues, eF=eF))
+        return float(ksum_total), ops
 
 
 _TERMS = dict(Kinetic=TermKinetic, AtomicLocal=TermAtomicLocal, AtomicNonlocal=TermAtomicNonlocal,

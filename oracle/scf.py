@@ -233,15 +233,19 @@ def self_consistent_field(basis, rho=None, tol=1e-6, maxiter=100, damping=0.8, m
     if is_converged is None:
         is_converged = lambda inf: inf["history_drho"][-1] < tol
 
+    if diagtol_first is None and not any(t in model.terms for t in ("Hartree", "Xc")):
+        diagtol_first = tol / 5          # default_diagtolalg, scf_callbacks.jl:220-229 (no nonlinear term)
+
     def fixpoint_map(rho_in):
-        info["n_iter"] += 1
-        _E, blocks = energy_hamiltonian(basis, terms, info["psi"], info["occupation"], rho_in,
-                                        info["eigenvalues"], info["eF"])
-        # determine_diagtol, scf_callbacks.jl:198-212
+        # determine_diagtol, scf_callbacks.jl:198-212, is handed the info of the PREVIOUS step
+        # (self_consistent_field.jl:198-203): n_iter is 0 and 1 for the first two steps
         if info["n_iter"] <= 1:
             dt = min(6 * diagtol_max if diagtol_first is None else diagtol_first, 5 * diagtol_max)
         else:
             dt = min(max(min(info["history_drho"]) * 0.2, 100 * np.finfo(float).eps), diagtol_max)
+        info["n_iter"] += 1
+        _E, blocks = energy_hamiltonian(basis, terms, info["psi"], info["occupation"], rho_in,
+                                        info["eigenvalues"], info["eF"])
         nconv, ncomp = nbandsalg.determine(info["occupation"], info["eigenvalues"], info["psi"])
         if info["psi"] is not None:
             ncomp = max(ncomp, max(p.shape[1] for p in info["psi"]))

@@ -13,7 +13,7 @@ Si = dftk.ElementPsp("Si")
 model = dftk.model_DFT(lat, [Si] * len(pos), pos, functionals=dftk.LDA(), symmetries=False)
 basis = dftk.PlaneWaveBasis(model, Ecut=30.0, kgrid=dftk.ExplicitKpoints([[0, 0, 0]]))
 _, ham = dftk.energy_hamiltonian(basis, None, None, rho=dftk.guess_density(basis))
-kb = ham[0].kblock
+kb = ham[0].bind()
 M = bench.n_bands_for(len(pos))
 X = dftk.random_orbitals(basis, basis.kpoints[0], M)
 torch.cuda.synchronize()

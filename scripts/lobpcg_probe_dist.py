@@ -17,7 +17,7 @@ model = dftk.model_DFT(lat, [Si] * len(pos), pos, functionals=dftk.LDA(), symmet
 arch = dftk.B200(local)
 basis = dftk.PlaneWaveBasis(model, Ecut=30.0, kgrid=dftk.ExplicitKpoints([[0, 0, 0]]), architecture=arch)
 _, ham = dftk.energy_hamiltonian(basis, None, None, rho=dftk.guess_density(basis))
-kb = ham[0].kblock
+kb = ham[0].bind()
 X = dftk.random_orbitals(basis, basis.kpoints[0], 503)
 torch.cuda.synchronize()
 if dist.is_initialized():

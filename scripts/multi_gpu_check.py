@@ -1,6 +1,8 @@
-"""torchrun worker: k-point-sharded SCF (one rank per GPU, NCCL density allreduce) must reproduce the
-single-GPU SCF.  Launched by tests/test_gpu_multi.py and usable standalone:
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/multi_gpu_check.py"""
+"""torchrun worker: (k, spin)-sharded SCF (one rank per GPU; per step one NCCL allgather of eigenvalues and one
+allreduce of the density + packed energy sums) must reproduce the single-GPU SCF.  Launched by tests/test_gpu_multi.py,
+by __graft_entry__.smoke() when >= 2 GPUs are visible, and usable standalone:
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/multi_gpu_check.py
+CASE=si (default; TEMPERATURE=0|0.01) or CASE=fe (collinear spin: spin x k blocks flattened over the ranks)."""
 import os
 import sys
 import json
@@ -14,29 +16,43 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 import dftk_b200 as dftk
 
-a = 5.131570667152971
-lat = np.array([[0, a, a], [a, 0, a], [a, a, 0]])
-pos = [np.ones(3) / 8, -np.ones(3) / 8]
-Si = dftk.ElementPsp("Si")
+case = os.environ.get("CASE", "si")
 temperature = float(os.environ.get("TEMPERATURE", "0.0"))
-model = dftk.model_DFT(lat, [Si, Si], pos, functionals=dftk.LDA(), temperature=temperature)
+if case == "si":
+    a = 5.131570667152971
+    lat = np.array([[0, a, a], [a, 0, a], [a, a, 0]])
+    Si = dftk.ElementPsp("Si")
+    model = dftk.model_DFT(lat, [Si, Si], [np.ones(3) / 8, -np.ones(3) / 8], functionals=dftk.LDA(), temperature=temperature)
+    Ecut, kgrid, tol = 10, (3, 3, 3), 1e-9
+else:
+    a = 2.71176
+    lat = a * np.array([[-1, 1, 1], [1, -1, 1], [1, 1, -1]], dtype=float)
+    Fe = dftk.ElementPsp("Fe", functional="pbe")
+    model = dftk.model_DFT(lat, [Fe], [np.zeros(3)], functionals=dftk.PBE(), temperature=0.01, magnetic_moments=[4.0])
+    Ecut, kgrid, tol = 15, (3, 3, 3), 1e-8
+    temperature = 0.01
+mixing = dftk.KerkerMixing() if temperature > 0 else None
 comm = dftk.KpointComm.from_torch_distributed()
-arch = dftk.B200(local, comm=comm)
-basis = dftk.PlaneWaveBasis(model, Ecut=10, kgrid=(3, 3, 3), architecture=arch, comm_kpts=comm)
-res = dftk.self_consistent_field(basis, tol=1e-9, mixing=dftk.KerkerMixing() if temperature > 0 else None)
-eig = comm.allgather_object([(basis.krange_thisproc_allspin[i], res["eigenvalues"][i].tolist())
-                             for i in range(len(basis.kpoints))])
+# default architecture: must land on this rank's GPU (LOCAL_RANK), not on cuda:0
+basis = dftk.PlaneWaveBasis(model, Ecut=Ecut, kgrid=kgrid, comm_kpts=comm)
+assert basis.architecture.device.index == local
+c0 = comm.n_collectives
+res = dftk.self_consistent_field(basis, tol=tol, mixing=mixing)
+coll_per_step = (comm.n_collectives - c0) / res["n_iter"]
 out = None
 if rank == 0:
     arch1 = dftk.B200(local)
-    basis1 = dftk.PlaneWaveBasis(model, Ecut=10, kgrid=(3, 3, 3), architecture=arch1)
-    ref = dftk.self_consistent_field(basis1, tol=1e-9, mixing=dftk.KerkerMixing() if temperature > 0 else None)
-    gathered = dict(x for part in eig for x in part)
-    deig = max(np.abs(np.array(gathered[i][:4]) - ref["eigenvalues"][i][:4]).max() for i in range(len(basis1.kpoints)))
+    basis1 = dftk.PlaneWaveBasis(model, Ecut=Ecut, kgrid=kgrid, architecture=arch1)
+    ref = dftk.self_consistent_field(basis1, tol=tol, mixing=mixing)
+    nocc = 4 if case == "si" else 8
+    deig = max(np.abs(np.array(res["eigenvalues_global"][b][:nocc]) - ref["eigenvalues"][b][:nocc]).max()
+               for b in range(len(basis1.kpoints)))
     drho = float((res["rho"] - ref["rho"]).norm()) * np.sqrt(basis.dvol)
-    out = dict(world=world, dE=abs(res["energies"].total - ref["energies"].total), deig=float(deig), drho=drho,
+    out = dict(world=world, case=case, dE=abs(res["energies"].total - ref["energies"].total), deig=float(deig), drho=drho,
                E=res["energies"].total, n_iter=res["n_iter"], n_iter_ref=ref["n_iter"], eF=res["eF"], eF_ref=ref["eF"],
-               nk_local=len(basis.kpoints), nk_total=len(basis1.kpoints))
+               nk_local=len(basis.kpoints), nk_total=len(basis1.kpoints), n_spin=model.n_spin_components,
+               spins_local=sorted({k.spin for k in basis.kpoints}), collectives_per_step=coll_per_step,
+               n_atoms=len(model.atoms))
     print("MULTIGPU_RESULT " + json.dumps(out), flush=True)
 dist.barrier()
 dist.destroy_process_group()

@@ -317,6 +317,13 @@ int emu_small_rmul(double* X, int64_t ld, int64_t n_rows, int n, const double* i
   for (int64_t r = 0; r < n_rows; ++r) small_rmul_row(r, (cplx*)X, ld, n, (const cplx*)invR, ldr);
   return 0;
 }
+int emu_small_heev(double* G, int64_t ldg, int n, double* w, double* stats) {
+  std::vector<cplx> As((size_t)n * n), V((size_t)n * n), rot((size_t)n + 4);
+  std::vector<double> red(SMALL_RED);
+  std::vector<int> iw((size_t)n + 4);
+  small_heev_cta((cplx*)G, ldg, n, w, As.data(), V.data(), rot.data(), red.data(), iw.data(), stats);
+  return 0;
+}
 int emu_small_chol(const double* O, int64_t ldo, int n, double* invR, int64_t ldi, double* stats) {
   std::vector<cplx> As((size_t)SMALL_MAX_N * SMALL_MAX_N), Bs((size_t)SMALL_MAX_N * SMALL_MAX_N);
   std::vector<double> red(SMALL_RED);

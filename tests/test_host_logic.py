@@ -95,8 +95,10 @@ def test_anderson_converges_linear_fixed_point():
 
 
 class _FakeBasis:
-    def __init__(self, model, weights, comm):
+    def __init__(self, model, weights, comm, layout=None):
         self.model, self.kweights, self.comm_kpts = model, weights, comm
+        if layout is not None:
+            self.layout = layout
 
 
 def test_occupation_insulator_and_metal():
@@ -128,8 +130,18 @@ def _gloo_worker(rank, world, port, q):
     mm = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), temperature=0.02)
     eig = [np.array([-0.2, 0.0, 0.1, 0.2, 0.5, 0.6]), np.array([-0.1, 0.0, 0.1, 0.25, 0.45, 0.7])]
     # each rank owns one of the two k-points: the Fermi level must equal the single-process result bit for bit
-    b = _FakeBasis(mm, [0.5], comm)
+    from dftk_b200.parallel import BlockLayout
+    layout = BlockLayout(2, 1, [0.5, 0.5], [1.0, 1.0], 2, rank)
+    assert layout.mine == [rank]
+    b = _FakeBasis(mm, [0.5], comm, layout)
     occ, eF = compute_occupation(b, [eig[rank]])
+    # packed collectives: a fixed-size allgather with statistics behind the eigenvalues, an array allreduce
+    from dftk_b200.occupation import gather_eigenvalues
+    ev, w, stats = gather_eigenvalues(b, [eig[rank]], stats=[10.0 + rank, 1.0])
+    assert np.array_equal(ev[0], eig[0]) and np.array_equal(ev[1], eig[1]) and w == [0.5, 0.5]
+    assert stats.tolist() == [[10.0, 1.0], [11.0, 1.0]]
+    assert comm.allreduce(np.array([1.0, rank]), "sum").tolist() == [2.0, 1.0]
+    assert comm.all_true(True) and not comm.all_true(rank == 0)
     q.put((rank, eF, occ[0].tolist()))
     dist.destroy_process_group()
 
@@ -154,6 +166,29 @@ def test_kpoint_comm_gloo_world2():
     occ, eF = compute_occupation(_FakeBasis(mm, [0.5, 0.5], dftk.KpointComm()), eig)
     assert out[0][1] == eF and out[1][1] == eF                      # bit-identical Fermi level on every rank
     assert out[0][2] == occ[0].tolist() and out[1][2] == occ[1].tolist()
+
+
+def test_block_layout_flattens_spin_and_balances():
+    """(k, spin) blocks are flattened and dealt longest-first; the map is deterministic, covers every block
+    once and leaves no rank empty (PlaneWaveBasis.jl:190-203 forbids empty ranks)."""
+    from dftk_b200.parallel import BlockLayout, lpt_assign, pad_kpoints_for_ranks
+    costs = [1150.0, 1144.0, 1161.0, 1139.0, 1150.0] * 2            # 5 k-points x 2 spins
+    for n in (1, 2, 4, 8):
+        lay = [BlockLayout(5, 2, [0.2] * 5, costs, n, r) for r in range(n)]
+        assert sorted(b for l in lay for b in l.mine) == list(range(10))
+        assert all(l.owner == lay[0].owner for l in lay)
+        loads = [sum(costs[b] for b in l.mine) for l in lay]
+        assert max(loads) - min(loads) <= max(costs) + 1e-9
+        assert all(l.mine == sorted(l.mine) for l in lay)
+    assert max(len(l.mine) for l in lay) == 2 and lay[0].max_local == 2     # 10 blocks on 8 ranks
+    # spin x k fills ranks that k alone could not: 3 k-points, 2 spins on 6 ranks
+    lay = BlockLayout(3, 2, [1 / 3] * 3, [1.0] * 6, 6, 4)
+    assert len(lay.mine) == 1
+    assert lpt_assign([3.0, 1.0, 1.0, 1.0], 2) == [0, 1, 1, 1]
+    kc, kw = pad_kpoints_for_ranks([[0, 0, 0]], [1.0], 4, n_spin=2)
+    assert len(kc) == 2 and kw == [0.5, 0.5]
+    with pytest.raises(ValueError):
+        BlockLayout(1, 1, [1.0], [1.0], 2, 0)
 
 
 def test_ewald_forces_and_force_symmetrisation_match_oracle():

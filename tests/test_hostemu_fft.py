@@ -302,6 +302,42 @@ def test_emulated_small_cholesky_failure_modes(emu):
     assert stats[0] == 0
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 14, 21, 36, 45, 96])
+def test_emulated_small_heev_matches_numpy(emu, n):
+    """k_small_heev = the Rayleigh-Ritz eigensolver of the batched small path (eigen(Hermitian(XAX)),
+    lobpcg_hyper_impl.jl:141-171): parallel cyclic Jacobi in one CTA.  Eigenvalues ascending, eigenvectors orthonormal to
+    machine precision (the reference re-orthogonalises LAPACK's vectors for exactly this property), A V = V diag(w);
+    only the upper triangle of the input is read; degenerate and indefinite spectra."""
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = (B + B.conj().T) / 2
+    if n >= 7:                                   # a degenerate cluster and a tiny eigenvalue, like a converged block
+        w0 = np.sort(rng.standard_normal(n))
+        w0[2] = w0[3] = w0[4]
+        w0[0] = 1e-13
+        Q, _ = np.linalg.qr(B)
+        A = (Q * w0) @ Q.conj().T
+        A = (A + A.conj().T) / 2
+    ld = n + 2
+    G = np.full((n, ld), np.nan + 0j)            # column-major n x n with leading dimension ld: G[j, i] = A[i, j]
+    for i in range(n):
+        for j in range(n):
+            if i <= j:
+                G[j, i] = A[i, j]                # lower triangle stays NaN: must not be read
+    w = np.zeros(n)
+    stats = np.zeros(4)
+    assert emu.emu_small_heev(_p(G), ctypes.c_int64(ld), n, _p(w), _p(stats)) == 0
+    assert stats[0] >= 1, "Jacobi did not converge"
+    V = G[:, :n].T.copy()
+    wref = np.linalg.eigvalsh(A)
+    scale = max(1.0, np.abs(wref).max())
+    np.testing.assert_allclose(w, wref, atol=4e-15 * scale * max(1, n / 8))
+    assert np.all(np.diff(w) >= 0)
+    assert np.abs(V.conj().T @ V - np.eye(n)).max() < 5e-16 * max(n, 32)
+    assert np.abs(A @ V - V * w).max() < 1e-14 * scale * max(1, n / 8)
+    assert stats[0] <= 15
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # INT8-emulated FP64 GEMM (i8emu_core.cuh; groundwork for a tcgen05 kind::i8 path, not on the default path)
 # ---------------------------------------------------------------------------------------------------------------
