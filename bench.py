@@ -149,7 +149,7 @@ def run_reference(args):
         return
     threads = effective_cpus()
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    nb = args.cpu_bands
+    nb = min(args.cpu_bands, max(16, 384 // (args.steps + args.warmup)))     # bounded sample: the whole run stays within minutes
     t0 = time.time()
     ob, blk, psi = oracle_block(args.workload, nb, threads)
     setup = time.time() - t0
@@ -173,6 +173,146 @@ def run_reference(args):
                 e2e=dict(value=value, unit="band-applies/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 setup_s=setup)
     print(json.dumps(line), flush=True)
+
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE configs C4 / C5
+GOLDEN = os.path.join(ROOT, "tests", "golden", "baseline_configs.json")
+
+
+def baseline_model(dftk, name):
+    """BASELINE.json configs[3] / [4] (SURVEY §8d fixes T = 0.01 Ha Fermi-Dirac and Kerker mixing for the metals)."""
+    if name == "C5":
+        lat = 2.71176 * np.array([[-1, 1, 1], [1, -1, 1], [1, 1, -1]], dtype=float)
+        Fe = dftk.ElementPsp("Fe", functional="pbe")
+        model = dftk.model_DFT(lat, [Fe], [np.zeros(3)], functionals=dftk.PBE(), temperature=0.01, magnetic_moments=[4.0])
+        return model, dict(Ecut=45.0, kgrid=(8, 8, 8)), "Fe bcc PBE collinear spin, Ecut 45 Ha, k 8x8x8 (spin x k blocks sharded)"
+    if name == "C4":
+        a = 7.65339
+        pos = [[0, 0, 0], [0, 0.5, 0.5], [0.5, 0, 0.5], [0.5, 0.5, 0]]
+        Al = dftk.ElementPsp("Al", functional="pbe")
+        model = dftk.model_DFT(a * np.eye(3), [Al] * 4, pos, functionals=dftk.PBE(), temperature=0.01)
+        return model, dict(Ecut=40.0, kgrid=(12, 12, 12)), "Al fcc 4-atom PBE, Fermi-Dirac T = 0.01 Ha, Ecut 40 Ha, k 12x12x12 (k blocks sharded)"
+    if name == "C2":
+        lat = np.array([[0, A_SI, A_SI], [A_SI, 0, A_SI], [A_SI, A_SI, 0]])
+        Si = dftk.ElementPsp("Si")
+        model = dftk.model_DFT(lat, [Si, Si], [np.ones(3) / 8, -np.ones(3) / 8], functionals=dftk.LDA())
+        return model, dict(Ecut=30.0, kgrid=(8, 8, 8)), "Si 2-atom LDA, Ecut 30 Ha, k 8x8x8"
+    raise KeyError(name)
+
+
+def sharded_scf(dftk, torch, dist, name, arch, comm, world, dev, repeats=2):
+    """A full SCF of a BASELINE config with its (k, spin) blocks sharded over the ranks (STRONG scaling: the total work is
+    fixed).  Per step: one NCCL allgather (eigenvalues) + one allreduce (density with the packed energy sums) + the
+    converged flag.  Reports the SCF-iteration time (max over ranks) and the energy against the CPU oracle's golden value
+    of the same full-size configuration (tests/golden/baseline_configs.json, scripts/make_golden_configs.py)."""
+    model, bk, desc = baseline_model(dftk, name)
+    t0 = time.perf_counter()
+    basis = dftk.PlaneWaveBasis(model, architecture=arch, comm_kpts=comm, **bk)
+    setup = time.perf_counter() - t0
+    mixing = dftk.KerkerMixing() if model.temperature > 0 else None
+    ctx = arch.ctx
+    out = None
+    for rep in range(repeats):           # the first run warms workspaces / handles
+        steps = []
+        c0, l0 = comm.n_collectives, ctx.launch_count(reset=True)
+        ctx.sync_count(reset=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = time.perf_counter()
+        res = dftk.self_consistent_field(basis, tol=1e-8, mixing=mixing, callback=lambda info: steps.append(info["time_step"]), seed=3)
+        torch.cuda.synchronize()
+        total = time.perf_counter() - t
+        tt = torch.tensor([total] + steps, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tt = tt.cpu().numpy()
+        n_it = res["n_iter"]
+        out = dict(config=desc, n_ranks=world, fft_size=list(basis.fft_size), blocks_total=basis.layout.n_blocks,
+                   blocks_this_rank=len(basis.kpoints), n_bands=int(res["psi"][0].shape[0]), total_s=float(tt[0]), n_iter=n_it,
+                   s_per_iter=float(tt[0]) / n_it, step_seconds=[float(x) for x in tt[1:]], converged=bool(res["converged"]),
+                   energy=float(res["energies"].total), eF=float(res["eF"]),
+                   collectives_per_step=(comm.n_collectives - c0) / n_it if world > 1 else 0,
+                   launches_per_step_rank0=ctx.launch_count() / n_it, host_syncs_lobpcg_per_step_rank0=ctx.sync_count() / n_it,
+                   setup_s=setup)
+    if os.path.exists(GOLDEN):
+        g = json.load(open(GOLDEN)).get(name)
+        if g:
+            n_at = len(model.atoms)
+            out["golden_energy"] = g["energies"]["total"]
+            out["dE_per_atom_vs_oracle"] = abs(out["energy"] - g["energies"]["total"]) / n_at
+            out["d_eF_vs_oracle"] = abs(out["eF"] - g["eF"])
+            ev = res["eigenvalues_global"]
+            nb = g["n_bands_compared"]
+            # the oracle's k-point list may be ordered differently: match blocks by (spin, coordinate)
+            dmax = 0.0
+            for b in range(basis.layout.n_blocks):
+                ik, sp = b % len(basis.kcoords_global), b // len(basis.kcoords_global)
+                for j, (kc, s2) in enumerate(zip(g["kcoords"], g["spins"])):
+                    if s2 == sp and np.allclose(kc, basis.kcoords_global[ik], atol=1e-10):
+                        dmax = max(dmax, float(np.abs(np.asarray(ev[b][:nb]) - np.asarray(g["eigenvalues"][j][:nb])).max()))
+                        break
+            out["max_d_eigenvalue_vs_oracle"] = dmax
+            out["parity_ok"] = bool(out["dE_per_atom_vs_oracle"] < 1e-8 and dmax < 1e-6)
+    del basis, res
+    torch.cuda.empty_cache()
+    return out
+
+
+def library_gpu_baseline(torch, basis, blk, kb, psi, n_local_bands):
+    """The reference's GPU formulation of H psi with LIBRARY kernels (what ext/DFTKCUDAExt.jl gets from cuFFT + cuBLAS,
+    src/terms/Hamiltonian.jl:155-176 + src/fft.jl:110-172): band at a time zero-fill, scatter, cuFFT backward, multiply,
+    cuFFT forward, gather, kinetic axpy; nonlocal term as two cuBLAS ZGEMMs.  Timed with CUDA events on the same block."""
+    dev = psi.device
+    nx, ny, nz = basis.fft_size
+    N = basis.N
+    mapping = basis.kpoints[blk.ik].mapping
+    V = blk.local_op.potential.reshape(nz, ny, nx)
+    kin = blk.fourier_op.multiplier
+    P = blk.nonlocal_op.P                               # (n_proj, n_pw) = column-major n_pw x n_proj
+    D = torch.as_tensor(blk.nonlocal_op.D, device=dev, dtype=torch.complex128)
+    cube = torch.empty(N, dtype=torch.complex128, device=dev)
+    nb = min(n_local_bands, psi.shape[0])
+    out = torch.empty((nb, psi.shape[1]), dtype=torch.complex128, device=dev)
+
+    def local(n_bands):
+        for n in range(n_bands):
+            cube.zero_()
+            cube[mapping] = psi[n]
+            r = torch.fft.ifftn(cube.view(nz, ny, nx))          # includes the 1/N of fft_norm * ifft_norm
+            r.mul_(V)
+            f = torch.fft.fftn(r)
+            out[n] = f.view(-1)[mapping] + kin * psi[n]
+
+    def nonlocal_(x):
+        proj = torch.conj(P) @ x.T                              # P' psi   (n_proj x M)
+        return (P.T @ (D @ proj)).T
+
+    def ev(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    ms_local = ev(lambda: local(nb)) / nb                        # per band
+    ms_nl = ev(lambda: nonlocal_(psi))                           # whole block
+    M = psi.shape[0]
+    # correctness of the formulation against the product on the sampled bands
+    local(min(nb, 4))
+    hp = out[:min(nb, 4)] + nonlocal_(psi[:min(nb, 4)])
+    ref = kb.apply_h(psi[:min(nb, 4)].contiguous())
+    err = float((hp - ref).abs().max() / ref.abs().max())
+    ms_block = ms_local * M + ms_nl
+    return dict(value=M / (ms_block * 1e-3), unit="band-applies/s", ms_per_block=ms_block, us_per_band_local=1e3 * ms_local,
+                ms_nonlocal=ms_nl, bands_sampled_local=nb, max_rel_diff_vs_product=err,
+                what="band-at-a-time zero-fill + scatter + cuFFT Z2Z + multiply + cuFFT + gather + axpy (torch.fft) and two cuBLAS "
+                     "ZGEMMs (torch.matmul) on the same block: the reference's own GPU formulation with library kernels")
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -257,10 +397,14 @@ def run_gpu(args):
     # measured DRAM traffic of the group (dram__bytes_read.sum + dram__bytes_write.sum over the five kernels of one
     # `ncu --set full` capture, profiles/ncu_full_r1.csv: 17.11 GB per 51-band launch on the 192^3 grid), scaled to the
     # block like `achieved`; only known for the profiled workload
-    traffic = 335.49e6 * M if args.workload == "si250" else None
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")       # written by scripts/summarize_ncu.py from the round's
+    if args.workload == "si250" and os.path.exists(tpath):            # `ncu --set full` capture (dram bytes read + written)
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["hpsi_local_dram_bytes_per_band"] * M, tj["source"]
     roofline = dict(bound="hbm", kernel="Hpsi-local group (kr_sphere_to_x, kr_y_backward, kr_z_apply, kr_y_forward, kr_x_to_sphere)",
                     achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=traffic,
-                    traffic_source="profiles/ncu_full_r1.csv" if traffic else None,
+                    traffic_source=traffic_src,
                     algorithmic_bytes_per_band=alg_bytes_band, ms_per_block=ms_local, us_per_band=1e3 * ms_local / M,
                     peak_source=peak_src + " (of measured)")
     n_proj = kb.n_proj
@@ -272,7 +416,17 @@ def run_gpu(args):
     tf_nl, tf_cublas = fl_nl / (ms_nl * 1e-3) / 1e12, fl_nl / (ms_nl_cublas * 1e-3) / 1e12
     roofline_gemm = dict(bound="tensor", kernel="nonlocal P D P'psi (k_zgemm_cn + k_zgemm_nn, FP64 DMMA)", achieved=tf_nl,
                          peak=tf_cublas, unit="TFLOP/s", frac=tf_nl / tf_cublas, flop=fl_nl, ms=ms_nl,
-                         peak_source="cuBLAS ZGEMM on the same shapes in the same run (calibration probe; nominal FP64 tensor 37-40 TFLOP/s)")
+                         peak_source="cuBLAS ZGEMM on the same shapes in the same run (calibration probe; nominal FP64 tensor 37-40 TFLOP/s)",
+                         frac_of_fixed_dmma_peak=tf_nl / 36.0,
+                         fixed_peak_note="36 TFLOP/s = FP64 DMMA rate implied by 89 % pipe-active at 31.9 TFLOP/s (profiles/ncu_full_r1.csv)")
+    # ---- the reference's GPU formulation with library kernels (cuFFT band-at-a-time + cuBLAS) on the same block
+    lib_gpu = None
+    if rank == 0 and not args.no_library:
+        try:
+            lib_gpu = library_gpu_baseline(torch, basis, blk, kb, psi, 32)
+            lib_gpu["speedup_of_product"] = (M / (ms_step * 1e-3)) / lib_gpu["value"]
+        except Exception as e:
+            lib_gpu = dict(error=repr(e))
 
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
@@ -372,7 +526,7 @@ def run_gpu(args):
 
     # ---- BASELINE config C2 (Si2 LDA, Ecut 30, 8x8x8 k-grid: 29 irreducible k-blocks of 7 bands) -- a full SCF to 1e-8;
     #      the launch-latency-bound regime (fused small-matrix LOBPCG kernels), reported beside the C3 numbers
-    if args.scf_steps > 0 and world == 1:
+    if args.scf_steps > 0 and world == 1 and not args.no_small:
         try:
             a2 = A_SI
             lat2 = np.array([[0, a2, a2], [a2, 0, a2], [a2, a2, 0]])
@@ -380,15 +534,33 @@ def run_gpu(args):
             b2 = dftk.PlaneWaveBasis(m2, Ecut=30.0, kgrid=(8, 8, 8), architecture=arch)
             dftk.self_consistent_field(b2, tol=1e-8)            # warm-up (workspaces, cuSOLVER handles)
             torch.cuda.synchronize()
+            ctx.launch_count(reset=True)
+            ctx.sync_count(reset=True)
             t = time.perf_counter()
             r2 = dftk.self_consistent_field(b2, tol=1e-8)
             torch.cuda.synchronize()
             dt2 = time.perf_counter() - t
+            l2, s2 = ctx.launch_count(), ctx.sync_count()
             extra["scf_c2"] = dict(total_s=dt2, n_iter=r2["n_iter"], s_per_iter=dt2 / r2["n_iter"], k_blocks=len(b2.kpoints),
-                                   fft_size=list(b2.fft_size), energy=r2["energies"].total, converged=bool(r2["converged"]))
+                                   fft_size=list(b2.fft_size), energy=r2["energies"].total, converged=bool(r2["converged"]),
+                                   launches_per_scf_step=l2 / r2["n_iter"], lobpcg_host_syncs_per_scf_step=s2 / r2["n_iter"])
+            if os.path.exists(GOLDEN) and "C2" in json.load(open(GOLDEN)):
+                g2 = json.load(open(GOLDEN))["C2"]
+                extra["scf_c2"]["dE_per_atom_vs_oracle"] = abs(r2["energies"].total - g2["energies"]["total"]) / 2
             del b2, r2
         except Exception as e:
             extra["scf_c2"] = dict(error=repr(e))
+
+    # ---- BASELINE configs C5 / C4: full SCFs with the (k, spin) blocks sharded over the ranks (strong scaling, parity vs
+    #      the oracle's golden energies asserted in the line)
+    if not args.no_sharded:
+        sh = {}
+        for name in args.sharded.split(","):
+            try:
+                sh[name] = sharded_scf(dftk, torch, dist, name, arch, comm, world, dev)
+            except Exception as e:
+                sh[name] = dict(error=repr(e))
+        extra["sharded_scf"] = sh
 
     # ---- CPU baseline on rank 0 (bounded sample)
     cpu = None
@@ -417,11 +589,35 @@ def run_gpu(args):
         dt = time.perf_counter() - t
         got = hpsi_check = kb.apply_h(psi[:nb].contiguous()).cpu().numpy().T
         err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        # single-thread number (the reference's own benchmark protocol, benchmark/run_benchmarks.jl:86)
+        oblk.workers = 1
+        try:
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):
+                t = time.perf_counter()
+                oblk.matmul(xs[:, :2])
+                dt1 = time.perf_counter() - t
+        except Exception:
+            t = time.perf_counter()
+            oblk.matmul(xs[:, :2])
+            dt1 = time.perf_counter() - t
+        oblk.workers = threads
+        # the reference's rule of thumb (docs/src/tricks/parallelization.md:62-72): 30 ms per 128^3 FFT and thread, two FFTs
+        # per band apply (FFT part only; the nonlocal GEMMs come on top)
+        rot = 2 * 0.030 * N / 128 ** 3
         cpu = dict(value=nb / dt, unit="band-applies/s", cores=threads, kind="port",
                    sample=f"{nb} bands of the same block, one pass (NumPy pocketfft band loop threaded over bands + OpenBLAS ZGEMM)",
-                   seconds=dt, max_rel_err_vs_gpu=err)
+                   seconds=dt, max_rel_err_vs_gpu=err,
+                   single_thread=dict(value=2 / dt1, unit="band-applies/s", cores=1, sample="2 bands of the same block, one thread"),
+                   reference_rule_of_thumb=dict(seconds_per_band_per_thread_fft_only=rot, value_all_cores=threads / rot, unit="band-applies/s",
+                                                source="docs/src/tricks/parallelization.md:62-72 (30 ms per 128^3 FFT per thread, 2 FFTs per band)"))
         del Pn
 
+    parity = dict(tolerances="energy 1e-8 Ha/atom, eigenvalues 1e-6 Ha (BASELINE.json north_star)",
+                  c3_hpsi_max_rel_err_vs_oracle=(cpu or {}).get("max_rel_err_vs_gpu"),
+                  c2_dE_per_atom_vs_oracle=extra.get("scf_c2", {}).get("dE_per_atom_vs_oracle"),
+                  **{f"{k.lower()}_dE_per_atom_vs_oracle": v.get("dE_per_atom_vs_oracle") for k, v in extra.get("sharded_scf", {}).items()},
+                  **{f"{k.lower()}_max_d_eigenvalue_vs_oracle": v.get("max_d_eigenvalue_vs_oracle") for k, v in extra.get("sharded_scf", {}).items()})
     if rank == 0:
         line = dict(metric="hpsi_band_applies_per_s", value=value, unit="band-applies/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -430,7 +626,8 @@ def run_gpu(args):
                                 fft_size=list(basis.fft_size), n_pw=n_pw, n_bands=M, n_proj=n_proj,
                                 parallelism=f"kpoints x{world}", cache="inputs (psi 16*n_pw*M bytes) larger than L2"),
                     block_applies_per_s=world * args.steps / (ms_total * 1e-3),
-                    roofline=roofline, roofline_gemm=roofline_gemm, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches_timed,
+                    roofline=roofline, roofline_gemm=roofline_gemm, cpu_baseline=cpu, gpu_library_baseline=lib_gpu, e2e=e2e,
+                    gpu_launches=launches_timed, parity=parity,
                     clocks=clocks, setup_s=setup, **extra)
         os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -446,9 +643,13 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DFTK_BENCH_WORKLOAD", "si250"), choices=list(WORKLOADS))
     ap.add_argument("--bands", type=int, default=0)
     ap.add_argument("--cpu-bands", type=int, default=0,
-                    help="bands in the CPU sample (0 = one per host thread, at most 32)")
+                    help="bands in the CPU sample (0 = 64)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-library", action="store_true", help="skip the cuFFT/cuBLAS formulation of the same H apply")
+    ap.add_argument("--no-small", action="store_true", help="skip the full SCF of BASELINE config C2")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded SCFs of the BASELINE metal configs")
+    ap.add_argument("--sharded", default="C5,C4", help="BASELINE configs whose (k, spin) blocks are sharded over the ranks")
     ap.add_argument("--no-scf", dest="scf", action="store_false",
                     help="skip the LOBPCG timing (eigensolver part of an SCF step, a few iterations)")
     ap.set_defaults(scf=True)
@@ -458,7 +659,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.cpu_bands <= 0:
-        args.cpu_bands = max(4, min(32, effective_cpus()))
+        args.cpu_bands = 64      # enough columns for the CPU ZGEMM not to be bound by the bandwidth of P
     if args.impl == "reference":
         run_reference(args)
     else:

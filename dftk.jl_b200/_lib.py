@@ -22,9 +22,11 @@ SIGNATURES = {
     "dftk_b200_nccl_unique_id": (c_int, [c_vp]),
     "dftk_b200_ctx_destroy": (c_int, [c_vp]),
     "dftk_b200_last_error": (ctypes.c_char_p, [c_vp]),
+    "dftk_b200_ctx_set_stream": (c_int, [c_vp, c_vp]),
     "dftk_b200_sync": (c_int, [c_vp]),
     "dftk_b200_mem_info": (c_int, [c_vp, P(c_i64), P(c_i64)]),
     "dftk_b200_launch_count": (c_i64, [c_vp, c_int]),
+    "dftk_b200_sync_count": (c_i64, [c_vp, c_int]),
     "dftk_b200_set_option": (c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "dftk_b200_grid_create": (c_int, [c_vp, c_int, c_int, c_int, c_dbl, P(c_vp)]),
     "dftk_b200_grid_destroy": (c_int, [c_vp]),
@@ -39,6 +41,7 @@ SIGNATURES = {
     "dftk_b200_band_energies": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dftk_b200_lobpcg": (c_int, [c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp,
                                  P(c_int), P(c_i64), P(c_int)]),
+    "dftk_b200_lobpcg_multi": (c_int, [c_i64, c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dftk_b200_density_accumulate": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "dftk_b200_allreduce": (c_int, [c_vp, c_vp, c_i64, c_int, c_int]),
     "dftk_b200_allgather": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int]),

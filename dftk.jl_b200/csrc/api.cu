@@ -21,6 +21,7 @@ static int record(dftk_b200_ctx* ctx, int code, const std::string& msg) {
   }                                                                         \
   catch (const dftk::Error& e) { return record((ctx), e.code, e.what()); }  \
   catch (const std::exception& e) { return record((ctx), DFTK_B200_EINVAL, e.what()); } \
+  catch (...) { return record((ctx), DFTK_B200_EINVAL, "unknown C++ exception"); }      \
   return DFTK_B200_OK;
 
 // Stage a (possibly host) input buffer onto the device.  Returns a device pointer.
@@ -119,6 +120,7 @@ static int ctx_create_common(int device, dftk_b200_ctx** out) {
   reg_set_attributes();
   blas_set_attributes();
   i8tc_set_attributes();
+  lobpcg_set_attributes();
   *out = c;
   return 0;
 }
@@ -165,6 +167,8 @@ int dftk_b200_ctx_destroy(dftk_b200_ctx* ctx) {
       cudaEventDestroy(ctx->ev_out[i]);
     }
   }
+  if (ctx->batch_ring_h) cudaFreeHost(ctx->batch_ring_h);
+  if (ctx->batch_gather_h) cudaFreeHost(ctx->batch_gather_h);
   if (ctx->nccl) ncclCommDestroy(ctx->nccl);
   if (ctx->cublas) cublasDestroy(ctx->cublas);
   if (ctx->solver_params) cusolverDnDestroyParams(ctx->solver_params);
@@ -177,6 +181,16 @@ int dftk_b200_sync(dftk_b200_ctx* ctx) {
   API_BEGIN
   REQUIRE(ctx, "sync: ctx is NULL");
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+int dftk_b200_ctx_set_stream(dftk_b200_ctx* ctx, void* cuda_stream) {
+  API_BEGIN
+  REQUIRE(ctx, "ctx_set_stream: ctx is NULL");
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));        // nothing of ours may still be in flight on the old stream
+  ctx->stream = (cudaStream_t)cuda_stream;
+  CUBLAS_CHECK(cublasSetStream(ctx->cublas, ctx->stream));
+  CUSOLVER_CHECK(cusolverDnSetStream(ctx->cusolver, ctx->stream));
   API_END(ctx)
 }
 
@@ -196,6 +210,13 @@ int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset) {
   return v;
 }
 
+int64_t dftk_b200_sync_count(dftk_b200_ctx* ctx, int reset) {
+  if (!ctx) return -1;
+  int64_t v = ctx->batch_rounds;
+  if (reset) ctx->batch_rounds = 0;
+  return v;
+}
+
 int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
   API_BEGIN
   REQUIRE(ctx && name, "set_option: NULL argument");
@@ -204,6 +225,7 @@ int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
   else if (n == "band_chunk") ctx->band_chunk = (int)value;
   else if (n == "gemm_stages") ctx->gemm_stages = (value == 3 ? 3 : 2);
   else if (n == "small_dense") ctx->small_dense = (int)value;
+  else if (n == "force_svd_fallback") ctx->force_svd_fallback = (int)value;
   else if (n == "fft_engine") ctx->fft_engine = (int)value;  // 0 = register two-pass where available, 1 = generic
   else throw Error(DFTK_B200_EINVAL, "set_option: unknown option " + n);
   API_END(ctx)
@@ -333,6 +355,10 @@ int dftk_b200_kblock_create(dftk_b200_grid* grid, int64_t n_pw, const int64_t* m
       for (size_t i = 0; i < (size_t)n_proj * n_proj; ++i) dc[2 * i] = kb->D_host[i];
       kb->Dc.ensure((size_t)n_proj * n_proj);
       CUDA_CHECK(cudaMemcpyAsync(kb->Dc.p, dc.data(), dc.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+      if (n_proj <= 96) {      // SMALL_MAX_COLS of the batched small-matrix path (lobpcg_small.cuh)
+        kb->PD.ensure((size_t)n_pw * n_proj);
+        zgemm(ctx, 0, n_pw, n_proj, n_proj, make_double2(1, 0), kb->P.p, n_pw, kb->Dc.p, n_proj, make_double2(0, 0), kb->PD.p, n_pw);
+      }
     }
     CUDA_CHECK(cudaStreamSynchronize(s));
   } catch (...) {
@@ -486,6 +512,22 @@ int dftk_b200_lobpcg(dftk_b200_kblock* kb, void* X, int64_t n_bands, double tol,
     CUDA_CHECK(cudaMemcpyAsync(X, ctx->stage_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
+  API_END(ctx)
+}
+
+int dftk_b200_lobpcg_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, void* const* X, int64_t n_bands, double tol,
+                           int miniter, int maxiter, int64_t n_conv_check, int use_tpa_preconditioner,
+                           double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec, int* converged) {
+  dftk_b200_ctx* ctx = (n_blocks > 0 && kbs && kbs[0]) ? kbs[0]->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(n_blocks >= 0, "lobpcg_multi: negative block count");
+  if (n_blocks == 0) return DFTK_B200_OK;
+  REQUIRE(kbs && X && lambda_host && resid_host && n_iter && n_matvec && converged, "lobpcg_multi: NULL argument");
+  REQUIRE(maxiter >= 0 && miniter >= 0, "lobpcg_multi: bad iteration limits");
+  for (int64_t i = 0; i < n_blocks; ++i)
+    REQUIRE(kbs[i] && X[i] && is_device_ptr(X[i]), "lobpcg_multi: orbitals must be device memory");
+  lobpcg_run_multi(n_blocks, kbs, (cplx* const*)X, n_bands, tol, miniter, maxiter, n_conv_check, use_tpa_preconditioner != 0,
+                   lambda_host, resid_host, n_iter, n_matvec, converged);
   API_END(ctx)
 }
 

@@ -94,6 +94,7 @@ struct dftk_b200_ctx {
   int band_chunk = 0;     // 0 = auto
   int fft_engine = 0;     // 0 = register two-pass engine where a factor pair exists, 1 = generic Stockham (applies to grids created afterwards)
   int gemm_stages = 2;    // cp.async ring depth of the DMMA GEMMs (2 -> 4 CTAs/SM, 3 -> 2 CTAs/SM)
+  int force_svd_fallback = 0;   // test hook: the next N ortho! calls behave as if safe_cholesky had given up
   int small_dense = 1;    // LOBPCG with <= 32 bands: fused small-matrix kernels (lobpcg_small.cuh); 0 = GEMM + cuSOLVER path
   dftk::DevBuf<int> small_counter;   // arrival counter of k_small_gram (kept at zero between launches)
   int sm_count = 148;
@@ -109,6 +110,12 @@ struct dftk_b200_ctx {
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   dftk::DevBuf<char> pipe_in[2], pipe_out[2];
+  // batched small-matrix LOBPCG (lobpcg.cu): descriptor ring and per-round result gather, device + pinned host sides
+  dftk::DevBuf<char> batch_ring;
+  dftk::DevBuf<double> batch_gather;
+  char* batch_ring_h = nullptr;
+  double* batch_gather_h = nullptr;
+  int64_t batch_rounds = 0;   // scheduler rounds (= host synchronisations) of the batched solves since creation / reset
 };
 
 namespace dftk {

@@ -9,7 +9,10 @@
 #include <cmath>
 #include <numeric>
 #include "structs.cuh"
-#include "lobpcg_small.cuh"
+#include <ucontext.h>
+#include <functional>
+#include <memory>
+#include "lobpcg_batch.cuh"
 
 namespace dftk {
 
@@ -221,54 +224,6 @@ __global__ void k_compute_lambda(const cplx* __restrict__ num, const cplx* __res
   lam[i] = (a.x * b.x + a.y * b.y) / d;
 }
 
-// ------------------------------------------------------------------ fused small-matrix path (lobpcg_small.cuh)
-extern __shared__ __align__(16) unsigned char small_dyn_smem[];
-
-// one launch per block-list Gram: CTA partials, the last CTA to finish sums them in a fixed order (deterministic)
-__global__ void __launch_bounds__(256)
-k_small_gram(SmallMatList A, SmallMatList B, long long rows_per_cta, long long n_rows, int upper_only, cplx* ws, cplx* C,
-             long long ldc, unsigned* counter) {
-  small_gram_cta((int)blockIdx.x, rows_per_cta, n_rows, A, B, upper_only, ws, (cplx*)small_dyn_smem);
-  __shared__ int is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    small_gram_reduce((int)gridDim.x, A, B, upper_only, ws, C, ldc);
-    if (threadIdx.x == 0) *counter = 0;
-  }
-}
-
-__global__ void __launch_bounds__(128)
-k_small_blocks_times(SmallMatList Y, const cplx* cm, long long ldcm, int ncols, cplx* out, long long ldo, long long n_rows,
-                     double alpha, double beta) {
-  cplx* cs = (cplx*)small_dyn_smem;
-  const int ny = Y.start[Y.n];
-  for (int e = threadIdx.x; e < ny * ncols; e += blockDim.x) cs[e] = cm[e % ny + ldcm * (e / ny)];
-  __syncthreads();
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_rows) small_blocks_times_row(r, Y, cs, ny, ncols, out, ldo, alpha, beta);
-}
-
-__global__ void __launch_bounds__(128)
-k_small_rmul(cplx* X, long long ld, long long n_rows, int n, const cplx* invR, long long ldr) {
-  cplx* rs = (cplx*)small_dyn_smem;
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) rs[e] = invR[e % n + ldr * (e / n)];
-  __syncthreads();
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n_rows) small_rmul_row(r, X, ld, n, rs, n);
-}
-
-__global__ void __launch_bounds__(SMALL_RED)
-k_small_chol(const cplx* O, long long ldo, int n, cplx* invR, long long ldi, double* stats) {
-  __shared__ cplx As[SMALL_MAX_N * SMALL_MAX_N], Bs[SMALL_MAX_N * SMALL_MAX_N];
-  __shared__ double red[SMALL_RED];
-  __shared__ int flag[2];
-  small_chol_cta(O, ldo, n, invR, ldi, stats, As, Bs, red, flag);
-}
-
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 // Optional section timing (env DFTK_B200_PROFILE=1): stream-synchronising wall clock per LOBPCG section.
@@ -345,7 +300,370 @@ struct SectionProf {
   }
 };
 
+
+// ------------------------------------------------------------------ deferred operations of the batched small path
+// A solve with <= SMALL_MAX_N bands never launches anything itself: it records operations, and the scheduler below
+// merges the same operation of all k-blocks in flight into ONE launch (lobpcg_batch.cuh).  Each solve runs as a
+// coroutine (ucontext) that yields where the algorithm needs a value on the host.
+enum OpType {
+  OP_GRAM = 0, OP_CHOL, OP_RMUL, OP_BTIMES, OP_HEEV, OP_RESIDUAL, OP_PRECOND, OP_COLNORMS, OP_SCALE, OP_COPY2D, OP_MAKECP,
+  OP_STATS, OP_RANDN, OP_LAMBDA, OP_APPLYH, OP_D2H, OP_NTYPES
+};
+struct ApplyHItem { dftk_b200_kblock* kb; const cplx* in; cplx* out; int ncols; };
+struct D2HItem { const double* src; int n; double* host_dst; };
+struct Op {
+  int type;
+  union U {
+    GramItem gram; CholItem chol; RmulItem rmul; BtimesItem btimes; HeevItem heev; ResidualItem residual; PrecondItem precond;
+    ColnormItem colnorm; ScaleItem scale; Copy2dItem copy2d; MakecpItem makecp; StatsItem stats; RandnItem randn;
+    LambdaItem lambda; ApplyHItem applyh; D2HItem d2h;
+    U() {}
+  } u;
+  Op() : type(-1) {}
+};
+
+struct Coro {
+  ucontext_t uc;
+  std::unique_ptr<char[]> stack;
+  size_t stack_size = 0;
+  std::function<void()> body;
+  bool finished = false, waiting_align = false, failed = false;
+  int err_code = 0;
+  std::string err;
+  std::vector<Op> ops;
+  size_t cursor = 0;
+};
+static thread_local Coro* g_coro = nullptr;
+static thread_local ucontext_t* g_main_uc = nullptr;
+
+static void coro_entry() {
+  Coro* c = g_coro;
+  try {
+    c->body();
+  } catch (const Error& e) {
+    c->failed = true;
+    c->err_code = e.code;
+    c->err = e.what();
+  } catch (const std::exception& e) {
+    c->failed = true;
+    c->err_code = DFTK_B200_EINVAL;
+    c->err = e.what();
+  } catch (...) {
+    c->failed = true;
+    c->err_code = DFTK_B200_EINVAL;
+    c->err = "unknown exception in a LOBPCG solve";
+  }
+  c->finished = true;
+  swapcontext(&c->uc, g_main_uc);
+}
+static inline void coro_yield(Coro* c) { swapcontext(&c->uc, g_main_uc); }
+
+// Launches the recorded operations: the same operation of several solves becomes one launch.
+struct BatchExec {
+  dftk_b200_ctx* ctx;
+  char* ring_h = nullptr;      // pinned staging of the item descriptors
+  size_t ring_cap = 0, ring_off = 0;
+  double* gather_h = nullptr;  // pinned landing zone of the per-round D2H gather
+  size_t gather_cap = 0;
+  std::vector<std::pair<double*, std::pair<size_t, int>>> scatter;   // host_dst <- gather_h[offset .. offset+n)
+  size_t gather_used = 0;
+  int64_t rounds = 0;
+
+  explicit BatchExec(dftk_b200_ctx* c) : ctx(c) {
+    // pinned staging buffers are created once per context (cudaMallocHost costs about a millisecond)
+    ring_cap = (size_t)4 << 20;
+    gather_cap = (size_t)1 << 18;
+    if (!ctx->batch_ring_h) {
+      CUDA_CHECK(cudaMallocHost((void**)&ctx->batch_ring_h, ring_cap));
+      CUDA_CHECK(cudaMallocHost((void**)&ctx->batch_gather_h, gather_cap * sizeof(double)));
+    }
+    ring_h = ctx->batch_ring_h;
+    gather_h = ctx->batch_gather_h;
+    ctx->batch_ring.ensure(ring_cap);
+    ctx->batch_gather.ensure(gather_cap);
+  }
+  BatchExec(const BatchExec&) = delete;
+  BatchExec& operator=(const BatchExec&) = delete;
+
+  // copy `n` descriptors to the device ring; returns the device address.  The ring is recycled at every stream
+  // synchronisation (the staging memory of an enqueued copy must stay untouched until the copy has run).
+  template <class T>
+  const T* upload(const std::vector<T>& items) {
+    const size_t bytes = (items.size() * sizeof(T) + 255) & ~(size_t)255;
+    if (ring_off + bytes > ring_cap) {
+      CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      ring_off = 0;
+      REQUIRE(bytes <= ring_cap, "batched LOBPCG: descriptor ring too small");
+    }
+    memcpy(ring_h + ring_off, items.data(), items.size() * sizeof(T));
+    char* d = ctx->batch_ring.p + ring_off;
+    CUDA_CHECK(cudaMemcpyAsync(d, ring_h + ring_off, items.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ring_off += bytes;
+    return (const T*)d;
+  }
+  template <class T, class F>
+  std::vector<T> collect(const std::vector<Op*>& ops, F get) {
+    std::vector<T> v;
+    v.reserve(ops.size());
+    for (Op* o : ops) v.push_back(get(o));
+    return v;
+  }
+  static unsigned gx_for(long long total) {
+    long long g = (total + 255) / 256;
+    return (unsigned)std::max<long long>(1, std::min<long long>(g, 148 * 32));
+  }
+
+  void gram_batch(std::vector<GramItem>& v) {
+    // per-item partial workspaces and arrival counters
+    size_t ws_total = 0;
+    int max_ctas = 1;
+    size_t smem = 0;
+    for (auto& it : v) {
+      const int nA = it.A.start[it.A.n], nB = it.B.start[it.B.n];
+      ws_total += (size_t)it.n_ctas * nA * nB;
+      max_ctas = std::max(max_ctas, it.n_ctas);
+      smem = std::max(smem, (size_t)SMALL_TR * (nA + nB) * sizeof(cplx));
+    }
+    cplx* ws = (cplx*)ctx->gemm_ws.ensure(ws_total * sizeof(cplx));
+    if (ctx->small_counter.cap < v.size()) {
+      unsigned* c = (unsigned*)ctx->small_counter.ensure(std::max<size_t>(v.size(), 256));
+      CUDA_CHECK(cudaMemsetAsync(c, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));
+    }
+    size_t off = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+      const int nA = v[i].A.start[v[i].A.n], nB = v[i].B.start[v[i].B.n];
+      v[i].ws = ws + off;
+      v[i].counter = (unsigned*)ctx->small_counter.p + i;
+      off += (size_t)v[i].n_ctas * nA * nB;
+    }
+    const GramItem* d = upload(v);
+    LAUNCH(ctx, kb_gram, dim3((unsigned)max_ctas, (unsigned)v.size()), 256, smem, d);
+  }
+  void btimes_batch(const std::vector<BtimesItem>& v) {
+    long long max_rows = 1;
+    size_t smem = 0;
+    for (auto& it : v) {
+      max_rows = std::max(max_rows, it.n_rows);
+      smem = std::max(smem, (size_t)it.Y.start[it.Y.n] * it.ncols * sizeof(cplx));
+    }
+    const BtimesItem* d = upload(v);
+    LAUNCH(ctx, kb_btimes, dim3((unsigned)((max_rows + 127) / 128), (unsigned)v.size()), 128, smem, d);
+  }
+
+  void launch(int type, const std::vector<Op*>& ops) {
+    const unsigned n = (unsigned)ops.size();
+    switch (type) {
+      case OP_GRAM: {
+        auto v = collect<GramItem>(ops, [](Op* o) { return o->u.gram; });
+        gram_batch(v);
+        break;
+      }
+      case OP_CHOL: {
+        auto v = collect<CholItem>(ops, [](Op* o) { return o->u.chol; });
+        LAUNCH(ctx, kb_chol, n, SMALL_RED, 0, upload(v));
+        break;
+      }
+      case OP_RMUL: {
+        auto v = collect<RmulItem>(ops, [](Op* o) { return o->u.rmul; });
+        long long max_rows = 1;
+        size_t smem = 0;
+        for (auto& it : v) {
+          max_rows = std::max(max_rows, it.n_rows);
+          smem = std::max(smem, (size_t)it.n * it.n * sizeof(cplx));
+        }
+        LAUNCH(ctx, kb_rmul, dim3((unsigned)((max_rows + 127) / 128), n), 128, smem, upload(v));
+        break;
+      }
+      case OP_BTIMES: {
+        auto v = collect<BtimesItem>(ops, [](Op* o) { return o->u.btimes; });
+        btimes_batch(v);
+        break;
+      }
+      case OP_HEEV: {
+        auto v = collect<HeevItem>(ops, [](Op* o) { return o->u.heev; });
+        size_t smem = 0;
+        for (auto& it : v) {
+          const size_t half = ((it.n + 1) & ~1) / 2;
+          smem = std::max(smem, (size_t)it.n * it.n * sizeof(cplx) + 2 * (half + 1) * sizeof(cplx) + SMALL_RED * sizeof(double) +
+                                    2 * (half + 1) * sizeof(int) + 16);
+        }
+        LAUNCH(ctx, kb_heev, n, SMALL_RED, smem, upload(v));
+        break;
+      }
+      case OP_RESIDUAL: {
+        auto v = collect<ResidualItem>(ops, [](Op* o) { return o->u.residual; });
+        int mc = 1;
+        for (auto& it : v) mc = std::max(mc, it.n_cols);
+        LAUNCH(ctx, kb_residual, dim3((unsigned)mc, n), 256, 0, upload(v));
+        break;
+      }
+      case OP_LAMBDA: {
+        auto v = collect<LambdaItem>(ops, [](Op* o) { return o->u.lambda; });
+        int mc = 1;
+        for (auto& it : v) mc = std::max(mc, it.n_cols);
+        LAUNCH(ctx, kb_lambda, dim3((unsigned)mc, n), 256, 0, upload(v));
+        break;
+      }
+      case OP_COLNORMS: {
+        auto v = collect<ColnormItem>(ops, [](Op* o) { return o->u.colnorm; });
+        int mc = 1;
+        for (auto& it : v) mc = std::max(mc, it.n_cols);
+        LAUNCH(ctx, kb_col_norms, dim3((unsigned)mc, n), 256, 0, upload(v));
+        break;
+      }
+      case OP_PRECOND: {
+        auto v = collect<PrecondItem>(ops, [](Op* o) { return o->u.precond; });
+        long long mt = 1;
+        for (auto& it : v) mt = std::max(mt, it.n_rows * it.n_cols);
+        LAUNCH(ctx, kb_precondition, dim3(gx_for(mt), n), 256, 0, upload(v));
+        break;
+      }
+      case OP_SCALE: {
+        auto v = collect<ScaleItem>(ops, [](Op* o) { return o->u.scale; });
+        long long mt = 1;
+        for (auto& it : v) mt = std::max(mt, it.n_rows * it.n_cols);
+        LAUNCH(ctx, kb_scale_cols_inv, dim3(gx_for(mt), n), 256, 0, upload(v));
+        break;
+      }
+      case OP_COPY2D: {
+        auto v = collect<Copy2dItem>(ops, [](Op* o) { return o->u.copy2d; });
+        long long mt = 1;
+        for (auto& it : v) mt = std::max(mt, it.n_rows * it.n_cols);
+        LAUNCH(ctx, kb_copy2d, dim3(gx_for(mt), n), 256, 0, upload(v));
+        break;
+      }
+      case OP_MAKECP: {
+        auto v = collect<MakecpItem>(ops, [](Op* o) { return o->u.makecp; });
+        long long mt = 1;
+        for (auto& it : v) mt = std::max(mt, (long long)it.n_rows * it.n_cols);
+        LAUNCH(ctx, kb_make_cP, dim3(gx_for(mt), n), 256, 0, upload(v));
+        break;
+      }
+      case OP_STATS: {
+        auto v = collect<StatsItem>(ops, [](Op* o) { return o->u.stats; });
+        LAUNCH(ctx, kb_matrix_stats, n, 256, 0, upload(v));
+        break;
+      }
+      case OP_RANDN: {
+        auto v = collect<RandnItem>(ops, [](Op* o) { return o->u.randn; });
+        long long mt = 1;
+        for (auto& it : v) mt = std::max(mt, it.n_rows);
+        LAUNCH(ctx, kb_randn_col, dim3(gx_for(mt), n), 256, 0, upload(v));
+        break;
+      }
+      case OP_APPLYH: {
+        // local + kinetic part: the k-block's own batched FFT pipeline; nonlocal part P (D P'psi) as two batched small
+        // products over all k-blocks of the round (projector counts of the small configurations are <= 20)
+        std::vector<GramItem> g;
+        std::vector<BtimesItem> b;
+        for (Op* o : ops) {
+          const ApplyHItem& a = o->u.applyh;
+          dftk_b200_kblock* kb = a.kb;
+          kb_apply_local_kinetic(kb, a.in, a.out, a.ncols, kb->has_V, kb->has_kin, false);
+          if (kb->n_proj == 0) continue;
+          if (kb->n_proj > SMALL_MAX_COLS || a.ncols > SMALL_MAX_N || !kb->PD.p) {
+            kb_apply_nonlocal(kb, a.in, a.out, a.ncols);
+            continue;
+          }
+          cplx* proj = kb->proj.ensure((size_t)2 * kb->n_proj * SMALL_MAX_N);
+          GramItem gi{};
+          gi.A.n = gi.B.n = 1;
+          gi.A.p[0] = kb->P.p; gi.A.ld[0] = kb->n_pw; gi.A.cols[0] = (int)kb->n_proj;
+          gi.B.p[0] = a.in; gi.B.ld[0] = kb->n_pw; gi.B.cols[0] = a.ncols;
+          for (int q = 1; q < 4; ++q) { gi.A.start[q] = (int)kb->n_proj; gi.B.start[q] = a.ncols; }
+          gi.n_rows = kb->n_pw;
+          small_gram_geometry(ctx, kb->n_pw, &gi.n_ctas, &gi.rows_per_cta);
+          gi.upper_only = 0;
+          gi.C = proj;
+          gi.ldc = kb->n_proj;
+          g.push_back(gi);
+          BtimesItem bi{};
+          bi.Y.n = 1;
+          bi.Y.p[0] = kb->PD.p; bi.Y.ld[0] = kb->n_pw; bi.Y.cols[0] = (int)kb->n_proj;
+          for (int q = 1; q < 4; ++q) bi.Y.start[q] = (int)kb->n_proj;
+          bi.cm = proj; bi.ldcm = kb->n_proj; bi.ncols = a.ncols;
+          bi.out = a.out; bi.ldo = kb->n_pw; bi.n_rows = kb->n_pw; bi.alpha = 1.0; bi.beta = 1.0;
+          b.push_back(bi);
+        }
+        if (!g.empty()) {
+          gram_batch(g);
+          btimes_batch(b);
+        }
+        break;
+      }
+      case OP_D2H: {
+        std::vector<GatherItem> v;
+        for (Op* o : ops) {
+          const D2HItem& d = o->u.d2h;
+          REQUIRE(gather_used + d.n <= gather_cap, "batched LOBPCG: gather buffer too small");
+          v.push_back(GatherItem{d.src, d.n, (int)gather_used});
+          scatter.push_back({d.host_dst, {gather_used, d.n}});
+          gather_used += d.n;
+        }
+        LAUNCH(ctx, kb_gather, n, 64, 0, upload(v), ctx->batch_gather.p);
+        break;
+      }
+      default: throw Error(DFTK_B200_EINVAL, "batched LOBPCG: unknown operation");
+    }
+  }
+  static void small_gram_geometry(dftk_b200_ctx* ctx, int64_t rows, int* n_ctas_out, long long* rpc_out) {
+    int64_t n_ctas = std::max<int64_t>(1, std::min<int64_t>((rows + 127) / 128, 2 * (int64_t)ctx->sm_count));
+    int64_t rpc = (rows + n_ctas - 1) / n_ctas;
+    rpc = (rpc + SMALL_TR - 1) / SMALL_TR * SMALL_TR;
+    n_ctas = std::max<int64_t>(1, (rows + rpc - 1) / rpc);
+    *n_ctas_out = (int)n_ctas;
+    *rpc_out = rpc;
+  }
+
+  // run everything recorded by the solves since the last round; one stream synchronisation at the end
+  void flush(std::vector<std::unique_ptr<Coro>>& coros) {
+    bool any = false;
+    for (auto& c : coros) any = any || c->cursor < c->ops.size();
+    if (!any) return;
+    rounds++;
+    std::vector<Op*> batch;
+    while (true) {
+      // count the operation types at the cursors; run the rarest one first so that solves that are an operation behind
+      // (a retry, a re-randomised column) catch up with the pack
+      int count[OP_NTYPES] = {0};
+      for (auto& c : coros)
+        if (c->cursor < c->ops.size()) count[c->ops[c->cursor].type]++;
+      int best = -1;
+      for (int t = 0; t < OP_NTYPES; ++t)
+        if (count[t] > 0 && (best < 0 || count[t] < count[best])) best = t;
+      if (best < 0) break;
+      batch.clear();
+      for (auto& c : coros)
+        if (c->cursor < c->ops.size() && c->ops[c->cursor].type == best) batch.push_back(&c->ops[c->cursor++]);
+      launch(best, batch);
+    }
+    if (gather_used)
+      CUDA_CHECK(cudaMemcpyAsync(gather_h, ctx->batch_gather.p, gather_used * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (auto& s : scatter) memcpy(s.first, gather_h + s.second.first, s.second.second * sizeof(double));
+    scatter.clear();
+    gather_used = 0;
+    ring_off = 0;
+    for (auto& c : coros) {
+      c->ops.clear();
+      c->cursor = 0;
+    }
+  }
+};
+
 // ------------------------------------------------------------------ solver object
+struct SolveArgs {
+  cplx* X;
+  double tol;
+  int miniter, maxiter;
+  int64_t n_conv_check;
+  double* lambda_host;
+  double* resid_host;
+  int* n_iter;
+  int64_t* n_matvec;
+  int* converged;
+};
+
 struct Lobpcg {
   dftk_b200_kblock* kb;
   dftk_b200_ctx* ctx;
@@ -359,10 +677,37 @@ struct Lobpcg {
   int64_t S3;
   cplx *G, *cX, *cP, *Ochol, *invR, *BYX, *tmpS;
   // big scratch
+  cplx *AX, *R, *AR, *P, *AP, *nX, *nAX, *nR, *nP, *nAP;
   cplx* tmpN;  // N x M
-  // fused small-matrix path (M <= SMALL_MAX_N): see lobpcg_small.cuh
+  // batched small-matrix path (M <= SMALL_MAX_N): operations are recorded on `co` and launched by BatchExec
   bool small = false;
-  unsigned* d_counter = nullptr;
+  Coro* co = nullptr;
+  int64_t ldBYX = 0;
+  int64_t n_chol_total = 0;
+
+  Op& newop(int type) {
+    co->ops.emplace_back();
+    Op& o = co->ops.back();
+    o.type = type;
+    return o;
+  }
+  // host <- device doubles; the solve continues once the value is there
+  void get(void* host, const void* dev, size_t bytes) {
+    if (small) {
+      Op& o = newop(OP_D2H);
+      o.u.d2h = D2HItem{(const double*)dev, (int)(bytes / sizeof(double)), (double*)host};
+      coro_yield(co);
+      return;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
+  // solves of one batch meet here so that the same operations of all of them share launches again after a divergence
+  void align() {
+    if (!small) return;
+    co->waiting_align = true;
+    coro_yield(co);
+  }
 
   static SmallMatList mklist(const std::vector<Mat>& v) {
     SmallMatList L{};
@@ -388,40 +733,78 @@ struct Lobpcg {
     return L;
   }
   void small_gram(const std::vector<Mat>& A, const std::vector<Mat>& B, cplx* C, int64_t ldc, bool upper_only) {
-    SmallMatList LA = mklist(A), LB = mklist(B);
-    const int nA = LA.start[LA.n], nB = LB.start[LB.n];
-    if (nA == 0 || nB == 0) return;
-    const int64_t rows = A[0].rows;
-    int64_t n_ctas = std::max<int64_t>(1, std::min<int64_t>((rows + 127) / 128, 2 * (int64_t)ctx->sm_count));
-    int64_t rpc = (rows + n_ctas - 1) / n_ctas;
-    rpc = (rpc + SMALL_TR - 1) / SMALL_TR * SMALL_TR;
-    n_ctas = std::max<int64_t>(1, (rows + rpc - 1) / rpc);
-    cplx* ws = (cplx*)ctx->gemm_ws.ensure((size_t)n_ctas * nA * nB * sizeof(cplx));
-    const size_t smem = (size_t)SMALL_TR * (nA + nB) * sizeof(cplx);
-    LAUNCH(ctx, k_small_gram, (unsigned)n_ctas, 256, smem, LA, LB, (long long)rpc, (long long)rows, upper_only ? 1 : 0, ws,
-           C, (long long)ldc, d_counter);
+    GramItem g{};
+    g.A = mklist(A);
+    g.B = mklist(B);
+    if (g.A.start[g.A.n] == 0 || g.B.start[g.B.n] == 0) return;
+    g.n_rows = A[0].rows;
+    BatchExec::small_gram_geometry(ctx, g.n_rows, &g.n_ctas, &g.rows_per_cta);
+    g.upper_only = upper_only ? 1 : 0;
+    g.C = C;
+    g.ldc = ldc;
+    newop(OP_GRAM).u.gram = g;
   }
   void small_blocks_times(const std::vector<Mat>& Y, const cplx* c, int64_t ldc, int64_t ncols, Mat out, double alpha,
                           double beta) {
     if (ncols == 0 || out.rows == 0) return;
     REQUIRE(ncols <= SMALL_MAX_N, "small path: too many output columns");
-    SmallMatList LY = mklist(Y);
-    const int ny = LY.start[LY.n];
-    LAUNCH(ctx, k_small_blocks_times, (unsigned)((out.rows + 127) / 128), 128, (size_t)ny * ncols * sizeof(cplx), LY, c,
-           (long long)ldc, (int)ncols, out.p, (long long)out.ld, (long long)out.rows, alpha, beta);
+    BtimesItem b{};
+    b.Y = mklist(Y);
+    b.cm = c; b.ldcm = ldc; b.ncols = (int)ncols; b.out = out.p; b.ldo = out.ld; b.n_rows = out.rows; b.alpha = alpha; b.beta = beta;
+    newop(OP_BTIMES).u.btimes = b;
   }
 
   void copy2d(Mat dst, Mat src) {
     if (src.rows == 0 || src.cols == 0) return;
+    if (small) {
+      newop(OP_COPY2D).u.copy2d = Copy2dItem{dst.p, dst.ld, src.p, src.ld, src.rows, (int)src.cols};
+      return;
+    }
     LAUNCH(ctx, k_copy2d, nblk(src.rows * src.cols), 256, 0, dst.p, dst.ld, (const cplx*)src.p, src.ld,
            src.rows, src.cols);
   }
-  void get(void* host, const void* dev, size_t bytes) {
-    CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  // contiguous device copy / zero fill of `n` complex numbers
+  void copy_flat(cplx* dst, const cplx* src, int64_t n) {
+    if (n <= 0) return;
+    if (small) {
+      newop(OP_COPY2D).u.copy2d = Copy2dItem{dst, n, src, n, n, 1};
+      return;
+    }
+    if (src) CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->stream));
+    else CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(cplx), ctx->stream));
+  }
+  void col_norms(Mat X, double* out) {
+    if (X.cols == 0) return;
+    if (small) {
+      newop(OP_COLNORMS).u.colnorm = ColnormItem{X.p, X.ld, X.rows, (int)X.cols, out};
+      return;
+    }
+    LAUNCH(ctx, k_col_norms, (unsigned)X.cols, 256, 0, (const cplx*)X.p, X.ld, X.rows, out);
+  }
+  void scale_cols_inv(Mat X, const double* norms) {
+    if (X.cols == 0) return;
+    if (small) {
+      newop(OP_SCALE).u.scale = ScaleItem{X.p, X.ld, X.rows, (int)X.cols, norms};
+      return;
+    }
+    LAUNCH(ctx, k_scale_cols_inv, nblk(X.rows * X.cols), 256, 0, X.p, X.ld, X.rows, X.cols, norms);
+  }
+  void matrix_stats(const cplx* A, int64_t ld, int64_t r, int64_t c, double* out) {
+    if (small) {
+      newop(OP_STATS).u.stats = StatsItem{A, ld, (int)r, (int)c, out};
+      return;
+    }
+    LAUNCH(ctx, k_matrix_stats, 1, 1024, 0, A, ld, r, c, out);
+  }
+  void randn_col(cplx* x, int64_t n_rows, uint64_t seed) {
+    if (small) {
+      newop(OP_RANDN).u.randn = RandnItem{x, n_rows, seed};
+      return;
+    }
+    LAUNCH(ctx, k_randn_col, nblk(n_rows), 256, 0, x, n_rows, seed);
   }
   void stats(const cplx* A, int64_t ld, int64_t r, int64_t c, double* out4) {
-    LAUNCH(ctx, k_matrix_stats, 1, 1024, 0, A, ld, r, c, d_stats);
+    matrix_stats(A, ld, r, c, d_stats);
     get(out4, d_stats, 4 * sizeof(double));
   }
   double normest(const cplx* A, int64_t ld, int64_t n) {
@@ -458,34 +841,44 @@ struct Lobpcg {
     }
   }
 
-  // ortho!(X) :216-261.  X: rows x n (in place).  `tmp` must hold rows x n.
-  // returns growth factor; throws on the (never observed) SVD-fallback condition
+  // SVD fallback of ortho! (only reachable when five shifted Cholesky factorisations fail); defined below
+  void ortho_svd_fallback(Mat X, cplx* tmp, int64_t ldtmp);
+
+  // ortho!(X) :216-261.  X: rows x n (in place).  `tmp` must hold rows x n.  Returns the growth factor.
   double ortho(Mat X, cplx* tmp, int64_t ldtmp) {
     const int64_t n = X.cols;
     if (n == 0) return 1.0;
     double growth = 1.0;
+    int fallbacks = 0;
     if (small) {
       // gram -> fused safe_cholesky/inverse/normest (one CTA) -> one host sync -> X *= invR
-      for (int outer = 0; outer < 50; ++outer) {
+      for (;;) {
         gram({X}, {X}, Ochol, S3, true);
-        LAUNCH(ctx, k_small_chol, 1, SMALL_RED, 0, (const cplx*)Ochol, (long long)S3, (int)n, invR, (long long)S3, d_stats);
+        newop(OP_CHOL).u.chol = CholItem{Ochol, (long long)S3, (int)n, invR, (long long)S3, d_stats};
         double s[4];
         get(s, d_stats, 4 * sizeof(double));
-        const int nchol = (int)s[0];
-        if (nchol == 0) throw Error(DFTK_B200_ENUM, "ortho!: Cholesky failing badly (SVD fallback not implemented)");
-        LAUNCH(ctx, k_small_rmul, (unsigned)((X.rows + 127) / 128), 128, (size_t)n * n * sizeof(cplx), X.p, (long long)X.ld,
-               (long long)X.rows, (int)n, (const cplx*)invR, (long long)S3);
+        int nchol = (int)s[0];
+        if (ctx->force_svd_fallback > 0) {
+          ctx->force_svd_fallback--;
+          nchol = 0;
+        }
+        if (nchol == 0) {      // safe_cholesky gave up (:226-231): SVD fallback, then a regular pass polishes the result
+          if (++fallbacks > 3) throw Error(DFTK_B200_ENUM, "ortho!: cannot orthogonalise the block even after the SVD fallback");
+          ortho_svd_fallback(X, tmp, ldtmp);
+          growth = 1.0;
+          continue;
+        }
+        newop(OP_RMUL).u.rmul = RmulItem{X.p, (long long)X.ld, (long long)X.rows, (int)n, invR, (long long)S3};
         const double norminvR = s[1];
         growth *= norminvR;
         const double condR = s[2] * norminvR;
         const double est = EPS * condR * condR;
         n_chol_total += nchol;
         if (nchol == 1 && est < 2 * EPS) break;
-        if (outer == 49) throw Error(DFTK_B200_ENUM, "ortho!: did not converge");
       }
       return growth;
     }
-    for (int outer = 0; outer < 50; ++outer) {
+    for (;;) {
       gram({X}, {X}, Ochol, S3, true);
       LAUNCH(ctx, k_hermitize_upper, nblk(n * n), 256, 0, Ochol, S3, n);
       // safe_cholesky :190-210
@@ -518,7 +911,16 @@ struct Lobpcg {
         // note: the reference recomputes norm(O) of the shifted matrix; the difference is O(eps)
         alpha *= 10;
       }
-      if (!ok) throw Error(DFTK_B200_ENUM, "ortho!: Cholesky failing badly (SVD fallback not implemented)");
+      if (ctx->force_svd_fallback > 0) {
+        ctx->force_svd_fallback--;
+        ok = false;
+      }
+      if (!ok) {
+        if (++fallbacks > 3) throw Error(DFTK_B200_ENUM, "ortho!: cannot orthogonalise the block even after the SVD fallback");
+        ortho_svd_fallback(X, tmp, ldtmp);
+        growth = 1.0;
+        continue;
+      }
       // X <- X * invR   (rmul!(X, invR))
       zgemm(ctx, 0, X.rows, n, n, make_double2(1, 0), X.p, X.ld, invR, S3, make_double2(0, 0), tmp, ldtmp,
             /*invR is upper triangular*/ true);
@@ -529,11 +931,9 @@ struct Lobpcg {
       double est = EPS * condR * condR;
       n_chol_total += nchol;
       if (nchol == 1 && est < 2 * EPS) break;
-      if (outer == 49) throw Error(DFTK_B200_ENUM, "ortho!: did not converge");
     }
     return growth;
   }
-  int64_t n_chol_total = 0;
 
   int potrf_upper(cplx* A, int64_t n) {
     int lwork = 0;
@@ -545,7 +945,8 @@ struct Lobpcg {
                                     (int)S3, (cuDoubleComplex*)w, lwork, dinfo));
     ctx->launches++;
     int info = 0;
-    get(&info, dinfo, sizeof(int));
+    CUDA_CHECK(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return info;
   }
   int trtri_upper(cplx* A, int64_t n) {
@@ -559,11 +960,18 @@ struct Lobpcg {
                                     CUDA_C_64F, A, S3, w, wd, hw.data(), wh, dinfo));
     ctx->launches++;
     int info = 0;
-    get(&info, dinfo, sizeof(int));
+    CUDA_CHECK(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return info;
   }
-  // eigen(Hermitian(G)) upper triangle; eigenvectors overwrite G, eigenvalues -> d_w (ascending)
-  void heevd(cplx* A, int64_t n) {
+  // eigen(Hermitian(A)) upper triangle, leading dimension S3; eigenvectors overwrite A, eigenvalues -> d_w (ascending)
+  // lam_out / n_keep (batched path only): the n_keep lowest eigenvalues are also written to lam_out
+  void heev(cplx* A, int64_t n, double* lam_out = nullptr, int n_keep = 0) {
+    if (small) {
+      // one-CTA Jacobi per k-block (lobpcg_small.cuh): no library call, no host synchronisation; tmpS holds V
+      newop(OP_HEEV).u.heev = HeevItem{A, (long long)S3, (int)n, d_w, tmpS, d_stats + 4, lam_out, n_keep};
+      return;
+    }
     // 64-bit generic API: unlike the legacy cusolverDnZheevd it has no OpenMP host stage whose speed depends on the
     // process' OMP_* environment (measured: 26 ms for n = 1509 under every setting vs 30-700 ms for Zheevd)
     if (!ctx->solver_params) CUSOLVER_CHECK(cusolverDnCreateParams(&ctx->solver_params));
@@ -579,7 +987,8 @@ struct Lobpcg {
                                     dinfo));
     ctx->launches++;
     int info = 0;
-    get(&info, dinfo, sizeof(int));
+    CUDA_CHECK(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (info != 0) throw Error(DFTK_B200_ENUM, "rayleigh_ritz: heevd failed, info=" + std::to_string(info));
   }
 
@@ -591,16 +1000,16 @@ struct Lobpcg {
     int64_t ny = 0;
     for (auto& y : Y) ny += y.cols;
     REQUIRE(ny <= ldBYX, "ortho_against: workspace too small");
-    LAUNCH(ctx, k_col_norms, (unsigned)n, 256, 0, (const cplx*)X.p, X.ld, X.rows, d_norms);
-    LAUNCH(ctx, k_scale_cols_inv, nblk(X.rows * n), 256, 0, X.p, X.ld, X.rows, n, (const double*)d_norms);
+    col_norms(X, d_norms);
+    scale_cols_inv(X, d_norms);
     std::vector<double> norms(n);
     for (int niter = 1;; ++niter) {
       gram(Y, {X}, BYX, ldBYX, false);
       blocks_times(Y, BYX, ldBYX, n, X, -1.0, 1.0);  // X -= Y * BY'X
       // drop_small! :264-268
-      LAUNCH(ctx, k_col_norms, (unsigned)n, 256, 0, (const cplx*)X.p, X.ld, X.rows, d_norms);
+      col_norms(X, d_norms);
       // ||BY'X|| is needed below; it does not depend on the re-randomisation, so both results share one host sync
-      LAUNCH(ctx, k_matrix_stats, 1, 1024, 0, (const cplx*)BYX, ldBYX, ny, n, d_stats);
+      matrix_stats(BYX, ldBYX, ny, n, d_stats);
       const size_t span = (size_t)(d_stats - d_norms) + 4;
       std::vector<double> both(span);
       get(both.data(), d_norms, span * sizeof(double));
@@ -610,7 +1019,7 @@ struct Lobpcg {
         if (norms[c] <= tol) {
           Mat xc = X.cols_range(c, 1);
           rng_counter += 0x100000000ull;
-          LAUNCH(ctx, k_randn_col, nblk(X.rows), 256, 0, xc.p, X.rows, rng_counter);
+          randn_col(xc.p, X.rows, rng_counter);
           // X[:,c] -= Y (BY' X[:,c])
           gram(Y, {xc}, tmpS, S3, false);
           blocks_times(Y, tmpS, S3, 1, xc, -1.0, 1.0);
@@ -619,108 +1028,168 @@ struct Lobpcg {
       if (std::sqrt(s[3]) < tol && niter > 1) break;
       double growth = ortho(X, tmp, ldtmp);
       if (growth * EPS < tol) break;
-      if (niter > 10) throw Error(DFTK_B200_ENUM, "ortho!(X,Y): failing badly (SVD fallback not implemented)");
+      if (niter > 10) {
+        // :307-314 "Ortho(X, Y) is failing badly, falling back to SVD": X <- U V' and return
+        ortho_svd_fallback(X, tmp, ldtmp);
+        ortho(X, tmp, ldtmp);
+        break;
+      }
     }
   }
-  int64_t ldBYX = 0;
+
+  void prepare(SolveArgs& a);
+  void body(SolveArgs& a);
 };
 
-int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int miniter, int maxiter,
-               int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter_out,
-               int64_t* n_matvec_out, int* converged_out) {
-  dftk_b200_ctx* ctx = kb->grid->ctx;
-  const int64_t N = kb->n_pw;
-  REQUIRE(M >= 1, "lobpcg: n_bands must be >= 1");
-  REQUIRE(N > 3 * M, "The eigenproblem is too small, and the iterative eigensolver will fail; increase "
-                     "the number of degrees of freedom, or use a dense eigensolver.");
+// ---- SVD fallback of ortho! (lobpcg_hyper_impl.jl:226-231, :307-314): X <- U V' for X = U S V'.
+// Through the eigendecomposition of the Gram matrix, X'X = V S² V': the columns of X V are S_l u_l.  Directions whose
+// singular value is below sqrt(eps) S_max cannot be recovered from the Gram matrix (LAPACK's U is arbitrary there, too):
+// they are replaced by random vectors projected against the recovered ones.  The caller runs a regular Cholesky pass
+// afterwards, which removes what rounding left (the block is well conditioned by then).
+__global__ void k_conj_transpose(const cplx* __restrict__ A, int64_t lda, cplx* __restrict__ B, int64_t ldb, int n) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int i = idx % n, j = idx / n;
+  const cplx v = A[j + lda * i];
+  B[i + ldb * j] = make_double2(v.x, -v.y);
+}
+void Lobpcg::ortho_svd_fallback(Mat X, cplx* tmp, int64_t ldtmp) {
+  const int64_t n = X.cols;
+  if (n == 0) return;
+  if (small) {
+    // everything this solve has recorded so far must have run: read something back (yields to the scheduler)
+    double dummy[4];
+    get(dummy, d_stats, 4 * sizeof(double));
+  }
+  // a rare recovery path, executed synchronously with the direct (immediate-launch) forms even inside a batched solve
+  const bool was_small = small;
+  small = false;
+  try {
+    const cplx one = make_double2(1, 0), zero = make_double2(0, 0);
+    gram({X}, {X}, Ochol, S3, true);
+    LAUNCH(ctx, k_hermitize_upper, nblk(n * n), 256, 0, Ochol, S3, n);
+    heev(Ochol, n);                                                   // V in Ochol (columns), S² in d_w, ascending
+    zgemm(ctx, 0, X.rows, n, n, one, X.p, X.ld, Ochol, S3, zero, tmp, ldtmp);   // T = X V
+    Mat T{tmp, ldtmp, X.rows, n};
+    std::vector<double> nrm(n);
+    col_norms(T, d_norms);
+    get(nrm.data(), d_norms, n * sizeof(double));
+    double smax = 0.0;
+    for (double v : nrm) smax = std::max(smax, v);
+    REQUIRE(std::isfinite(smax) && smax > 0.0, "ortho!: SVD fallback on a zero or non-finite block");
+    std::vector<int64_t> good, bad;
+    for (int64_t c = 0; c < n; ++c) (nrm[c] > std::sqrt(EPS) * smax ? good : bad).push_back(c);
+    scale_cols_inv(T, d_norms);                                       // u_l = X v_l / S_l (the lost ones are rewritten below)
+    for (int64_t c : bad) {
+      Mat tc = T.cols_range(c, 1);
+      rng_counter += 0x100000000ull;
+      randn_col(tc.p, X.rows, rng_counter);
+      for (int pass = 0; pass < 2; ++pass)                            // project against all other columns, twice
+        for (int64_t o = 0; o < n; ++o) {
+          if (o == c || (std::find(bad.begin(), bad.end(), o) != bad.end() && o > c)) continue;
+          Mat to = T.cols_range(o, 1);
+          zgemm(ctx, 2, 1, 1, X.rows, one, to.p, to.ld, tc.p, tc.ld, zero, tmpS, S3);
+          zgemm(ctx, 0, X.rows, 1, 1, make_double2(-1, 0), to.p, to.ld, tmpS, S3, one, tc.p, tc.ld);
+        }
+      col_norms(tc, d_norms);
+      scale_cols_inv(tc, d_norms);
+    }
+    LAUNCH(ctx, k_conj_transpose, nblk(n * n), 256, 0, (const cplx*)Ochol, S3, invR, S3, (int)n);   // V'
+    zgemm(ctx, 0, X.rows, n, n, one, tmp, ldtmp, invR, S3, zero, X.p, X.ld);                          // X = U V'
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  } catch (...) {
+    small = was_small;
+    throw;
+  }
+  small = was_small;
+}
+
+void Lobpcg::prepare(SolveArgs& a) {
+  (void)a;
+  S3 = 3 * M;
+  ldBYX = 2 * M > S3 ? 2 * M : S3;
+  cplx* big = kb->lobpcg_ws.ensure((size_t)11 * N * M);
+  AX = big; R = big + N * M; AR = big + 2 * N * M; P = big + 3 * N * M; AP = big + 4 * N * M;
+  nX = big + 5 * N * M; nAX = big + 6 * N * M; nR = big + 7 * N * M; nP = big + 8 * N * M; nAP = big + 9 * N * M;
+  tmpN = big + 10 * N * M;
+  size_t small_elems = (size_t)S3 * S3 * 4 + (size_t)S3 * M * 2 + (size_t)ldBYX * M + 4 * M + 64;
+  cplx* sm = kb->small_ws.ensure(small_elems);
+  G = sm;
+  Ochol = sm + S3 * S3;
+  invR = sm + 2 * S3 * S3;
+  tmpS = sm + 3 * S3 * S3;
+  cX = sm + 4 * S3 * S3;
+  cP = cX + S3 * M;
+  BYX = cP + S3 * M;
+  d_cdots = BYX + ldBYX * M;
+  double* dsc = kb->scal.ensure(4 * M + 3 * S3 + 64);     // per k-block: batched solves run side by side
+  d_lam = dsc;
+  d_norms = dsc + M;
+  d_meankin = dsc + 2 * M;
+  d_w = dsc + 3 * M;
+  d_stats = dsc + 3 * M + 3 * S3;       // [0..4) matrix stats / Cholesky stats, [4..8) Jacobi stats
+}
+
+void Lobpcg::body(SolveArgs& a) {
+  cplx* Xio = a.X;
+  const double tol = a.tol;
+  const int miniter = a.miniter, maxiter = a.maxiter;
+  int64_t n_conv_check = a.n_conv_check;
   if (n_conv_check <= 0 || n_conv_check > M) n_conv_check = M;
-  use_prec = use_prec && kb->has_kin;
 
   SectionProf prof;
-  prof.on = getenv("DFTK_B200_PROFILE") != nullptr;
+  prof.on = !small && getenv("DFTK_B200_PROFILE") != nullptr;
   prof.aggregate = prof.on && atoi(getenv("DFTK_B200_PROFILE")) == 2;
   prof.st = ctx->stream;
-  Lobpcg L;
-  L.kb = kb;
-  L.ctx = ctx;
-  L.N = N;
-  L.M = M;
-  L.use_prec = use_prec;
-  const int64_t S3 = 3 * M;
-  L.S3 = S3;
-  L.ldBYX = 2 * M > S3 ? 2 * M : S3;
-  // workspaces
-  cplx* big = kb->lobpcg_ws.ensure((size_t)11 * N * M);
-  cplx *AX = big, *R = big + N * M, *AR = big + 2 * N * M, *P = big + 3 * N * M, *AP = big + 4 * N * M,
-       *nX = big + 5 * N * M, *nAX = big + 6 * N * M, *nR = big + 7 * N * M, *nP = big + 8 * N * M,
-       *nAP = big + 9 * N * M;
-  L.tmpN = big + 10 * N * M;
-  size_t small_elems = (size_t)S3 * S3 * 4 + (size_t)S3 * M * 2 + (size_t)L.ldBYX * M + 4 * M + 64;
-  cplx* sm = kb->small_ws.ensure(small_elems);
-  L.G = sm;
-  L.Ochol = sm + S3 * S3;
-  L.invR = sm + 2 * S3 * S3;
-  L.tmpS = sm + 3 * S3 * S3;
-  L.cX = sm + 4 * S3 * S3;
-  L.cP = L.cX + S3 * M;
-  L.BYX = L.cP + S3 * M;
-  L.d_cdots = L.BYX + L.ldBYX * M;
-  double* dsc = ctx->scal.ensure(4 * M + 3 * S3 + 64);
-  L.d_lam = dsc;
-  L.d_norms = dsc + M;
-  L.d_meankin = dsc + 2 * M;
-  L.d_w = dsc + 3 * M;
-  L.d_stats = dsc + 3 * M + 3 * S3;
-  L.small = M <= SMALL_MAX_N && ctx->small_dense != 0;
-  if (L.small) {
-    unsigned* c = (unsigned*)ctx->small_counter.ensure(4);
-    CUDA_CHECK(cudaMemsetAsync(c, 0, 4 * sizeof(int), ctx->stream));   // also recovers from an aborted earlier solve
-    L.d_counter = c;
-  }
 
   Mat X{Xio, N, N, M};
   auto mat = [&](cplx* p) { return Mat{p, N, N, M}; };
   auto applyH = [&](Mat in, Mat out) {
     // A*X: full H apply on a block of columns (mul!(AX, A, X), :379,416)
+    if (in.cols == 0) return;
+    if (small) {
+      newop(OP_APPLYH).u.applyh = ApplyHItem{kb, in.p, out.p, (int)in.cols};
+      return;
+    }
     kb_apply_local_kinetic(kb, in.p, out.p, in.cols, kb->has_V, kb->has_kin, false);
     kb_apply_nonlocal(kb, in.p, out.p, in.cols);
   };
-  const size_t colbytes = (size_t)N * sizeof(cplx);
-  auto copycols = [&](cplx* dst, const cplx* src, int64_t c0, int64_t nc) {
-    if (nc > 0)
-      CUDA_CHECK(cudaMemcpyAsync(dst + N * c0, src + N * c0, colbytes * nc, cudaMemcpyDeviceToDevice, ctx->stream));
-  };
+  auto copycols = [&](cplx* dst, const cplx* src, int64_t c0, int64_t nc) { copy_flat(dst + N * c0, src + N * c0, N * nc); };
 
   std::vector<double> resid_hist((size_t)M * (maxiter + 1), 0.0);
   auto RH = [&](int64_t i, int it) -> double& { return resid_hist[(size_t)it * M + i]; };
 
   // X = ortho!(copy(X)) :370
   prof.begin("ortho(X0)");
-  L.ortho(X, L.tmpN, N);
+  ortho(X, tmpN, N);
+  align();
   prof.begin("H*X");
   int64_t n_matvec = M;
   applyH(X, mat(AX));
   prof.begin("misc");
-  CUDA_CHECK(cudaMemsetAsync(big + N * M, 0, (size_t)4 * N * M * sizeof(cplx), ctx->stream));   // R, AR, P, AP
-  CUDA_CHECK(cudaMemsetAsync(nR, 0, (size_t)3 * N * M * sizeof(cplx), ctx->stream));           // nR, nP, nAP
+  copy_flat(R, nullptr, 4 * N * M);      // R, AR, P, AP
+  copy_flat(nR, nullptr, 3 * N * M);     // nR, nP, nAP
   copycols(nX, Xio, 0, M);
   copycols(nAX, AX, 0, M);
   // λ = compute_λ(X, AX, X)
-  columnwise_dots(ctx, Xio, N, AX, N, N, M, L.d_cdots);
-  columnwise_dots(ctx, Xio, N, Xio, N, N, M, L.d_cdots + M);
-  LAUNCH(ctx, k_compute_lambda, nblk(M), 256, 0, (const cplx*)L.d_cdots, (const cplx*)(L.d_cdots + M),
-         L.d_lam, M);
+  if (small) {
+    newop(OP_LAMBDA).u.lambda = LambdaItem{Xio, AX, N, N, (int)M, d_lam};
+  } else {
+    columnwise_dots(ctx, Xio, N, AX, N, N, M, d_cdots);
+    columnwise_dots(ctx, Xio, N, Xio, N, N, M, d_cdots + M);
+    LAUNCH(ctx, k_compute_lambda, nblk(M), 256, 0, (const cplx*)d_cdots, (const cplx*)(d_cdots + M), d_lam, M);
+  }
 
   int64_t nlocked = 0, a0 = 0;
   int niter = 0;
-  std::vector<double> norms(M), lam_h(M);
+  std::vector<double> norms(M + 8), lam_h(M);
   int64_t ncolsY = 0;
-  bool done = false;
   int final_iter = maxiter;
   while (true) {
     const int64_t Ma = M - a0;
     std::vector<Mat> Y, AY;
     if (niter > 0) {
+      align();
       prof.begin("H*R");
       applyH(mat(R).cols_from(a0), mat(AR).cols_from(a0));
       n_matvec += Ma;
@@ -733,27 +1202,44 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
       ncolsY = (int64_t)Y.size() * Ma;
       // rayleigh_ritz :141-171
       prof.begin("RR gram Y'AY");
-      L.gram(Y, AY, L.G, S3, true);
+      gram(Y, AY, G, S3, true);
       prof.begin("RR heevd");
-      // only the block upper triangle of G is written; heevd reads the upper triangle only
-      L.heevd(L.G, ncolsY);
+      // only the block upper triangle of G is written; the eigensolver reads the upper triangle only
+      heev(G, ncolsY, d_lam + a0, (int)Ma);
       prof.begin("X,AX = Y cX");
       // cX = vectors[:, 1:Ma], λ = values[1:Ma]
-      L.copy2d(Mat{L.cX, S3, ncolsY, Ma}, Mat{L.G, S3, ncolsY, Ma});
-      CUDA_CHECK(cudaMemcpyAsync(L.d_lam + a0, L.d_w, Ma * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-      L.blocks_times(Y, L.cX, S3, Ma, mat(nX).cols_from(a0), 1.0, 0.0);
-      L.blocks_times(AY, L.cX, S3, Ma, mat(nAX).cols_from(a0), 1.0, 0.0);
+      copy2d(Mat{cX, S3, ncolsY, Ma}, Mat{G, S3, ncolsY, Ma});
+      if (!small) CUDA_CHECK(cudaMemcpyAsync(d_lam + a0, d_w, Ma * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      blocks_times(Y, cX, S3, Ma, mat(nX).cols_from(a0), 1.0, 0.0);
+      blocks_times(AY, cX, S3, Ma, mat(nAX).cols_from(a0), 1.0, 0.0);
     }
     prof.begin("residual+precond");
     // residuals :443-445 (+ precondprep! :452-457 fused)
-    LAUNCH(ctx, k_residual, (unsigned)Ma, 256, 0, (const cplx*)(nAX + N * a0), (const cplx*)(nX + N * a0),
-           (const double*)(L.d_lam + a0), nR + N * a0, N, N, use_prec ? (const double*)kb->kin.p : nullptr,
-           L.d_norms, L.d_meankin);
-    L.get(norms.data(), L.d_norms, Ma * sizeof(double));
+    if (small) {
+      newop(OP_RESIDUAL).u.residual = ResidualItem{nAX + N * a0, nX + N * a0, d_lam + a0, nR + N * a0, N, N, (int)Ma,
+                                                   use_prec ? kb->kin.p : nullptr, d_norms, d_meankin};
+      // one read-back: the residual norms and the status of the Jacobi eigensolver of this Rayleigh-Ritz step
+      const size_t span = (size_t)(d_stats - d_norms) + 8;
+      std::vector<double> both(span);
+      get(both.data(), d_norms, span * sizeof(double));
+      std::copy(both.begin(), both.begin() + Ma, norms.begin());
+      if (niter > 0 && both[(d_stats - d_norms) + 4] == 0.0)
+        throw Error(DFTK_B200_ENUM, "rayleigh_ritz: Jacobi eigensolver did not converge");
+    } else {
+      LAUNCH(ctx, k_residual, (unsigned)Ma, 256, 0, (const cplx*)(nAX + N * a0), (const cplx*)(nX + N * a0),
+             (const double*)(d_lam + a0), nR + N * a0, N, N, use_prec ? (const double*)kb->kin.p : nullptr,
+             d_norms, d_meankin);
+      get(norms.data(), d_norms, Ma * sizeof(double));
+    }
     for (int64_t i = 0; i < Ma; ++i) RH(a0 + i, niter) = norms[i];
-    if (use_prec)
-      LAUNCH(ctx, k_precondition, nblk(N * Ma), 256, 0, nR + N * a0, N, N, Ma, (const double*)kb->kin.p,
-             (const double*)L.d_meankin);
+    if (use_prec) {
+      if (small) {
+        newop(OP_PRECOND).u.precond = PrecondItem{nR + N * a0, N, N, (int)Ma, kb->kin.p, d_meankin};
+      } else {
+        LAUNCH(ctx, k_precondition, nblk(N * Ma), 256, 0, nR + N * a0, N, N, Ma, (const double*)kb->kin.p,
+               (const double*)d_meankin);
+      }
+    }
 
     const int64_t prev_nlocked = nlocked;
     if (niter >= miniter) {
@@ -766,7 +1252,6 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
       copycols(Xio, nX, a0, Ma);
       copycols(AX, nAX, a0, Ma);
       final_iter = niter;
-      done = true;
       break;
     }
     const int64_t newly = nlocked - prev_nlocked;
@@ -775,12 +1260,15 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
       const int64_t lenXn = Ma - newly;
       prof.begin("cP ortho");
       // cP = (cX - e)[:, newly:Ma]; ortho!(cP, cX, cX)
-      LAUNCH(ctx, k_make_cP, nblk(ncolsY * lenXn), 256, 0, L.cP, (const cplx*)L.cX, S3, ncolsY, lenXn, newly,
-             lenXn);
-      L.ortho_against(Mat{L.cP, S3, ncolsY, lenXn}, {Mat{L.cX, S3, ncolsY, Ma}}, L.G, S3);
+      if (small) {
+        newop(OP_MAKECP).u.makecp = MakecpItem{cP, cX, S3, (int)ncolsY, (int)lenXn, (int)newly, (int)lenXn};
+      } else {
+        LAUNCH(ctx, k_make_cP, nblk(ncolsY * lenXn), 256, 0, cP, (const cplx*)cX, S3, ncolsY, lenXn, newly, lenXn);
+      }
+      ortho_against(Mat{cP, S3, ncolsY, lenXn}, {Mat{cX, S3, ncolsY, Ma}}, G, S3);
       prof.begin("P,AP = Y cP");
-      L.blocks_times(Y, L.cP, S3, lenXn, mat(nP).cols_from(a0 + newly), 1.0, 0.0);
-      L.blocks_times(AY, L.cP, S3, lenXn, mat(nAP).cols_from(a0 + newly), 1.0, 0.0);
+      blocks_times(Y, cP, S3, lenXn, mat(nP).cols_from(a0 + newly), 1.0, 0.0);
+      blocks_times(AY, cP, S3, lenXn, mat(nAP).cols_from(a0 + newly), 1.0, 0.0);
     }
     prof.begin("copies+check");
     copycols(Xio, nX, a0, Ma);
@@ -788,8 +1276,8 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
     copycols(R, nR, a0, Ma);
     // sanity check :531-535
     {
-      LAUNCH(ctx, k_col_norms, (unsigned)Ma, 256, 0, (const cplx*)(Xio + N * a0), N, N, L.d_norms);
-      L.get(norms.data(), L.d_norms, Ma * sizeof(double));
+      col_norms(Mat{Xio + N * a0, N, N, Ma}, d_norms);
+      get(norms.data(), d_norms, Ma * sizeof(double));
       for (int64_t i = 0; i < Ma; ++i)
         if (!(std::fabs(norms[i] * norms[i] - 1.0) < std::sqrt(EPS)))
           throw Error(DFTK_B200_ENUM, "LOBPCG is badly failing to keep the vectors normalized; this should never happen");
@@ -802,37 +1290,154 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int minit
       Z.push_back(mat(P).cols_from(a0));
     }
     prof.begin("ortho R vs (X,P)");
-    L.ortho_against(mat(R).cols_from(a0), Z, L.tmpN, N);
+    ortho_against(mat(R).cols_from(a0), Z, tmpN, N);
     prof.end();
 
     if (niter >= maxiter) break;
     niter++;
   }
-  (void)done;
   prof.report(niter);
   // final_retval :325-338
-  L.get(lam_h.data(), L.d_lam, M * sizeof(double));
+  get(lam_h.data(), d_lam, M * sizeof(double));
   std::vector<int64_t> perm(M);
   std::iota(perm.begin(), perm.end(), 0);
   bool sorted = std::is_sorted(lam_h.begin(), lam_h.end());
   if (!sorted) {
-    std::stable_sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) { return lam_h[a] < lam_h[b]; });
+    std::stable_sort(perm.begin(), perm.end(), [&](int64_t p, int64_t q) { return lam_h[p] < lam_h[q]; });
     // permute X columns through tmpN
-    for (int64_t c = 0; c < M; ++c)
-      CUDA_CHECK(cudaMemcpyAsync(L.tmpN + N * c, Xio + N * perm[c], colbytes, cudaMemcpyDeviceToDevice, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(Xio, L.tmpN, colbytes * M, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int64_t c = 0; c < M; ++c) copy_flat(tmpN + N * c, Xio + N * perm[c], N);
+    copy_flat(Xio, tmpN, N * M);
   }
   double maxres = 0.0;
   for (int64_t c = 0; c < M; ++c) {
-    lambda_host[c] = lam_h[perm[c]];
-    resid_host[c] = RH(perm[c], final_iter);
-    if (c < n_conv_check) maxres = std::max(maxres, resid_host[c]);
+    a.lambda_host[c] = lam_h[perm[c]];
+    a.resid_host[c] = RH(perm[c], final_iter);
+    if (c < n_conv_check) maxres = std::max(maxres, a.resid_host[c]);
   }
-  *n_iter_out = final_iter;
-  *n_matvec_out = n_matvec;
-  *converged_out = maxres < tol ? 1 : 0;
-  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *a.n_iter = final_iter;
+  *a.n_matvec = n_matvec;
+  *a.converged = maxres < tol ? 1 : 0;
+  if (!small) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+static void init_solver(Lobpcg& L, dftk_b200_kblock* kb, int64_t M, bool use_prec) {
+  dftk_b200_ctx* ctx = kb->grid->ctx;
+  const int64_t N = kb->n_pw;
+  REQUIRE(M >= 1, "lobpcg: n_bands must be >= 1");
+  REQUIRE(N > 3 * M, "The eigenproblem is too small, and the iterative eigensolver will fail; increase "
+                     "the number of degrees of freedom, or use a dense eigensolver.");
+  L.kb = kb;
+  L.ctx = ctx;
+  L.N = N;
+  L.M = M;
+  L.use_prec = use_prec && kb->has_kin;
+  L.small = M <= SMALL_MAX_N && ctx->small_dense != 0;
+}
+
+// All k-blocks of a rank in lockstep (diagonalize_all_kblocks, src/eigen/diag.jl:16-52: independent eigenproblems).
+int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, double tol, int miniter,
+                     int maxiter, int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter,
+                     int64_t* n_matvec, int* converged) {
+  if (n_blocks <= 0) return 0;
+  dftk_b200_ctx* ctx = kbs[0]->grid->ctx;
+  std::vector<Lobpcg> L(n_blocks);
+  std::vector<SolveArgs> A(n_blocks);
+  for (int64_t i = 0; i < n_blocks; ++i) {
+    REQUIRE(kbs[i] && Xs[i], "lobpcg: NULL k-block or orbital pointer");
+    REQUIRE(kbs[i]->grid->ctx == ctx, "lobpcg: all k-blocks of a batch must belong to one context");
+    init_solver(L[i], kbs[i], M, use_prec);
+    A[i] = SolveArgs{Xs[i], tol, miniter, maxiter, n_conv_check, lambda_host + i * M, resid_host + i * M, n_iter + i,
+                     n_matvec + i, converged + i};
+    L[i].rng_counter += (uint64_t)i << 48;
+    L[i].prepare(A[i]);
+  }
+  for (int64_t i = 0; i < n_blocks; ++i)
+    for (int64_t j = 0; j < i; ++j) REQUIRE(kbs[i] != kbs[j], "lobpcg: a k-block appears twice in one batch");
+  if (!L[0].small) {
+    for (int64_t i = 0; i < n_blocks; ++i) L[i].body(A[i]);
+    return 0;
+  }
+  // batched path: one coroutine per k-block, operations merged by BatchExec
+  BatchExec exec(ctx);
+  if (ctx->small_counter.cap < (size_t)std::max<int64_t>(n_blocks, 256)) {
+    unsigned* c = (unsigned*)ctx->small_counter.ensure(std::max<size_t>((size_t)n_blocks, 256));
+    (void)c;
+  }
+  CUDA_CHECK(cudaMemsetAsync(ctx->small_counter.p, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));   // also recovers from an aborted solve
+  std::vector<std::unique_ptr<Coro>> coros;
+  ucontext_t main_uc;
+  ucontext_t* saved_main = g_main_uc;
+  Coro* saved_coro = g_coro;
+  g_main_uc = &main_uc;
+  for (int64_t i = 0; i < n_blocks; ++i) {
+    coros.emplace_back(new Coro());
+    Coro* c = coros.back().get();
+    c->stack_size = (size_t)1 << 20;
+    c->stack.reset(new char[c->stack_size]);       // not value-initialised: pages are touched only as deep as the solve goes
+    Lobpcg* Lp = &L[i];
+    SolveArgs* Ap = &A[i];
+    Lp->co = c;
+    c->body = [Lp, Ap]() { Lp->body(*Ap); };
+    getcontext(&c->uc);
+    c->uc.uc_stack.ss_sp = c->stack.get();
+    c->uc.uc_stack.ss_size = c->stack_size;
+    c->uc.uc_link = nullptr;
+    makecontext(&c->uc, (void (*)())coro_entry, 0);
+  }
+  std::string first_err;
+  int first_code = 0;
+  try {
+    while (true) {
+      bool all_done = true;
+      for (auto& c : coros) {
+        if (c->finished || c->waiting_align) continue;
+        g_coro = c.get();
+        swapcontext(&main_uc, &c->uc);
+        if (c->failed && first_err.empty()) {
+          first_err = c->err;
+          first_code = c->err_code;
+        }
+      }
+      if (!first_err.empty()) break;
+      exec.flush(coros);
+      bool all_waiting = true;
+      for (auto& c : coros) {
+        if (c->finished) continue;
+        all_done = false;
+        if (!c->waiting_align) all_waiting = false;
+      }
+      if (all_done) break;
+      if (all_waiting)
+        for (auto& c : coros) c->waiting_align = false;
+    }
+  } catch (...) {
+    g_main_uc = saved_main;
+    g_coro = saved_coro;
+    cudaStreamSynchronize(ctx->stream);
+    throw;
+  }
+  g_main_uc = saved_main;
+  g_coro = saved_coro;
+  if (!first_err.empty()) {
+    cudaStreamSynchronize(ctx->stream);
+    throw Error(first_code, first_err);
+  }
+  ctx->batch_rounds += exec.rounds;
   return 0;
+}
+
+void lobpcg_set_attributes() {
+  const int big = 200 * 1024;
+  CUDA_CHECK(cudaFuncSetAttribute(kb_heev, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CUDA_CHECK(cudaFuncSetAttribute(kb_btimes, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(kb_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+}
+
+int lobpcg_run(dftk_b200_kblock* kb, cplx* Xio, int64_t M, double tol, int miniter, int maxiter,
+               int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter_out,
+               int64_t* n_matvec_out, int* converged_out) {
+  return lobpcg_run_multi(1, &kb, &Xio, M, tol, miniter, maxiter, n_conv_check, use_prec, lambda_host, resid_host,
+                          n_iter_out, n_matvec_out, converged_out);
 }
 
 }  // namespace dftk

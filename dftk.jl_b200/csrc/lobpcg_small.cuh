@@ -270,8 +270,9 @@ HD void small_chol_cta(const cplx* __restrict__ O, long long ldo, int n, cplx* _
 // eigenvalues) and w the eigenvalues.  As: n*n cplx (shared), V: n*n cplx scratch (global, leading dimension n),
 // rot: 2*(n/2+1) cplx (shared; {c, s} and the phase of each pair), red: SMALL_RED doubles, iwork: 2*(n/2+1) ints (shared).
 // stats[0] = sweeps used (0: no convergence within the cap), stats[1] = final off-diagonal Frobenius norm.
+// lam_out (optional): the lowest n_keep eigenvalues once more, where the caller keeps the Ritz values of its active block.
 HD void small_heev_cta(cplx* __restrict__ G, long long ldg, int n, double* __restrict__ w, cplx* As, cplx* __restrict__ V,
-                       cplx* rot, double* red, int* iwork, double* __restrict__ stats) {
+                       cplx* rot, double* red, int* iwork, double* __restrict__ stats, double* __restrict__ lam_out, int n_keep) {
   const int m = (n + 1) & ~1, half = m / 2;
   int* pp = iwork;
   int* qq = iwork + half;
@@ -385,6 +386,7 @@ HD void small_heev_cta(cplx* __restrict__ G, long long ldg, int n, double* __res
     }
     iwork[i] = rank;     // pp/qq are dead by now (2*half >= n)
     w[rank] = li;
+    if (lam_out && rank < n_keep) lam_out[rank] = li;
   }
   TSYNC();
   TLOOP(e, n * n) {

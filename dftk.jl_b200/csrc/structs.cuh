@@ -41,6 +41,7 @@ struct dftk_b200_kblock {
   dftk::DevBuf<dftk::cplx> P;     // n_pw x n_proj
   std::vector<double> D_host;     // n_proj x n_proj
   dftk::DevBuf<dftk::cplx> Dc;    // complex copy of D on the device (n_proj x n_proj)
+  dftk::DevBuf<dftk::cplx> PD;    // P D (n_pw x n_proj), kept when n_proj is small: Hψ += (P D)(P'ψ) as two batched small products
   dftk::DevBuf<double> V;         // N, pre-scaled by 1/N (fft_norm*ifft_norm)
   bool has_V = false;
   // scratch
@@ -49,6 +50,7 @@ struct dftk_b200_kblock {
   dftk::DevBuf<dftk::cplx> lobpcg_ws; // big LOBPCG workspace
   dftk::DevBuf<dftk::cplx> small_ws;  // small dense LOBPCG workspace
   dftk::DevBuf<double> wts;
+  dftk::DevBuf<double> scal;          // per-block scalars of a LOBPCG solve (several blocks are solved side by side)
 };
 
 namespace dftk {
@@ -100,4 +102,8 @@ void kb_nonlocal_force_rows(dftk_b200_kblock* kb, const cplx* psi, const double*
 int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter, int maxiter,
                int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host,
                int* n_iter, int64_t* n_matvec, int* converged);
+int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, double tol, int miniter,
+                     int maxiter, int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter,
+                     int64_t* n_matvec, int* converged);
+void lobpcg_set_attributes();
 }  // namespace dftk

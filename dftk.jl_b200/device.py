@@ -52,8 +52,17 @@ class Context:
     def sync(self):
         check(self.L.dftk_b200_sync(self.h), self.h)
 
+    def set_stream(self, stream):
+        """Run all work of this context on `stream` (a torch.cuda.Stream, a raw cudaStream_t integer, or None = default)."""
+        raw = 0 if stream is None else getattr(stream, "cuda_stream", stream)
+        check(self.L.dftk_b200_ctx_set_stream(self.h, ctypes.c_void_p(raw)), self.h)
+
     def launch_count(self, reset=False):
         return int(self.L.dftk_b200_launch_count(self.h, 1 if reset else 0))
+
+    def sync_count(self, reset=False):
+        """Scheduler rounds (host synchronisations) of the batched LOBPCG solves."""
+        return int(self.L.dftk_b200_sync_count(self.h, 1 if reset else 0))
 
     def set_option(self, name, value):
         check(self.L.dftk_b200_set_option(self.h, name.encode(), int(value)), self.h)
@@ -94,6 +103,26 @@ class Context:
                 self.h = None
         except Exception:
             pass
+
+
+def lobpcg_multi(kblocks, Xs, tol=1e-6, miniter=1, maxiter=100, n_conv_check=None, prec=True):
+    """dftk_b200_lobpcg_multi: all (k, spin) blocks of a rank in one call.  Xs[i]: (n_bands, n_pw_i) device tensors,
+    updated in place.  Returns one result dict per block (the fields of `KBlock.lobpcg`)."""
+    n = len(kblocks)
+    if n == 0:
+        return []
+    ctx = kblocks[0].ctx
+    nb = Xs[0].shape[0]
+    assert all(x.shape[0] == nb and x.is_contiguous() for x in Xs)
+    kb_arr = (c_vp * n)(*[kb.h.value for kb in kblocks])
+    x_arr = (c_vp * n)(*[x.data_ptr() for x in Xs])
+    lam, res = np.zeros((n, nb)), np.zeros((n, nb))
+    nit, conv, nmv = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int64)
+    check(ctx.L.dftk_b200_lobpcg_multi(n, kb_arr, x_arr, nb, float(tol), int(miniter), int(maxiter),
+                                       nb if n_conv_check is None else int(n_conv_check), int(prec), _ptr(lam), _ptr(res),
+                                       _ptr(nit), _ptr(nmv), _ptr(conv)), ctx.h)
+    return [dict(λ=lam[i].copy(), X=Xs[i], residual_norms=res[i].copy(), n_iter=int(nit[i]), n_matvec=int(nmv[i]),
+                 converged=bool(conv[i])) for i in range(n)]
 
 
 class FFTGrid:

@@ -22,35 +22,82 @@ def lobpcg_hyper(A, X0, *, prec=True, tol=None, maxiter=100, miniter=1, n_conv_c
                            prec=bool(prec))
 
 
+def _lobpcg_hyper_batched(blocks, X0s, *, prec=True, tol=None, maxiter=100, miniter=1, n_conv_check=None):
+    """The same solver for a list of independent Hamiltonian blocks in ONE library call (dftk_b200_lobpcg_multi): the
+    k-blocks of a rank advance in lockstep and share kernel launches and host synchronisations."""
+    from .device import lobpcg_multi
+    if tol is None:
+        tol = 20 * blocks[0].shape[1] * np.finfo(float).eps
+    return lobpcg_multi([b.bind() for b in blocks], X0s, tol=tol, miniter=miniter, maxiter=maxiter,
+                        n_conv_check=n_conv_check, prec=bool(prec))
+
+
+lobpcg_hyper.batched = _lobpcg_hyper_batched
+
+
+def _start_vectors(g, nev, n_Gk, generator):
+    """Guess selection of diag.jl:22-38: truncate, take, or pad with orthogonalised random vectors."""
+    if g.shape[1] != n_Gk:
+        raise ValueError(f"Mismatch in dimension between guess ({g.shape[1]}) and Hamiltonian ({n_Gk})")
+    if g.shape[0] > nev:
+        return g[:nev].clone()
+    if g.shape[0] == nev:
+        return g.clone()
+    extra = torch.view_as_complex(torch.randn(nev - g.shape[0], n_Gk, 2, dtype=torch.float64, device=g.device,
+                                              generator=generator))
+    Q, _ = torch.linalg.qr(torch.cat([g, extra], dim=0).T)
+    return Q.T.contiguous()
+
+
 def diagonalize_all_kblocks(eigensolver, ham, nev_per_kpoint, *, psiguess=None, prec_type="TPA",
                             interpolate_kpoints=True, tol=1e-6, miniter=1, maxiter=100, n_conv_check=None,
                             generator=None):
+    """diag.jl:9-65.  The per-k eigenproblems are independent: an eigensolver that offers `.batched` (lobpcg_hyper does)
+    gets all blocks of this rank in one call.  Without a guess the reference interpolates each k-point's start vectors
+    from the solution of the previous one (diag.jl:39-44), which chains the solves; here the first block of every spin
+    channel is solved on its own and its solution is interpolated to all other blocks of that channel, which are then
+    solved together."""
     basis = ham.basis
-    results = []
-    for ik, kpt in enumerate(basis.kpoints):
-        n_Gk = kpt.n_G
-        if n_Gk < nev_per_kpoint:
-            raise ValueError(f"The size of the plane wave basis is {n_Gk}, and you are asking for "
+    nk = len(basis.kpoints)
+    for kpt in basis.kpoints:
+        if kpt.n_G < nev_per_kpoint:
+            raise ValueError(f"The size of the plane wave basis is {kpt.n_G}, and you are asking for "
                              f"{nev_per_kpoint} eigenvalues. Increase Ecut.")
-        if psiguess is not None:
-            g = psiguess[ik]
-            if g.shape[1] != n_Gk:
-                raise ValueError(f"Mismatch in dimension between guess ({g.shape[1]}) and Hamiltonian ({n_Gk})")
-            if g.shape[0] > nev_per_kpoint:
-                X0 = g[:nev_per_kpoint].clone()
-            elif g.shape[0] == nev_per_kpoint:
-                X0 = g.clone()
-            else:
-                extra = torch.view_as_complex(torch.randn(nev_per_kpoint - g.shape[0], n_Gk, 2, dtype=torch.float64,
-                                                          device=g.device, generator=generator))
-                Q, _ = torch.linalg.qr(torch.cat([g, extra], dim=0).T)
-                X0 = Q.T.contiguous()
-        elif interpolate_kpoints and ik > 0 and basis.kpoints[ik - 1].spin == kpt.spin:
-            X0 = interpolate_kpoint(results[ik - 1]["X"], basis, basis.kpoints[ik - 1], kpt)
+    kw = dict(prec=prec_type is not None, tol=tol, miniter=miniter, maxiter=maxiter, n_conv_check=n_conv_check)
+    batched = getattr(eigensolver, "batched", None)
+    results = [None] * nk
+
+    def solve(idx, guesses):
+        if not idx:
+            return
+        if batched is not None:
+            for i, r in zip(idx, batched([ham[i] for i in idx], guesses, **kw)):
+                results[i] = r
         else:
-            X0 = random_orbitals(basis, kpt, nev_per_kpoint, generator)
-        results.append(eigensolver(ham[ik], X0, prec=prec_type is not None, tol=tol, miniter=miniter,
-                                   maxiter=maxiter, n_conv_check=n_conv_check))
+            for i, g in zip(idx, guesses):
+                results[i] = eigensolver(ham[i], g, **kw)
+
+    if psiguess is not None:
+        solve(list(range(nk)), [_start_vectors(psiguess[ik], nev_per_kpoint, basis.kpoints[ik].n_G, generator)
+                                for ik in range(nk)])
+    elif not interpolate_kpoints or batched is None:
+        for ik, kpt in enumerate(basis.kpoints):      # the reference's chain, one block after the other
+            if interpolate_kpoints and ik > 0 and basis.kpoints[ik - 1].spin == kpt.spin:
+                X0 = interpolate_kpoint(results[ik - 1]["X"], basis, basis.kpoints[ik - 1], kpt)
+            else:
+                X0 = random_orbitals(basis, kpt, nev_per_kpoint, generator)
+            solve([ik], [X0])
+    else:
+        heads = [ik for ik, kpt in enumerate(basis.kpoints) if ik == 0 or basis.kpoints[ik - 1].spin != kpt.spin]
+        solve(heads, [random_orbitals(basis, basis.kpoints[ik], nev_per_kpoint, generator) for ik in heads])
+        rest, guesses = [], []
+        for ik, kpt in enumerate(basis.kpoints):
+            if ik in heads:
+                continue
+            h = max(i for i in heads if i <= ik)
+            rest.append(ik)
+            guesses.append(interpolate_kpoint(results[h]["X"], basis, basis.kpoints[h], kpt))
+        solve(rest, guesses)
     return dict(λ=[r["λ"] for r in results], X=[r["X"] for r in results],
                 residual_norms=[r["residual_norms"] for r in results], n_iter=[r["n_iter"] for r in results],
                 converged=all(r["converged"] for r in results), n_matvec=sum(r["n_matvec"] for r in results))

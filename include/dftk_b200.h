@@ -45,10 +45,16 @@ int dftk_b200_ctx_create_dist(int device, const void* nccl_unique_id, int rank, 
 int dftk_b200_nccl_unique_id(void* out128);
 int dftk_b200_ctx_destroy(dftk_b200_ctx* ctx);
 const char* dftk_b200_last_error(dftk_b200_ctx* ctx); /* ctx may be NULL: last global error */
+/* Every kernel, copy and library call of this context is enqueued on ONE CUDA stream: the legacy default stream after
+ * creation (ordered with the caller's default-stream work, which is what DFTK's GPU path uses), or the `cudaStream_t`
+ * given here (e.g. CUDA.jl's task-local stream, `CUDA.stream().handle`).  Handles created from the context follow. */
+int dftk_b200_ctx_set_stream(dftk_b200_ctx* ctx, void* cuda_stream);
 int dftk_b200_sync(dftk_b200_ctx* ctx);
 int dftk_b200_mem_info(dftk_b200_ctx* ctx, int64_t* free_bytes, int64_t* total_bytes);
 /* number of kernel launches issued by this library on the context since creation / last reset */
 int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset);
+/* number of scheduler rounds (= host synchronisations) of the batched LOBPCG solves since creation / last reset */
+int64_t dftk_b200_sync_count(dftk_b200_ctx* ctx, int reset);
 /* tuning knobs: "gemm_backend" (0 = own DMMA kernels, 1 = cuBLAS, for A/B comparison and peak calibration only,
  * 2 / 3 = experimental INT8-residue emulation of C = A'B with the integer products on CUDA cores / on the tensor cores
  * (tcgen05.mma.kind::i8); groundwork that has not been validated on hardware yet),
@@ -107,6 +113,15 @@ int dftk_b200_lobpcg(dftk_b200_kblock* kb, void* X, int64_t n_bands, double tol,
                      int maxiter, int64_t n_conv_check, int use_tpa_preconditioner,
                      double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec,
                      int* converged);
+
+/* All (k, spin) blocks of a rank at once (diagonalize_all_kblocks, src/eigen/diag.jl:9-65: the per-k eigenproblems are
+ * independent).  Same algorithm and same results per block as dftk_b200_lobpcg; for blocks of <= 32 bands the solves advance
+ * in lockstep and every operation of all blocks is ONE kernel launch (one host synchronisation per round instead of per
+ * block) -- the launch-latency-bound regime of small cells with many k-points.  X[i]: n_pw_i × n_bands (device);
+ * lambda_host / resid_host: n_blocks × n_bands (block-major); n_iter / n_matvec / converged: n_blocks each. */
+int dftk_b200_lobpcg_multi(int64_t n_blocks, dftk_b200_kblock* const* kblocks, void* const* X, int64_t n_bands,
+                           double tol, int miniter, int maxiter, int64_t n_conv_check, int use_tpa_preconditioner,
+                           double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec, int* converged);
 
 /* ---- density (compute_density inner loop, src/densities.jl:32-44):
  *      rho[:,:,:] += sum_n occ_w[n] |IFFT psi_n|² / Ω   with occ_w[n] = occupation·kweight (host) ---- */

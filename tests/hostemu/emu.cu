@@ -321,7 +321,7 @@ int emu_small_heev(double* G, int64_t ldg, int n, double* w, double* stats) {
   std::vector<cplx> As((size_t)n * n), V((size_t)n * n), rot((size_t)n + 4);
   std::vector<double> red(SMALL_RED);
   std::vector<int> iw((size_t)n + 4);
-  small_heev_cta((cplx*)G, ldg, n, w, As.data(), V.data(), rot.data(), red.data(), iw.data(), stats);
+  small_heev_cta((cplx*)G, ldg, n, w, As.data(), V.data(), rot.data(), red.data(), iw.data(), stats, nullptr, 0);
   return 0;
 }
 int emu_small_chol(const double* O, int64_t ldo, int n, double* invR, int64_t ldi, double* stats) {

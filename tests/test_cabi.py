@@ -68,3 +68,31 @@ def test_sm100a_code_and_dmma_in_library(built):
     # register two-pass FFT stage for the 192-point axis of the headline workload is in the library
     elf = subprocess.run(["cuobjdump", "-elf", built], capture_output=True, text=True).stdout
     assert "kr_z_applyILi12ELi16E" in elf
+
+
+def _build_c_smoke(built, tmpdir):
+    exe = os.path.join(tmpdir, "c_smoke")
+    libdir = os.path.dirname(built)
+    subprocess.check_call(["gcc", "-O1", "-Wall", os.path.join(ROOT, "tests", "c_smoke.c"), "-I", os.path.join(ROOT, "include"),
+                           "-L", libdir, "-l:libdftk_b200.so", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    return exe
+
+
+def test_c_program_links_against_the_library(built, tmp_path):
+    """A plain-C consumer (tests/c_smoke.c: no CUDA headers, no Python) compiles against include/dftk_b200.h and links the
+    shared library; without a GPU it must report that and exit with the skip code, not crash."""
+    import torch
+    exe = _build_c_smoke(built, str(tmp_path))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 77 and "no sm_100 device" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_c_program_runs_h_apply_on_gpu(built, tmp_path):
+    exe = _build_c_smoke(built, str(tmp_path))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "max |H psi - (c + kin) psi|" in r.stdout

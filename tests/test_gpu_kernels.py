@@ -121,10 +121,6 @@ def test_band_energies_and_density(si):
     np.testing.assert_allclose(rho.cpu().numpy(), ref, atol=1e-12 * ref.max())
 
 
-@pytest.mark.skipif(os.environ.get("DFTK_B200_EXPERIMENTAL") != "1",
-                    reason="groundwork: the INT8-residue GEMM backends (2: CUDA-core reference pipeline, 3: tcgen05 kind::i8) are "
-                           "validated in host emulation only (tests/test_hostemu_fft.py), not yet on hardware; "
-                           "set DFTK_B200_EXPERIMENTAL=1 to run them")
 @pytest.mark.parametrize("backend", [2, 3])      # 2: integer products on CUDA cores, 3: tcgen05.mma.kind::i8 (i8tc.cu)
 @pytest.mark.parametrize("shape", [(3000, 7, 5), (70000, 20, 9), (140000, 150, 130)])
 def test_i8_emulated_gemm_matches_fp64(shape, backend):
@@ -201,6 +197,71 @@ def test_lobpcg_matches_oracle(si, backend, small):
     finally:
         ctx().set_option("gemm_backend", 0)
         ctx().set_option("small_dense", 1)
+
+
+def test_lobpcg_multi_matches_single_solves_and_oracle():
+    """dftk_b200_lobpcg_multi (all k-blocks of a rank in lockstep, one launch per operation for all of them) against
+    (a) the same blocks solved one at a time and (b) the oracle: same eigenvalues, same iteration counts per block.
+    Blocks of different size (different k -> different n_pw), different convergence speed, partial convergence."""
+    import dftk_b200
+    from dftk_b200.device import lobpcg_multi
+    from gpu_common import silicon_setup, device_blocks, to_dev, ctx
+    from oracle import lobpcg as olob
+    ks = [(0.1, -0.2, 0.3), (0.0, 0.0, 0.0), (0.5, 0.0, 0.0), (0.25, 0.25, -0.125), (0.5, 0.5, 0.5)]
+    m, b, t, rho, ham = silicon_setup(Ecut=12, fft_size=(24, 24, 24), kcoords=ks, kweights=[0.2] * 5)
+    grid, kbs = device_blocks(b, ham)
+    assert len({kb.n_pw for kb in kbs}) > 1
+    rng = np.random.default_rng(11)
+    nb = 7
+    X0 = [rng.standard_normal((blk.kpt.n_G, nb)) + 1j * rng.standard_normal((blk.kpt.n_G, nb)) for blk in ham]
+    c = ctx()
+    c.launch_count(reset=True)
+    single = [kb.lobpcg(to_dev(x.T), tol=1e-8, maxiter=100, n_conv_check=5) for kb, x in zip(kbs, X0)]
+    launches_single = c.launch_count(reset=True)
+    c.sync_count(reset=True)
+    Xs = [to_dev(x.T) for x in X0]
+    multi = lobpcg_multi(kbs, Xs, tol=1e-8, maxiter=100, n_conv_check=5)
+    launches_multi, rounds = c.launch_count(reset=True), c.sync_count()
+    for blk, kb, x0, rs, rm, X in zip(ham, kbs, X0, single, multi, Xs):
+        ref = olob.lobpcg(blk, x0.copy(), olob.PreconditionerTPA(blk.kin), tol=1e-8, maxiter=100, n_conv_check=5)
+        assert rm["converged"] and rs["converged"] and ref["converged"]
+        np.testing.assert_allclose(rm["λ"][:5], ref["λ"][:5], atol=1e-7)
+        np.testing.assert_allclose(rm["λ"], rs["λ"], atol=1e-11)
+        assert rm["n_iter"] == rs["n_iter"] and rm["n_matvec"] == rs["n_matvec"]
+        assert abs(rm["n_iter"] - ref["n_iter"]) <= max(3, ref["n_iter"] // 5)
+        r = kb.apply_h(X) - torch.from_numpy(rm["λ"]).to(X.device)[:, None] * X
+        assert r.norm(dim=1)[:5].max().item() < 1e-8
+        G = X.conj() @ X.T
+        assert (G - torch.eye(nb, dtype=G.dtype, device=G.device)).abs().max().item() < 1e-12
+    # the point of the exercise: far fewer launches than block-by-block, one synchronisation per round for all blocks
+    assert launches_multi < 0.5 * launches_single, (launches_multi, launches_single)
+    assert rounds > 0
+
+
+def test_lobpcg_svd_fallback_recovers_rank_deficient_block(si):
+    """ortho! falls back to an SVD when safe_cholesky gives up (lobpcg_hyper_impl.jl:226-231; the reference recovers
+    through X <- U V').  With finite data five shifted factorisations practically never all fail, so the test forces the
+    branch (option force_svd_fallback) on a start block with an exactly vanishing and a duplicated column: the fallback
+    must hand back an orthonormal block and the solve must converge to the oracle's eigenvalues (both LOBPCG paths)."""
+    from gpu_common import to_dev, ctx
+    from oracle import lobpcg as olob
+    blk, kb = si["blk"], si["kb"]
+    rng = np.random.default_rng(9)
+    X0 = rng.standard_normal((blk.kpt.n_G, 6)) + 1j * rng.standard_normal((blk.kpt.n_G, 6))
+    ref = olob.lobpcg(blk, X0.copy(), olob.PreconditionerTPA(blk.kin), tol=1e-8, maxiter=200)
+    for small in (1, 0):
+        ctx().set_option("small_dense", small)
+        try:
+            Xd = X0.T.copy()
+            Xd[2] = Xd[0]            # duplicated column
+            Xd[3] = 0.0              # an exactly vanishing column
+            ctx().set_option("force_svd_fallback", 2)
+            res = kb.lobpcg(to_dev(Xd), tol=1e-8, maxiter=300)
+            assert res["converged"]
+            np.testing.assert_allclose(res["λ"], ref["λ"], atol=1e-7)
+        finally:
+            ctx().set_option("small_dense", 1)
+            ctx().set_option("force_svd_fallback", 0)
 
 
 @pytest.mark.parametrize("fft_size,Ecut", [((40, 45, 48), 30), ((32, 27, 36), 14), ((33, 40, 21), 10),

@@ -9,12 +9,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("temperature", [0.0, 0.01])
-def test_sharded_scf_matches_single_gpu(temperature):
+@pytest.mark.parametrize("case,temperature", [("si", 0.0), ("si", 0.01), ("fe", 0.01)])
+def test_sharded_scf_matches_single_gpu(case, temperature):
     import torch
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, TEMPERATURE=str(temperature))
+        pytest.skip("needs 2 GPUs (the driver's 1-GPU box skips this; __graft_entry__.smoke() and bench.py --gpus N run the "
+                    "same check whenever more than one GPU is visible)")
+    env = dict(os.environ, TEMPERATURE=str(temperature), CASE=case)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29531",
                         os.path.join(ROOT, "scripts", "multi_gpu_check.py")], capture_output=True, text=True, env=env,
@@ -22,5 +23,6 @@ def test_sharded_scf_matches_single_gpu(temperature):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("MULTIGPU_RESULT ")][-1]
     out = json.loads(line[len("MULTIGPU_RESULT "):])
-    assert out["dE"] < 2e-8 and out["deig"] < 1e-6 and out["drho"] < 1e-7, out
+    assert out["dE"] < 1e-8 * out["n_atoms"] and out["deig"] < 1e-6 and out["drho"] < 1e-7, out
     assert out["nk_local"] < out["nk_total"]
+    assert out["collectives_per_step"] <= 3.5, out      # eigenvalue allgather + density/energy allreduce + converged flag
