@@ -68,7 +68,8 @@ from .hamiltonian import Hamiltonian, DftHamiltonianBlock, energy_hamiltonian, e
 from .eigen import lobpcg_hyper, diagonalize_all_kblocks, random_orbitals
 from .occupation import compute_occupation
 from .densities import compute_density, symmetrize_rho
-from .forces import compute_forces, compute_forces_cart, symmetrize_forces, energy_forces_ewald
+from .forces import (compute_forces, compute_forces_cart, symmetrize_forces, energy_forces_ewald,
+                     energy_forces_ewald_device)
 from .scf import (self_consistent_field, next_density, AdaptiveBands, FixedBands, AdaptiveDiagtol,
-                  ScfConvergenceDensity, ScfConvergenceEnergy, SimpleMixing, KerkerMixing,
+                  ScfConvergenceDensity, ScfConvergenceEnergy, SimpleMixing, KerkerMixing, LdosMixing, compute_ldos,
                   AndersonAcceleration, ScfDefaultCallback)

@@ -42,6 +42,7 @@ SIGNATURES = {
     "dftk_b200_lobpcg": (c_int, [c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp,
                                  P(c_int), P(c_i64), P(c_int)]),
     "dftk_b200_lobpcg_multi": (c_int, [c_i64, c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "dftk_b200_random_orbitals": (c_int, [c_i64, c_vp, c_vp, c_i64, ctypes.c_uint64]),
     "dftk_b200_density_accumulate": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "dftk_b200_allreduce": (c_int, [c_vp, c_vp, c_i64, c_int, c_int]),
     "dftk_b200_allgather": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int]),
@@ -49,7 +50,9 @@ SIGNATURES = {
     "dftk_b200_symmetrize_fourier": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "dftk_b200_local_forces": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "dftk_b200_nonlocal_force_rows": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "dftk_b200_ewald": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp]),
     "dftk_b200_columnwise_dots": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "dftk_b200_tall_gram": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "dftk_b200_zgemm": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp,
                                 c_vp, c_i64]),
 }

@@ -531,6 +531,16 @@ int dftk_b200_lobpcg_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, void*
   API_END(ctx)
 }
 
+int dftk_b200_random_orbitals(int64_t n_blocks, dftk_b200_kblock* const* kbs, void* const* X, int64_t n_bands, uint64_t seed) {
+  dftk_b200_ctx* ctx = (n_blocks > 0 && kbs && kbs[0]) ? kbs[0]->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(n_blocks >= 0 && (n_blocks == 0 || (kbs && X)) && n_bands >= 1, "random_orbitals: bad argument");
+  for (int64_t i = 0; i < n_blocks; ++i)
+    REQUIRE(kbs[i] && X[i] && is_device_ptr(X[i]), "random_orbitals: orbitals must be device memory");
+  random_orbitals_multi(n_blocks, kbs, (cplx* const*)X, n_bands, seed);
+  API_END(ctx)
+}
+
 int dftk_b200_density_accumulate(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host,
                                  int64_t n_bands, double* rho) {
   dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
@@ -619,6 +629,15 @@ int dftk_b200_local_forces(dftk_b200_grid* grid, const void* w, int n_atoms, con
   API_END(ctx)
 }
 
+int dftk_b200_ewald(dftk_b200_ctx* ctx, const double* lattice, int n_atoms, const double* charges, const double* positions,
+                    double eta, const int32_t* glims, const int32_t* rlims, double* energy_host, double* forces_host) {
+  API_BEGIN
+  REQUIRE(ctx && lattice && charges && positions && glims && rlims && n_atoms >= 1, "ewald: bad argument");
+  REQUIRE(!is_device_ptr(lattice) && !is_device_ptr(charges) && !is_device_ptr(positions), "ewald: inputs are host arrays");
+  ewald(ctx, lattice, n_atoms, charges, positions, eta, (const int*)glims, (const int*)rlims, energy_host, forces_host);
+  API_END(ctx)
+}
+
 int dftk_b200_nonlocal_force_rows(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host, int64_t n_bands,
                                   const double* gpk, double* rows_host) {
   dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
@@ -640,6 +659,15 @@ int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, 
   columnwise_dots(ctx, (const cplx*)A, n_rows, (const cplx*)B, n_rows, n_rows, n_cols, o);
   CUDA_CHECK(cudaMemcpyAsync(out_host, o, n_cols * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+int dftk_b200_tall_gram(dftk_b200_ctx* ctx, const void* A, int64_t lda, int64_t n_cols_a, const void* B, int64_t ldb,
+                        int64_t n_cols_b, int64_t n_rows, void* out_host) {
+  API_BEGIN
+  REQUIRE(ctx && A && B && out_host && n_rows >= 1, "tall_gram: bad argument");
+  REQUIRE(is_device_ptr(A) && is_device_ptr(B) && !is_device_ptr(out_host), "tall_gram: A, B on the device, result on the host");
+  tall_gram(ctx, (const cplx*)A, lda, (int)n_cols_a, (const cplx*)B, ldb, (int)n_cols_b, n_rows, (cplx*)out_host);
   API_END(ctx)
 }
 

@@ -112,7 +112,8 @@ const RegKernels* reg_kernels_for(int n) {
 void reg_set_attributes() {
   for (const RegKernels& k : reg_table())
     for (const void* f : {k.sphere_to_x, k.y_backward, k.z_apply, k.z_to_cube, k.z_from_cube, k.z_density,
-                          k.y_forward, k.x_to_sphere})
+                          k.y_forward, k.x_to_sphere, k.m_sphere_to_x, k.m_y_backward, k.m_z_apply, k.m_y_forward,
+                          k.m_x_to_sphere})
       CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
 }
 // must match RegPair<A,B>::L (fft_reg.cuh)
@@ -261,6 +262,76 @@ void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, i
     kb_planes_to_sphere(kb, hpsi + b0 * kb->n_pw, kb->n_pw, nb, 1.0, with_kin ? kb->kin.p : nullptr, p,
                         kb->n_pw, accumulate ? 1 : 0);
   }
+}
+
+bool kb_apply_local_kinetic_multi(int n, dftk_b200_kblock* const* kbs, const cplx* const* psi, cplx* const* hpsi,
+                                  const int* n_bands, const void* (*upload)(void* self, const void* host, size_t bytes), void* self) {
+  if (n <= 0) return true;
+  dftk_b200_grid* g = kbs[0]->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  if (!(g->rx && g->ry && g->rz)) return false;
+  int total = 0, max_cols = 0, max_zc = 0;
+  for (int i = 0; i < n; ++i) {
+    dftk_b200_kblock* kb = kbs[i];
+    if (kb->grid != g || !kb->T.ranges_ok || !kb->has_V || !kb->has_kin || n_bands[i] <= 0) return false;
+    // whole band blocks in one chunk (the small problems this path serves have <= 32 bands)
+    if (band_chunk_for(kb, n_bands[i]) < n_bands[i]) return false;
+    total += n_bands[i];
+    max_cols = std::max(max_cols, kb->T.n_cols);
+    max_zc = std::max(max_zc, kb->T.n_zc);
+  }
+  if (total > 65535) return false;
+  std::vector<FftMultiItem> items(n);
+  std::vector<int2> bandmap(total);
+  int b = 0;
+  for (int i = 0; i < n; ++i) {
+    dftk_b200_kblock* kb = kbs[i];
+    ensure_scratch(kb, n_bands[i]);
+    FftMultiItem& it = items[i];
+    it.T = kb->T;
+    it.psi = psi[i];
+    it.ldpsi = kb->n_pw;
+    it.W1 = kb->W1.p;
+    it.W2 = kb->W2.p;
+    it.V = kb->V.p;
+    it.out = hpsi[i];
+    it.ldout = kb->n_pw;
+    it.kin = kb->kin.p;
+    for (int l = 0; l < n_bands[i]; ++l) bandmap[b++] = make_int2(i, l);
+  }
+  const FftMultiItem* d_items = (const FftMultiItem*)upload(self, items.data(), items.size() * sizeof(FftMultiItem));
+  const int2* d_map = (const int2*)upload(self, bandmap.data(), bandmap.size() * sizeof(int2));
+  {
+    int L = reg_L(g->rx), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twx.p;
+    void* args[] = {&d_items, &d_map, &tw, &L, &Lp};
+    launch_ptr(ctx, g->rx->m_sphere_to_x, dim3(cdiv(max_cols, L), total), L * g->rx->T, reg_smem(g->rx) + 5 * L * sizeof(int), args);
+  }
+  {
+    int L = reg_L(g->ry), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twy.p;
+    void* args[] = {&d_items, &d_map, &tw, &L, &Lp};
+    launch_ptr(ctx, g->ry->m_y_backward, dim3(cdiv(g->nx, L), max_zc, total), L * g->ry->T, reg_smem(g->ry), args);
+  }
+  {
+    int L = reg_L(g->rz), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twz.p;
+    void* args[] = {&d_items, &d_map, &tw, &L, &Lp};
+    launch_ptr(ctx, g->rz->m_z_apply, dim3(cdiv(g->nx, L), g->ny, total), L * g->rz->T, reg_smem(g->rz) / 2, args);
+  }
+  {
+    int L = reg_L(g->ry), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twy.p;
+    void* args[] = {&d_items, &d_map, &tw, &L, &Lp};
+    launch_ptr(ctx, g->ry->m_y_forward, dim3(cdiv(g->nx, L), max_zc, total), L * g->ry->T, reg_smem(g->ry), args);
+  }
+  {
+    int L = reg_L(g->rx), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twx.p;
+    void* args[] = {&d_items, &d_map, &tw, &L, &Lp};
+    launch_ptr(ctx, g->rx->m_x_to_sphere, dim3(cdiv(max_cols, L), total), L * g->rx->T, reg_smem(g->rx) + 5 * L * sizeof(int), args);
+  }
+  return true;
 }
 
 void kb_sphere_to_real(dftk_b200_kblock* kb, const cplx* psi, cplx* cube, int64_t n_bands, double scale) {

@@ -59,6 +59,50 @@ kr_x_to_sphere(SphereTablesX T, const cplx* tw, const cplx* W1, cplx* out, int64
                         Dim3i{(int)blockIdx.x, (int)blockIdx.y, 0});
 }
 
+// ---- the same five H-apply stages for MANY k-blocks in one launch (batched small-matrix LOBPCG, lobpcg.cu): the band
+//      index of the grid runs over the bands of all blocks; `bandmap[band] = {item, band within the item}`.  Blocks of
+//      one basis share the FFT grid (same factor pair, same shared-memory size); only the pruning tables differ.
+template <int A, int B>
+__global__ void __launch_bounds__(REG_MAXT(A, B))
+kr_sphere_to_x_multi(const FftMultiItem* __restrict__ items, const int2* __restrict__ bandmap, const cplx* tw, int L, int Lp) {
+  const int2 bm = bandmap[blockIdx.y];
+  const FftMultiItem& it = items[bm.x];
+  if ((int)blockIdx.x * L >= it.T.n_cols) return;
+  reg_sphere_to_x<A, B>(it.T, tw, it.psi, it.ldpsi, it.W1, L, Lp, (cplx*)dyn_smem_reg, Dim3i{(int)blockIdx.x, bm.y, 0});
+}
+template <int A, int B>
+__global__ void __launch_bounds__(REG_MAXT(A, B))
+kr_y_backward_multi(const FftMultiItem* __restrict__ items, const int2* __restrict__ bandmap, const cplx* tw, int L, int Lp) {
+  const int2 bm = bandmap[blockIdx.z];
+  const FftMultiItem& it = items[bm.x];
+  if ((int)blockIdx.y >= it.T.n_zc) return;
+  reg_y_backward<A, B>(it.T, tw, it.W1, it.W2, L, Lp, (cplx*)dyn_smem_reg, Dim3i{(int)blockIdx.x, (int)blockIdx.y, bm.y});
+}
+template <int A, int B>
+__global__ void __launch_bounds__(REG_MAXT(A, B))
+kr_z_apply_multi(const FftMultiItem* __restrict__ items, const int2* __restrict__ bandmap, const cplx* tw, int L, int Lp) {
+  const int2 bm = bandmap[blockIdx.z];
+  const FftMultiItem& it = items[bm.x];
+  reg_z_apply_potential<A, B>(it.T, tw, it.W2, it.V, L, Lp, (cplx*)dyn_smem_reg, Dim3i{(int)blockIdx.x, (int)blockIdx.y, bm.y});
+}
+template <int A, int B>
+__global__ void __launch_bounds__(REG_MAXT(A, B))
+kr_y_forward_multi(const FftMultiItem* __restrict__ items, const int2* __restrict__ bandmap, const cplx* tw, int L, int Lp) {
+  const int2 bm = bandmap[blockIdx.z];
+  const FftMultiItem& it = items[bm.x];
+  if ((int)blockIdx.y >= it.T.n_zc) return;
+  reg_y_forward<A, B>(it.T, tw, it.W2, it.W1, L, Lp, (cplx*)dyn_smem_reg, Dim3i{(int)blockIdx.x, (int)blockIdx.y, bm.y});
+}
+template <int A, int B>
+__global__ void __launch_bounds__(REG_MAXT(A, B))
+kr_x_to_sphere_multi(const FftMultiItem* __restrict__ items, const int2* __restrict__ bandmap, const cplx* tw, int L, int Lp) {
+  const int2 bm = bandmap[blockIdx.y];
+  const FftMultiItem& it = items[bm.x];
+  if ((int)blockIdx.x * L >= it.T.n_cols) return;
+  reg_x_to_sphere<A, B>(it.T, tw, it.W1, it.out, it.ldout, 1.0, it.kin, it.psi, it.ldpsi, 0, L, Lp, (cplx*)dyn_smem_reg,
+                        Dim3i{(int)blockIdx.x, bm.y, 0});
+}
+
 template <int A, int B>
 static RegKernels make_entry() {
   RegKernels k;
@@ -73,6 +117,11 @@ static RegKernels make_entry() {
   k.z_density = (const void*)kr_z_density<A, B>;
   k.y_forward = (const void*)kr_y_forward<A, B>;
   k.x_to_sphere = (const void*)kr_x_to_sphere<A, B>;
+  k.m_sphere_to_x = (const void*)kr_sphere_to_x_multi<A, B>;
+  k.m_y_backward = (const void*)kr_y_backward_multi<A, B>;
+  k.m_z_apply = (const void*)kr_z_apply_multi<A, B>;
+  k.m_y_forward = (const void*)kr_y_forward_multi<A, B>;
+  k.m_x_to_sphere = (const void*)kr_x_to_sphere_multi<A, B>;
   return k;
 }
 

@@ -387,19 +387,22 @@ struct BatchExec {
 
   // copy `n` descriptors to the device ring; returns the device address.  The ring is recycled at every stream
   // synchronisation (the staging memory of an enqueued copy must stay untouched until the copy has run).
-  template <class T>
-  const T* upload(const std::vector<T>& items) {
-    const size_t bytes = (items.size() * sizeof(T) + 255) & ~(size_t)255;
+  const void* upload_bytes(const void* host, size_t n_bytes) {
+    const size_t bytes = (n_bytes + 255) & ~(size_t)255;
     if (ring_off + bytes > ring_cap) {
       CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
       ring_off = 0;
       REQUIRE(bytes <= ring_cap, "batched LOBPCG: descriptor ring too small");
     }
-    memcpy(ring_h + ring_off, items.data(), items.size() * sizeof(T));
+    memcpy(ring_h + ring_off, host, n_bytes);
     char* d = ctx->batch_ring.p + ring_off;
-    CUDA_CHECK(cudaMemcpyAsync(d, ring_h + ring_off, items.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(d, ring_h + ring_off, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
     ring_off += bytes;
-    return (const T*)d;
+    return d;
+  }
+  template <class T>
+  const T* upload(const std::vector<T>& items) {
+    return (const T*)upload_bytes(items.data(), items.size() * sizeof(T));
   }
   template <class T, class F>
   std::vector<T> collect(const std::vector<Op*>& ops, F get) {
@@ -556,10 +559,28 @@ struct BatchExec {
         // products over all k-blocks of the round (projector counts of the small configurations are <= 20)
         std::vector<GramItem> g;
         std::vector<BtimesItem> b;
+        {
+          // local + kinetic part of all k-blocks in five launches when they share the grid's register FFT engine
+          std::vector<dftk_b200_kblock*> kbs;
+          std::vector<const cplx*> in;
+          std::vector<cplx*> out;
+          std::vector<int> nb;
+          for (Op* o : ops) {
+            const ApplyHItem& a = o->u.applyh;
+            kbs.push_back(a.kb); in.push_back(a.in); out.push_back(a.out); nb.push_back(a.ncols);
+          }
+          auto up = [](void* self, const void* host, size_t bytes) -> const void* {
+            return ((BatchExec*)self)->upload_bytes(host, bytes);
+          };
+          if (!kb_apply_local_kinetic_multi((int)kbs.size(), kbs.data(), in.data(), out.data(), nb.data(), up, this))
+            for (Op* o : ops) {
+              const ApplyHItem& a = o->u.applyh;
+              kb_apply_local_kinetic(a.kb, a.in, a.out, a.ncols, a.kb->has_V, a.kb->has_kin, false);
+            }
+        }
         for (Op* o : ops) {
           const ApplyHItem& a = o->u.applyh;
           dftk_b200_kblock* kb = a.kb;
-          kb_apply_local_kinetic(kb, a.in, a.out, a.ncols, kb->has_V, kb->has_kin, false);
           if (kb->n_proj == 0) continue;
           if (kb->n_proj > SMALL_MAX_COLS || a.ncols > SMALL_MAX_N || !kb->PD.p) {
             kb_apply_nonlocal(kb, a.in, a.out, a.ncols);
@@ -1320,49 +1341,13 @@ void Lobpcg::body(SolveArgs& a) {
   if (!small) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
-static void init_solver(Lobpcg& L, dftk_b200_kblock* kb, int64_t M, bool use_prec) {
-  dftk_b200_ctx* ctx = kb->grid->ctx;
-  const int64_t N = kb->n_pw;
-  REQUIRE(M >= 1, "lobpcg: n_bands must be >= 1");
-  REQUIRE(N > 3 * M, "The eigenproblem is too small, and the iterative eigensolver will fail; increase "
-                     "the number of degrees of freedom, or use a dense eigensolver.");
-  L.kb = kb;
-  L.ctx = ctx;
-  L.N = N;
-  L.M = M;
-  L.use_prec = use_prec && kb->has_kin;
-  L.small = M <= SMALL_MAX_N && ctx->small_dense != 0;
-}
-
-// All k-blocks of a rank in lockstep (diagonalize_all_kblocks, src/eigen/diag.jl:16-52: independent eigenproblems).
-int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, double tol, int miniter,
-                     int maxiter, int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter,
-                     int64_t* n_matvec, int* converged) {
-  if (n_blocks <= 0) return 0;
-  dftk_b200_ctx* ctx = kbs[0]->grid->ctx;
-  std::vector<Lobpcg> L(n_blocks);
-  std::vector<SolveArgs> A(n_blocks);
-  for (int64_t i = 0; i < n_blocks; ++i) {
-    REQUIRE(kbs[i] && Xs[i], "lobpcg: NULL k-block or orbital pointer");
-    REQUIRE(kbs[i]->grid->ctx == ctx, "lobpcg: all k-blocks of a batch must belong to one context");
-    init_solver(L[i], kbs[i], M, use_prec);
-    A[i] = SolveArgs{Xs[i], tol, miniter, maxiter, n_conv_check, lambda_host + i * M, resid_host + i * M, n_iter + i,
-                     n_matvec + i, converged + i};
-    L[i].rng_counter += (uint64_t)i << 48;
-    L[i].prepare(A[i]);
-  }
-  for (int64_t i = 0; i < n_blocks; ++i)
-    for (int64_t j = 0; j < i; ++j) REQUIRE(kbs[i] != kbs[j], "lobpcg: a k-block appears twice in one batch");
-  if (!L[0].small) {
-    for (int64_t i = 0; i < n_blocks; ++i) L[i].body(A[i]);
-    return 0;
-  }
-  // batched path: one coroutine per k-block, operations merged by BatchExec
+// Batched execution: one coroutine per k-block runs `bodies[i]` (which records operations on L[i].co); BatchExec merges
+// the recorded operations of all blocks into shared launches, one stream synchronisation per round.
+static void run_batched(dftk_b200_ctx* ctx, std::vector<Lobpcg>& L, std::vector<std::function<void()>>& bodies) {
+  const int64_t n_blocks = (int64_t)L.size();
   BatchExec exec(ctx);
-  if (ctx->small_counter.cap < (size_t)std::max<int64_t>(n_blocks, 256)) {
-    unsigned* c = (unsigned*)ctx->small_counter.ensure(std::max<size_t>((size_t)n_blocks, 256));
-    (void)c;
-  }
+  if (ctx->small_counter.cap < (size_t)std::max<int64_t>(n_blocks, 256))
+    ctx->small_counter.ensure(std::max<size_t>((size_t)n_blocks, 256));
   CUDA_CHECK(cudaMemsetAsync(ctx->small_counter.p, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));   // also recovers from an aborted solve
   std::vector<std::unique_ptr<Coro>> coros;
   ucontext_t main_uc;
@@ -1374,10 +1359,8 @@ int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const
     Coro* c = coros.back().get();
     c->stack_size = (size_t)1 << 20;
     c->stack.reset(new char[c->stack_size]);       // not value-initialised: pages are touched only as deep as the solve goes
-    Lobpcg* Lp = &L[i];
-    SolveArgs* Ap = &A[i];
-    Lp->co = c;
-    c->body = [Lp, Ap]() { Lp->body(*Ap); };
+    L[i].co = c;
+    c->body = bodies[i];
     getcontext(&c->uc);
     c->uc.uc_stack.ss_sp = c->stack.get();
     c->uc.uc_stack.ss_size = c->stack_size;
@@ -1418,12 +1401,116 @@ int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const
   }
   g_main_uc = saved_main;
   g_coro = saved_coro;
+  for (auto& l : L) l.co = nullptr;
   if (!first_err.empty()) {
     cudaStreamSynchronize(ctx->stream);
     throw Error(first_code, first_err);
   }
   ctx->batch_rounds += exec.rounds;
+}
+
+static void init_solver(Lobpcg& L, dftk_b200_kblock* kb, int64_t M, bool use_prec) {
+  dftk_b200_ctx* ctx = kb->grid->ctx;
+  const int64_t N = kb->n_pw;
+  REQUIRE(M >= 1, "lobpcg: n_bands must be >= 1");
+  REQUIRE(N > 3 * M, "The eigenproblem is too small, and the iterative eigensolver will fail; increase "
+                     "the number of degrees of freedom, or use a dense eigensolver.");
+  L.kb = kb;
+  L.ctx = ctx;
+  L.N = N;
+  L.M = M;
+  L.use_prec = use_prec && kb->has_kin;
+  L.small = M <= SMALL_MAX_N && ctx->small_dense != 0;
+}
+
+// All k-blocks of a rank in lockstep (diagonalize_all_kblocks, src/eigen/diag.jl:16-52: independent eigenproblems).
+int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, double tol, int miniter,
+                     int maxiter, int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter,
+                     int64_t* n_matvec, int* converged) {
+  if (n_blocks <= 0) return 0;
+  dftk_b200_ctx* ctx = kbs[0]->grid->ctx;
+  std::vector<Lobpcg> L(n_blocks);
+  std::vector<SolveArgs> A(n_blocks);
+  for (int64_t i = 0; i < n_blocks; ++i) {
+    REQUIRE(kbs[i] && Xs[i], "lobpcg: NULL k-block or orbital pointer");
+    REQUIRE(kbs[i]->grid->ctx == ctx, "lobpcg: all k-blocks of a batch must belong to one context");
+    init_solver(L[i], kbs[i], M, use_prec);
+    A[i] = SolveArgs{Xs[i], tol, miniter, maxiter, n_conv_check, lambda_host + i * M, resid_host + i * M, n_iter + i,
+                     n_matvec + i, converged + i};
+    L[i].prepare(A[i]);
+  }
+  for (int64_t i = 0; i < n_blocks; ++i)
+    for (int64_t j = 0; j < i; ++j) REQUIRE(kbs[i] != kbs[j], "lobpcg: a k-block appears twice in one batch");
+  if (!L[0].small) {
+    for (int64_t i = 0; i < n_blocks; ++i) L[i].body(A[i]);
+    return 0;
+  }
+  std::vector<std::function<void()>> bodies;
+  for (int64_t i = 0; i < n_blocks; ++i) {
+    Lobpcg* Lp = &L[i];
+    SolveArgs* Ap = &A[i];
+    bodies.push_back([Lp, Ap]() { Lp->body(*Ap); });
+  }
+  run_batched(ctx, L, bodies);
   return 0;
+}
+
+// random_orbitals (src/common/orbitals.jl:82-87: ortho_qr(randn)) for several k-blocks at once: counter-based normal
+// numbers, then the solver's own ortho! (Cholesky-QR with its retries) -- same span, orthonormal to 2 eps.
+void random_orbitals_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, uint64_t seed) {
+  if (n_blocks <= 0) return;
+  dftk_b200_ctx* ctx = kbs[0]->grid->ctx;
+  std::vector<Lobpcg> L(n_blocks);
+  std::vector<SolveArgs> A(n_blocks);
+  for (int64_t i = 0; i < n_blocks; ++i) {
+    REQUIRE(kbs[i] && Xs[i] && kbs[i]->grid->ctx == ctx, "random_orbitals: bad k-block / orbital pointer");
+    init_solver(L[i], kbs[i], M, false);
+    A[i] = SolveArgs{Xs[i], 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    L[i].prepare(A[i]);
+    const uint64_t s = seed * 0x9E3779B97F4A7C15ull + ((uint64_t)i << 40);
+    for (int64_t c = 0; c < M; ++c)
+      LAUNCH(ctx, k_randn_col, nblk(L[i].N), 256, 0, Xs[i] + L[i].N * c, L[i].N, s + ((uint64_t)c << 24) * 2654435761ull);
+  }
+  if (!L[0].small) {
+    for (int64_t i = 0; i < n_blocks; ++i) L[i].ortho(Mat{Xs[i], L[i].N, L[i].N, M}, L[i].tmpN, L[i].N);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  std::vector<std::function<void()>> bodies;
+  for (int64_t i = 0; i < n_blocks; ++i) {
+    Lobpcg* Lp = &L[i];
+    cplx* X = Xs[i];
+    bodies.push_back([Lp, X, M]() { Lp->ortho(Mat{X, Lp->N, Lp->N, M}, Lp->tmpN, Lp->N); });
+  }
+  run_batched(ctx, L, bodies);
+}
+
+// C (nA x nB, host, column-major) = A' B for tall column-major blocks (n_rows >> nA, nB <= SMALL_MAX_COLS): one fused launch
+// (CTA partials + last-CTA reduction, lobpcg_small.cuh).  Used by the host driver for the history dot products of Anderson
+// mixing (src/scf/anderson.jl:81-130) instead of a QR factorisation of the N_fft x m history matrix.
+void tall_gram(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int nA, const cplx* B, int64_t ldb, int nB, int64_t n_rows,
+               cplx* out_host) {
+  REQUIRE(nA >= 1 && nB >= 1 && nA <= SMALL_MAX_COLS && nB <= SMALL_MAX_COLS, "tall_gram: 1 <= columns <= 96");
+  BatchExec exec(ctx);
+  if (ctx->small_counter.cap < 256) {
+    ctx->small_counter.ensure(256);
+    CUDA_CHECK(cudaMemsetAsync(ctx->small_counter.p, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));
+  }
+  cplx* C = (cplx*)ctx->batch_gather.p;       // >= 96 x 96 complex fit the gather buffer
+  GramItem g{};
+  g.A.n = g.B.n = 1;
+  g.A.p[0] = A; g.A.ld[0] = lda; g.A.cols[0] = nA;
+  g.B.p[0] = B; g.B.ld[0] = ldb; g.B.cols[0] = nB;
+  for (int q = 1; q < 4; ++q) { g.A.start[q] = nA; g.B.start[q] = nB; }
+  g.n_rows = n_rows;
+  BatchExec::small_gram_geometry(ctx, n_rows, &g.n_ctas, &g.rows_per_cta);
+  g.upper_only = 0;
+  g.C = C;
+  g.ldc = nA;
+  std::vector<GramItem> v{g};
+  exec.gram_batch(v);
+  CUDA_CHECK(cudaMemcpyAsync(out_host, C, (size_t)nA * nB * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
 void lobpcg_set_attributes() {

@@ -10,6 +10,18 @@ struct SphereTablesX;
 struct RegKernels {
   int A, B, T;
   const void *sphere_to_x, *y_backward, *z_apply, *z_to_cube, *z_from_cube, *z_density, *y_forward, *x_to_sphere;
+  const void *m_sphere_to_x, *m_y_backward, *m_z_apply, *m_y_forward, *m_x_to_sphere;   // many k-blocks per launch
+};
+// one k-block's share of a batched H-apply launch (local + kinetic part)
+struct FftMultiItem {
+  SphereTablesX T;
+  const cplx* psi;
+  long long ldpsi;
+  cplx *W1, *W2;
+  const double* V;
+  cplx* out;
+  long long ldout;
+  const double* kin;
 };
 const RegKernels* reg_kernels_for(int n);   // nullptr: use the generic Stockham engine
 void reg_set_attributes();
@@ -62,6 +74,10 @@ void kb_planes_to_sphere(dftk_b200_kblock* kb, cplx* out, int64_t ldout, int nb,
                          const double* kin, const cplx* psi, int64_t ldpsi, int accumulate);
 void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_t n_bands,
                             bool with_local, bool with_kin, bool accumulate);
+// the same for several k-blocks of ONE grid in five launches in total; returns false (nothing done) when the blocks do
+// not qualify (different grids, generic FFT engine, missing potential / kinetic term): the caller then loops
+bool kb_apply_local_kinetic_multi(int n, dftk_b200_kblock* const* kbs, const cplx* const* psi, cplx* const* hpsi,
+                                  const int* n_bands, const void* (*upload)(void* self, const void* host, size_t bytes), void* self);
 void kb_sphere_to_real(dftk_b200_kblock* kb, const cplx* psi, cplx* cube, int64_t n_bands, double scale);
 void kb_real_to_sphere(dftk_b200_kblock* kb, const cplx* cube, cplx* out, int64_t n_bands, double scale);
 void kb_density_accumulate(dftk_b200_kblock* kb, const cplx* psi, const double* occ_w_host,
@@ -98,6 +114,8 @@ void i8tc_set_attributes();
 void local_forces(dftk_b200_grid* g, const cplx* w, int n_atoms, const double* pos_host, double* out_host);
 void kb_nonlocal_force_rows(dftk_b200_kblock* kb, const cplx* psi, const double* occ_w_host, int64_t n_bands,
                             const double* gpk, double* out_host);
+void ewald(dftk_b200_ctx* ctx, const double* lattice_colmajor, int n_atoms, const double* charges, const double* positions,
+           double eta, const int* glims, const int* rlims, double* energy_host, double* forces_host);
 // lobpcg.cu
 int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter, int maxiter,
                int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host,
@@ -105,5 +123,8 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter
 int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, double tol, int miniter,
                      int maxiter, int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter,
                      int64_t* n_matvec, int* converged);
+void random_orbitals_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, uint64_t seed);
+void tall_gram(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int nA, const cplx* B, int64_t ldb, int nB, int64_t n_rows,
+               cplx* out_host);
 void lobpcg_set_attributes();
 }  // namespace dftk

@@ -82,6 +82,15 @@ class Context:
         check(self.L.dftk_b200_allgather(self.h, _ptr(send), _ptr(recv), send.numel(), dt), self.h)
         return recv
 
+    def real_gram(self, A, B):
+        """A B^T for real (n_a, n) / (n_b, n) float64 device tensors with even n (rows = vectors): one fused launch
+        (dftk_b200_tall_gram on the complex-pair view; the real part is the real Gram matrix).  Returns a host array."""
+        n = A.shape[1]
+        assert n % 2 == 0 and B.shape[1] == n and A.is_contiguous() and B.is_contiguous()
+        out = np.zeros((B.shape[0], A.shape[0]), dtype=np.complex128)           # column-major n_a x n_b
+        check(self.L.dftk_b200_tall_gram(self.h, _ptr(A), n // 2, A.shape[0], _ptr(B), n // 2, B.shape[0], n // 2, _ptr(out)), self.h)
+        return np.ascontiguousarray(out.real.T)
+
     def zgemm(self, transA, A, B, C, alpha=1.0, beta=0.0):
         """C = alpha op(A) B + beta C on column-major data: tensors are (cols, rows) C-contiguous."""
         al = np.array([np.real(alpha), np.imag(alpha)], dtype=np.float64)
@@ -123,6 +132,19 @@ def lobpcg_multi(kblocks, Xs, tol=1e-6, miniter=1, maxiter=100, n_conv_check=Non
                                        _ptr(nit), _ptr(nmv), _ptr(conv)), ctx.h)
     return [dict(λ=lam[i].copy(), X=Xs[i], residual_norms=res[i].copy(), n_iter=int(nit[i]), n_matvec=int(nmv[i]),
                  converged=bool(conv[i])) for i in range(n)]
+
+
+def random_orbitals_multi(kblocks, n_bands, seed):
+    """dftk_b200_random_orbitals: orthonormal random start vectors (n_bands, n_pw_i) for a list of k-blocks."""
+    n = len(kblocks)
+    if n == 0:
+        return []
+    ctx = kblocks[0].ctx
+    Xs = [kb._new(n_bands) for kb in kblocks]
+    kb_arr = (c_vp * n)(*[kb.h.value for kb in kblocks])
+    x_arr = (c_vp * n)(*[x.data_ptr() for x in Xs])
+    check(ctx.L.dftk_b200_random_orbitals(n, kb_arr, x_arr, int(n_bands), ctypes.c_uint64(int(seed) & (2 ** 64 - 1))), ctx.h)
+    return Xs
 
 
 class FFTGrid:

@@ -1,16 +1,24 @@
 """lobpcg_hyper / diagonalize_all_kblocks (mirror of src/eigen/diag.jl:9-65 and
 src/eigen/diag_lobpcg_hyper.jl:5-18).  The eigensolver itself runs inside libdftk_b200
 (dftk_b200_lobpcg); this file only chooses start vectors and packs results like the reference."""
+import math
 import numpy as np
 import torch
 
 
+def _draw_seed(generator):
+    """One 63-bit seed from the SCF's torch generator (deterministic per rank and call order)."""
+    if generator is None:
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+    return int(torch.randint(0, 2 ** 62, (1,), device=generator.device, generator=generator).item())
+
+
 def random_orbitals(basis, kpt, howmany, generator=None):
-    """orbitals.jl:82-87: randn + QR (on the device)."""
-    dev = kpt.mapping.device
-    A = torch.view_as_complex(torch.randn(kpt.n_G, howmany, 2, dtype=torch.float64, device=dev, generator=generator))
-    Q, _ = torch.linalg.qr(A)
-    return Q[:, :howmany].T.contiguous()      # stored (n_bands, n_G)
+    """orbitals.jl:82-87 (ortho_qr(randn)): filled and orthonormalised by libdftk_b200 (counter-based normal numbers +
+    the eigensolver's Cholesky-QR ortho!), stored (n_bands, n_G)."""
+    from .device import random_orbitals_multi
+    ik = next(i for i, k in enumerate(basis.kpoints) if k is kpt)
+    return random_orbitals_multi([basis.kblocks[ik]], howmany, _draw_seed(generator))[0]
 
 
 def lobpcg_hyper(A, X0, *, prec=True, tol=None, maxiter=100, miniter=1, n_conv_check=None):
@@ -43,10 +51,10 @@ def _start_vectors(g, nev, n_Gk, generator):
         return g[:nev].clone()
     if g.shape[0] == nev:
         return g.clone()
+    # the solver starts with ortho!(X0) (lobpcg_hyper_impl.jl:370): the padded block only has to be full rank
     extra = torch.view_as_complex(torch.randn(nev - g.shape[0], n_Gk, 2, dtype=torch.float64, device=g.device,
                                               generator=generator))
-    Q, _ = torch.linalg.qr(torch.cat([g, extra], dim=0).T)
-    return Q.T.contiguous()
+    return torch.cat([g, extra / math.sqrt(n_Gk)], dim=0).contiguous()
 
 
 def diagonalize_all_kblocks(eigensolver, ham, nev_per_kpoint, *, psiguess=None, prec_type="TPA",
@@ -88,8 +96,9 @@ def diagonalize_all_kblocks(eigensolver, ham, nev_per_kpoint, *, psiguess=None, 
                 X0 = random_orbitals(basis, kpt, nev_per_kpoint, generator)
             solve([ik], [X0])
     else:
+        from .device import random_orbitals_multi
         heads = [ik for ik, kpt in enumerate(basis.kpoints) if ik == 0 or basis.kpoints[ik - 1].spin != kpt.spin]
-        solve(heads, [random_orbitals(basis, basis.kpoints[ik], nev_per_kpoint, generator) for ik in heads])
+        solve(heads, random_orbitals_multi([basis.kblocks[ik] for ik in heads], nev_per_kpoint, _draw_seed(generator)))
         rest, guesses = [], []
         for ik, kpt in enumerate(basis.kpoints):
             if ik in heads:
@@ -115,5 +124,5 @@ def interpolate_kpoint(X_in, basis, kpt_in, kpt_out):
     out = torch.zeros((X_in.shape[0], kpt_out.n_G), dtype=X_in.dtype, device=dev)
     ok = src >= 0
     out[:, ok] = X_in[:, src[ok]]
-    Q, _ = torch.linalg.qr(out.T)
-    return Q.T.contiguous()
+    # the reference orthonormalises here (ortho_qr); our eigensolver starts with ortho!(X0) anyway (same span)
+    return out

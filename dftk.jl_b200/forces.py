@@ -69,8 +69,37 @@ def forces_nonlocal(basis, psi, occupation):
     return symmetrize_forces(basis, [F[i] for i in range(F.shape[0])])
 
 
+def ewald_parameters(lattice, positions, eta=None):
+    """η and the summation limits of ewald.jl:86-104."""
+    lattice = np.asarray(lattice, dtype=float)
+    pos = np.array([np.asarray(p, dtype=float) for p in positions])
+    recip = 2 * math.pi * np.linalg.inv(lattice.T)
+    if eta is None:
+        eta = math.sqrt(math.sqrt(1.69 * np.linalg.norm(recip / (2 * math.pi)) / np.linalg.norm(lattice))) / 2
+    max_exp = -math.log(np.finfo(float).eps) + 5
+    Glims = estimate_integer_lattice_bounds(recip, math.sqrt(max_exp) * 2 * eta)
+    poslims = [float(np.max(pos[:, i][:, None] - pos[:, i][None, :])) for i in range(3)]
+    Rlims = estimate_integer_lattice_bounds(lattice, math.sqrt(max_exp) / eta, poslims)
+    return eta, Glims, Rlims
+
+
+def energy_forces_ewald_device(ctx, lattice, charges, positions, eta=None):
+    """energy_forces_ewald (ewald.jl:64-168, q = 0) on the device: the O(n_atoms² n_R) real-space sum and the O(n_atoms n_G)
+    reciprocal sum are one kernel each (dftk_b200_ewald); η and the limits are the host's."""
+    eta, Glims, Rlims = ewald_parameters(lattice, positions, eta)
+    n = len(positions)
+    lat = np.asfortranarray(np.asarray(lattice, dtype=np.float64))
+    ch = np.ascontiguousarray(charges, dtype=np.float64)
+    pos = np.ascontiguousarray(np.array([np.asarray(p, dtype=np.float64) for p in positions]))
+    gl, rl = np.array(Glims, dtype=np.int32), np.array(Rlims, dtype=np.int32)
+    e, f = np.zeros(1), np.zeros((n, 3))
+    check(ctx.L.dftk_b200_ewald(ctx.h, _ptr(lat), n, _ptr(ch), _ptr(pos), float(eta), _ptr(gl), _ptr(rl), _ptr(e), _ptr(f)), ctx.h)
+    return float(e[0]), [f[i].copy() for i in range(n)]
+
+
 def energy_forces_ewald(lattice, charges, positions, eta=None):
-    """ewald.jl:64-168 for q = 0 (energy as terms.energy_ewald, plus the forces)."""
+    """ewald.jl:64-168 for q = 0 (energy as terms.energy_ewald, plus the forces): vectorised NumPy on the host -- the form the
+    CPU-only unit tests compare with the oracle; the product's terms use `energy_forces_ewald_device`."""
     lattice = np.asarray(lattice, dtype=float)
     charges = np.asarray(charges, dtype=float)
     pos = np.array([np.asarray(p, dtype=float) for p in positions])
@@ -160,7 +189,8 @@ def compute_forces(basis_or_scfres, psi=None, occupation=None, *, rho=None, per_
             if f is not None:
                 parts[name] = f
         elif name == "Ewald":
-            parts[name] = energy_forces_ewald(model.lattice, [a.charge_ionic() for a in model.atoms], model.positions)[1]
+            parts[name] = energy_forces_ewald_device(basis.architecture.ctx, model.lattice, [a.charge_ionic() for a in model.atoms],
+                                                     model.positions)[1]
     total = [sum((p[i] for p in parts.values()), np.zeros(3)) for i in range(len(model.positions))]
     return (total, parts) if per_term else total
 

@@ -112,17 +112,138 @@ class KerkerMixing:
         return torch.stack([(dtot + spin) / 2, (dtot - spin) / 2])
 
 
-class AndersonAcceleration:
-    """anderson.jl:42-130, history kept on the device."""
+class LdosMixing:
+    """LdosMixing = χ0Mixing([LdosModel()], RPA = true), the reference's default mixing (self_consistent_field.jl:177;
+    mixing.jl:205-292, chi0models.jl:20-41): solve (1 - χ0 v_c)^† δρ = δF by GMRES with
+    χ0(r, r') = -D_loc(r) δ(r, r') + D_loc(r) D_loc(r') / D, the local density of states from one more density pass with
+    the weights -f'((ε - εF)/T_mix)/T_mix (compute_ldos, dos.jl:43-65; Gaussian smearing at T_mix = max(T, min(0.1, 100 T))).
+    Degenerates to simple mixing at T = 0.  Everything stays on the device: the LDOS is a `compute_density` call (batched
+    FFT pipeline + NCCL allreduce + symmetrisation), the Hartree kernel two cube FFTs, the Krylov dot products one fused
+    Gram launch per Arnoldi step."""
 
-    def __init__(self, m=10, maxcond=1e6, errorfactor=1e5):
-        self.m, self.maxcond, self.errorfactor = m, maxcond, errorfactor
+    def __init__(self, rtol=0.01, krylovdim=30, maxiter=100, temperature=None):
+        self.rtol, self.krylovdim, self.maxiter, self.temperature = rtol, krylovdim, maxiter, temperature
+        self.last = None
+
+    def mix_density(self, basis, dF, *, psi=None, eigenvalues=None, eF=None, **kw):
+        m = basis.model
+        Tm = self.temperature if self.temperature is not None else max(m.temperature, min(0.1, 100 * m.temperature))
+        if Tm == 0 or psi is None or eigenvalues is None or eF is None:
+            return dF
+        ldos = compute_ldos(basis, eF, eigenvalues, psi, temperature=Tm)
+        if float(ldos.abs().max()) < math.sqrt(np.finfo(float).eps):
+            return dF
+        tdos = float(ldos.sum()) * basis.dvol
+        hartree = basis.term("Hartree")
+        green = hartree.poisson_green_coeffs if hartree is not None else None
+        shape = dF.shape
+
+        def adjoint(d):          # ε^† δF = δF - χ0 (v_c δF), both DC components removed (mixing.jl:268-278)
+            d = d.reshape(shape)
+            if green is not None:
+                dV = basis.irfft(green * basis.fft(d.sum(dim=0)).reshape(-1)).reshape(1, -1).expand(shape[0], -1)
+            else:
+                dV = torch.zeros_like(d)
+            dV = dV - dV.mean()
+            deF = float((ldos * dV).sum()) * basis.dvol
+            e = d - (-ldos * dV + ldos * (deF / tdos))
+            return (e - e.mean()).reshape(-1)
+
+        dc = dF.mean()
+        x, self.last = _gmres(basis.architecture.ctx, adjoint, (dF - dc).reshape(-1), self.rtol, 1e-12, self.krylovdim,
+                              self.maxiter)
+        if not self.last["converged"]:
+            import warnings
+            warnings.warn("LDOS mixing GMRES not converged")
+        return x.reshape(shape) + dc
+
+
+def compute_ldos(basis, eF, eigenvalues, psi, *, temperature, weight_threshold=np.finfo(float).eps):
+    """dos.jl:43-65 with Gaussian smearing (occupation_derivative f'(x) = -exp(-x²)/sqrt(π)): a density pass with the
+    weights -filled/T f'((ε - εF)/T); the k-sum, the allreduce and the symmetrisation come with compute_density."""
+    filled = basis.model.filled_occupation
+    w = [filled / temperature * np.exp(-((np.asarray(e) - eF) / temperature) ** 2) / math.sqrt(math.pi) for e in eigenvalues]
+    w = [wk[:p.shape[0]] for wk, p in zip(w, psi)]
+    return compute_density(basis, psi, w, occupation_threshold=weight_threshold)
+
+
+def _gmres(ctx, apply, b, rtol, atol, krylovdim, maxiter):
+    """Restarted GMRES from x0 = 0 (Arnoldi + Givens rotations), the algorithm behind the reference's
+    `KrylovKit.linsolve(f, b; rtol, ishermitian=false)` (mixing.jl:283).  Vectors are flat float64 device tensors; the
+    projections of an Arnoldi step onto all previous vectors are ONE fused Gram launch (dftk_b200_tall_gram)."""
+    n = b.numel()
+    npad = n + (n & 1)
+
+    def pad(v):
+        return v if npad == n else torch.cat([v, v.new_zeros(1)])
+
+    tol = max(atol, rtol * float(b.norm()))
+    x = torch.zeros_like(b)
+    r = b.clone()
+    beta = float(r.norm())
+    n_apply = 0
+    for _restart in range(maxiter):
+        if beta <= tol:
+            break
+        V = torch.zeros((krylovdim + 1, npad), dtype=torch.float64, device=b.device)
+        V[0, :n] = r / beta
+        H = np.zeros((krylovdim + 1, krylovdim))
+        cs, sn, g = np.zeros(krylovdim), np.zeros(krylovdim), np.zeros(krylovdim + 1)
+        g[0] = beta
+        k_used = 0
+        for k in range(krylovdim):
+            w = pad(apply(V[k, :n]))
+            n_apply += 1
+            for _pass in range(2):                                 # classical Gram-Schmidt, twice (as stable as MGS)
+                h = ctx.real_gram(V[:k + 1], w[None, :].contiguous())[:, 0]
+                w = w - torch.as_tensor(h, device=b.device) @ V[:k + 1]
+                H[:k + 1, k] += h
+            H[k + 1, k] = float(w.norm())
+            for j in range(k):
+                t = cs[j] * H[j, k] + sn[j] * H[j + 1, k]
+                H[j + 1, k] = -sn[j] * H[j, k] + cs[j] * H[j + 1, k]
+                H[j, k] = t
+            den = math.hypot(H[k, k], H[k + 1, k])
+            wnorm = H[k + 1, k]
+            cs[k], sn[k] = H[k, k] / den, H[k + 1, k] / den
+            H[k, k], H[k + 1, k] = den, 0.0
+            g[k + 1] = -sn[k] * g[k]
+            g[k] = cs[k] * g[k]
+            k_used = k + 1
+            if abs(g[k + 1]) <= tol or wnorm == 0.0:
+                break
+            V[k + 1] = w / wnorm
+        y = np.linalg.solve(np.triu(H[:k_used, :k_used]), g[:k_used])
+        x = x + (torch.as_tensor(y, device=b.device) @ V[:k_used])[:n]
+        r = b - apply(x)
+        n_apply += 1
+        beta = float(r.norm())
+    return x, dict(converged=beta <= tol, n_apply=n_apply, residual=beta)
+
+
+class AndersonAcceleration:
+    """anderson.jl:42-130, history kept on the device.  The least-squares problem min |Pf + M β| is solved from the Gram
+    matrix of [M, Pf] -- one fused launch over the N_fft-sized history (dftk_b200_tall_gram) instead of a QR factorisation
+    of the N_fft × m matrix -- with one step of iterative refinement on the true residual (a second launch), which
+    restores the accuracy the normal equations lose when cond(M) approaches maxcond; cond(M) = sqrt(cond(M'M))."""
+
+    def __init__(self, m=10, maxcond=1e6, errorfactor=1e5, ctx=None):
+        self.m, self.maxcond, self.errorfactor, self.ctx = m, maxcond, errorfactor, ctx
         self.xs, self.rs, self.errs = [], [], []
 
     def _push(self, x, r):
         self.xs.append(x.clone()); self.rs.append(r.clone()); self.errs.append(float(r.norm()))
         if len(self.xs) > self.m:
             self.xs.pop(0); self.rs.pop(0); self.errs.pop(0)
+
+    def _gram(self, A, B):
+        if self.ctx is None or not A.is_cuda:
+            return (A @ B.T).cpu().numpy()            # host tensors (CPU-only unit tests of the host logic)
+        n = A.shape[1]
+        if n & 1:
+            A = torch.cat([A, A.new_zeros(A.shape[0], 1)], dim=1)
+            B = torch.cat([B, B.new_zeros(B.shape[0], 1)], dim=1)
+        return self.ctx.real_gram(A.contiguous(), B.contiguous())
 
     def __call__(self, x, alpha, Pf):
         shape = x.shape
@@ -135,19 +256,28 @@ class AndersonAcceleration:
         min_err = min(min(self.errs), float(Pf.norm()))
         keep = [i for i in range(len(self.errs)) if i == len(self.errs) - 1 or not self.errs[i] > self.errorfactor * min_err]
         self.xs, self.rs, self.errs = ([l[i] for i in keep] for l in (self.xs, self.rs, self.errs))
-        M = torch.stack(self.rs, dim=1) - Pf[:, None]
-        while True:
-            Q, R = torch.linalg.qr(M)
-            if M.shape[1] > 1 and float(torch.linalg.cond(R)) > self.maxcond:
-                idrop = int(np.argmax(self.errs[:-1]))
-                for l in (self.xs, self.rs, self.errs):
-                    l.pop(idrop)
-                M = M[:, [c for c in range(M.shape[1]) if c != idrop]]
-                continue
-            break
-        betas = -torch.linalg.solve_triangular(R, (Q.T @ Pf)[:, None], upper=True).reshape(-1)
+        M = torch.stack(self.rs, dim=0) - Pf[None, :]              # rows M_j = Pf_j - Pf
+        Gext = self._gram(torch.cat([M, Pf[None, :]], dim=0), torch.cat([M, Pf[None, :]], dim=0))
+        k = M.shape[0]
+        G, g = Gext[:k, :k], Gext[:k, k]
+        cols = list(range(k))
+
+        def cond(idx):
+            ev = np.linalg.eigvalsh(G[np.ix_(idx, idx)])
+            return math.inf if ev[0] <= 0 else math.sqrt(ev[-1] / ev[0])
+
+        while len(cols) > 1 and cond(cols) > self.maxcond:
+            idrop = int(np.argmax(self.errs[:-1]))
+            for l in (self.xs, self.rs, self.errs):
+                l.pop(idrop)
+            cols.pop(idrop)
+        Mk = M[cols]
+        Gk = G[np.ix_(cols, cols)]
+        betas = -np.linalg.solve(Gk, g[cols])
+        res = Pf + torch.as_tensor(betas, device=Pf.device) @ Mk      # refinement on the true least-squares residual
+        betas = betas - np.linalg.solve(Gk, self._gram(Mk, res[None, :])[:, 0])
         xn = x + alpha * Pf
-        for ib, b in enumerate(betas.cpu().tolist()):
+        for ib, b in enumerate(betas.tolist()):
             xn = xn + b * (self.xs[ib] - x + alpha * (self.rs[ib] - Pf))
         self._push(x, Pf)
         return xn.reshape(shape)
@@ -189,7 +319,7 @@ def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=N
     model = basis.model
     start = time.time()
     rho = guess_density(basis) if rho is None else rho
-    mixing = mixing or SimpleMixing()      # reference default LdosMixing degenerates to SimpleMixing at T = 0
+    mixing = mixing or LdosMixing()        # the reference default (self_consistent_field.jl:177); simple mixing at T = 0
     nbandsalg = nbandsalg or AdaptiveBands(model)
     if diagtolalg is None:       # default_diagtolalg, scf_callbacks.jl:220-229
         nonlinear = any(t in model.term_types for t in ("Hartree", "Xc"))
@@ -200,7 +330,7 @@ def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=N
     info = dict(basis=basis, rho=rho, psi=psi, occupation=None, eigenvalues=None, eF=None, n_iter=0, n_matvec=0,
                 eigenvalues_global=None, occupation_global=None,
                 converged=False, history_Etot=[], history_drho=[], stage="iterate", algorithm="SCF")
-    acc = AndersonAcceleration(m=anderson_m)
+    acc = AndersonAcceleration(m=anderson_m, ctx=basis.architecture.ctx)
 
     def fixpoint_map(rho_in):
         # the reference hands the info of the PREVIOUS step to determine_diagtol (self_consistent_field.jl:198-203):
@@ -226,7 +356,8 @@ def self_consistent_field(basis, *, rho=None, psi=None, tol=1e-6, is_converged=N
         info["energies"] = energies
         info["history_Etot"].append(energies.total)
         info["history_drho"].append(float(drho.norm()) * math.sqrt(basis.dvol))
-        nxt_rho = rho_in + mixing.mix_density(basis, drho)
+        nxt_rho = rho_in + mixing.mix_density(basis, drho, rho_in=rho_in, psi=nxt["psi"], eigenvalues=nxt["eigenvalues"],
+                                              eF=nxt["eF"], occupation=nxt["occupation"], n_iter=info["n_iter"])
         info["converged"] = basis.comm_kpts.all_true(is_converged(info))
         info["time_step"] = time.time() - t0
         if callback:

@@ -231,8 +231,10 @@ def energy_ewald(lattice, charges, positions, eta=None):
 
 class TermEwald:
     def __init__(self, basis):
+        from .forces import energy_forces_ewald_device
         m = basis.model
-        self.energy = energy_ewald(m.lattice, [a.charge_ionic() for a in m.atoms], m.positions)
+        self.energy = energy_forces_ewald_device(basis.architecture.ctx, m.lattice, [a.charge_ionic() for a in m.atoms],
+                                                 m.positions)[0]
 
     def ene_ops(self, basis, psi, occupation, **kw):
         return self.energy, [NoopOperator(basis, k) for k in basis.kpoints]

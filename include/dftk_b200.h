@@ -123,6 +123,11 @@ int dftk_b200_lobpcg_multi(int64_t n_blocks, dftk_b200_kblock* const* kblocks, v
                            double tol, int miniter, int maxiter, int64_t n_conv_check, int use_tpa_preconditioner,
                            double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec, int* converged);
 
+/* Start vectors (random_orbitals, src/common/orbitals.jl:82-87: orthonormalised complex normal numbers) for several
+ * k-blocks at once: X[i] (n_pw_i × n_bands, device) is filled and orthonormalised on the device. */
+int dftk_b200_random_orbitals(int64_t n_blocks, dftk_b200_kblock* const* kblocks, void* const* X, int64_t n_bands,
+                              uint64_t seed);
+
 /* ---- density (compute_density inner loop, src/densities.jl:32-44):
  *      rho[:,:,:] += sum_n occ_w[n] |IFFT psi_n|² / Ω   with occ_w[n] = occupation·kweight (host) ---- */
 int dftk_b200_density_accumulate(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host,
@@ -161,9 +166,21 @@ int dftk_b200_local_forces(dftk_b200_grid* grid, const void* w, int n_atoms, con
 int dftk_b200_nonlocal_force_rows(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host, int64_t n_bands,
                                   const double* gpk, double* rows_host);
 
+/* Ewald energy and forces of the ionic point charges (energy_forces_ewald, src/terms/ewald.jl:64-168, q = 0): the real-space
+ * and the reciprocal-space lattice sums as one kernel each.  lattice: 3×3 column-major (columns = lattice vectors), charges:
+ * n_atoms, positions: 3·n_atoms fractional (all host); eta and the summation limits (|G_i| <= glims[i], |R_i| <= rlims[i]) are
+ * the caller's (ewald.jl:86-104).  energy_host: 1 double (Hartree); forces_host: 3·n_atoms, reduced coordinates; either NULL. */
+int dftk_b200_ewald(dftk_b200_ctx* ctx, const double* lattice, int n_atoms, const double* charges, const double* positions,
+                    double eta, const int32_t* glims, const int32_t* rlims, double* energy_host, double* forces_host);
+
 /* ---- small dense helpers used by the host driver (columnwise_dots, src/common/linalg.jl:2-15) ---- */
 int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,
                               int64_t n_cols, void* out_host /*complex[n_cols]*/);
+/* out (n_cols_a × n_cols_b, HOST, column-major complex) = A' B for tall column-major device blocks with at most 96 columns
+ * each: one fused launch.  With real vectors viewed as complex pairs the real part is the real Gram matrix -- the history
+ * dot products of Anderson mixing (src/scf/anderson.jl:81-130) and of GMRES (LdosMixing, src/scf/mixing.jl:283). */
+int dftk_b200_tall_gram(dftk_b200_ctx* ctx, const void* A, int64_t lda, int64_t n_cols_a, const void* B, int64_t ldb,
+                        int64_t n_cols_b, int64_t n_rows, void* out_host);
 /* C = alpha * op(A) * B + beta * C on complex128 column-major device arrays (own DMMA kernels);
  * transA: 0 = N, 2 = C (conjugate transpose) */
 int dftk_b200_zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k,

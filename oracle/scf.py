@@ -216,6 +216,91 @@ def kerker_mix(basis, dF, kTF=0.8):
     return np.stack([(dtot + spin) / 2, (dtot - spin) / 2])
 
 
+# ------------------------------------------------------------------ LdosMixing: mixing.jl:205-292, chi0models.jl:20-41, dos.jl:43-65
+def gmres(apply, b, rtol=0.01, atol=1e-12, krylovdim=30, maxiter=100):
+    """Restarted GMRES from x0 = 0 (modified Gram-Schmidt Arnoldi, Givens rotations), the published algorithm behind the
+    `KrylovKit.linsolve(f, b; rtol, ishermitian=false)` call of mixing.jl:283 (KrylovKit is a third-party dependency, compat
+    "0.8.3, 0.9, 0.10", not under /root/reference): stop when the residual estimate is below max(atol, rtol ||b||)."""
+    b = np.asarray(b, dtype=float)
+    shape = b.shape
+    b = b.reshape(-1)
+    x = np.zeros_like(b)
+    tol = max(atol, rtol * np.linalg.norm(b))
+    r = b.copy()
+    beta = np.linalg.norm(r)
+    n_apply = 0
+    for _restart in range(maxiter):
+        if beta <= tol:
+            break
+        V = [r / beta]
+        H = np.zeros((krylovdim + 1, krylovdim))
+        cs, sn = np.zeros(krylovdim), np.zeros(krylovdim)
+        g = np.zeros(krylovdim + 1)
+        g[0] = beta
+        k_used = 0
+        for k in range(krylovdim):
+            w = apply(V[k].reshape(shape)).reshape(-1)
+            n_apply += 1
+            for j in range(k + 1):
+                H[j, k] = np.dot(V[j], w)
+                w = w - H[j, k] * V[j]
+            H[k + 1, k] = np.linalg.norm(w)
+            for j in range(k):
+                t = cs[j] * H[j, k] + sn[j] * H[j + 1, k]
+                H[j + 1, k] = -sn[j] * H[j, k] + cs[j] * H[j + 1, k]
+                H[j, k] = t
+            den = math.hypot(H[k, k], H[k + 1, k])
+            cs[k], sn[k] = H[k, k] / den, H[k + 1, k] / den
+            H[k, k] = den
+            H[k + 1, k] = 0.0
+            g[k + 1] = -sn[k] * g[k]
+            g[k] = cs[k] * g[k]
+            k_used = k + 1
+            if abs(g[k + 1]) <= tol:
+                break
+            V.append(w / np.linalg.norm(w))
+        y = np.linalg.solve(np.triu(H[:k_used, :k_used]), g[:k_used])
+        for j in range(k_used):
+            x = x + y[j] * V[j]
+        r = b - apply(x.reshape(shape)).reshape(-1)
+        n_apply += 1
+        beta = np.linalg.norm(r)
+    return x.reshape(shape), dict(converged=beta <= tol, n_apply=n_apply, residual=beta)
+
+
+def compute_ldos(basis, eF, eigenvalues, psi, temperature, weight_threshold=np.finfo(float).eps):
+    """dos.jl:43-65 with Gaussian smearing: occupation_derivative f'(x) = -exp(-x²)/sqrt(pi)."""
+    filled = basis.model.filled_occupation
+    w = [-filled / temperature * (-np.exp(-((np.asarray(e) - eF) / temperature) ** 2) / math.sqrt(math.pi)) for e in eigenvalues]
+    return compute_density(basis, psi, w, weight_threshold)
+
+
+def ldos_mix(basis, dF, terms, info, rtol=0.01):
+    """mix_density(::χ0Mixing with [LdosModel()], RPA = true), mixing.jl:262-292."""
+    m = basis.model
+    Tm = max(m.temperature, min(0.1, 100 * m.temperature))         # default_smearing_temperature, mixing.jl:296-301
+    if Tm == 0:
+        return dF
+    ldos = compute_ldos(basis, info["eF"], info["eigenvalues"], info["psi"], Tm)
+    if np.abs(ldos).max() < math.sqrt(np.finfo(float).eps):
+        return dF
+    tdos = ldos.sum() * basis.dvol
+    green = terms.green
+
+    def adjoint(d):
+        dV = np.zeros_like(d)
+        if green is not None:
+            dV[:] = basis.irfft_cube(green * basis.fft_cube(d.sum(axis=0)))[None, :]      # Hartree kernel on the total density
+        dV = dV - dV.mean()
+        deF = np.sum(ldos * dV) * basis.dvol
+        e = d - (-ldos * dV + ldos * deF / tdos)                                          # εδF .-= χ0 δV
+        return e - e.mean()
+
+    dc = dF.mean()
+    x, st = gmres(adjoint, dF - dc, rtol=rtol)
+    return x + dc
+
+
 # ------------------------------------------------------------------ self_consistent_field.jl
 def self_consistent_field(basis, rho=None, tol=1e-6, maxiter=100, damping=0.8, mixing="simple",
                           nbandsalg=None, is_converged=None, rng=None, callback=None,
@@ -261,7 +346,14 @@ def self_consistent_field(basis, rho=None, tol=1e-6, maxiter=100, damping=0.8, m
         info["energies"] = E
         info["history_Etot"].append(E["total"])
         info["history_drho"].append(float(np.linalg.norm(drho) * math.sqrt(basis.dvol)))
-        mixed = drho if mixing == "simple" else kerker_mix(basis, drho)
+        if mixing == "simple":
+            mixed = drho
+        elif mixing == "kerker":
+            mixed = kerker_mix(basis, drho)
+        elif mixing == "ldos":             # the reference default (self_consistent_field.jl:177)
+            mixed = ldos_mix(basis, drho, terms, info)
+        else:
+            raise ValueError(mixing)
         info["converged"] = bool(is_converged(info))
         if callback:
             callback(info)

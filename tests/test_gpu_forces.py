@@ -100,3 +100,32 @@ def test_force_entry_points_reject_bad_arguments():
     rows[:] = 1.0
     assert ctx.L.dftk_b200_nonlocal_force_rows(kb.h, _ptr(psi), _ptr(out), 0, _ptr(gpk), _ptr(rows)) == 0
     assert not rows.any()
+
+
+def test_ewald_kernels_match_oracle():
+    """dftk_b200_ewald (real-space and reciprocal-space lattice sums as one kernel each) against the oracle's
+    energy_forces_ewald and the reference's golden Ewald energies (test/ewald.jl:1-52)."""
+    import dftk_b200 as dftk
+    from gpu_common import ctx
+    from oracle import forces as oforces
+    from silicon import LATTICE, POSITIONS
+    c = ctx()
+    for lat_g, ch, pos_g, ref, tol in [(16 * np.eye(3), [1], [[0, 0, 0]], -0.088665545, 1e-8),
+                                        (LATTICE, [14, 14], POSITIONS, -102.8741963352893, 1e-8),
+                                        (16 * np.eye(3), [5, 5], [[0, 0, 0], [0.14763485355139283, 0, 0]], 1.790634595, 1e-7)]:
+        pg = [np.array(q, dtype=float) for q in pos_g]
+        e, f = dftk.energy_forces_ewald_device(c, lat_g, ch, pg)
+        assert e == pytest.approx(ref, abs=tol)
+        eo, fo = oforces.energy_forces_ewald(np.asarray(lat_g, dtype=float), ch, pg)
+        assert e == pytest.approx(eo, abs=1e-11 * max(1, abs(eo)))
+        np.testing.assert_allclose(np.array(f), np.array(fo), atol=1e-11 * max(1.0, np.abs(np.array(fo)).max()))
+    # a low-symmetry 5-atom, two-species cell with a skewed lattice
+    rng = np.random.default_rng(3)
+    lat = np.array([[7.0, 0.4, -0.3], [0.2, 8.0, 0.5], [-0.1, 0.3, 9.5]])
+    pos = [rng.random(3) for _ in range(5)]
+    ch = [4, 3, 4, 1, 3]
+    e, f = dftk.energy_forces_ewald_device(c, lat, ch, pos)
+    eo, fo = oforces.energy_forces_ewald(lat, ch, pos)
+    assert e == pytest.approx(eo, abs=1e-11 * abs(eo))
+    np.testing.assert_allclose(np.array(f), np.array(fo), atol=1e-10)
+    assert np.abs(np.sum(np.array(f), axis=0)).max() < 1e-9            # translation invariance

@@ -187,6 +187,71 @@ def test_aluminium_pbe_smearing_matches_oracle():
     _compare_scf(res, ores, basis, ob, 4, 6)
 
 
+def test_aluminium_default_ldos_mixing_matches_oracle():
+    """The reference's DEFAULT mixing (LdosMixing, self_consistent_field.jl:177; mixing.jl:205-292): product default vs the
+    oracle's restatement (same chi0 model, same GMRES): energy, Fermi level and the number of SCF iterations."""
+    import dftk_b200 as dftk
+    from oracle.basis import Element, Model, PlaneWaveBasis as OBasis
+    from oracle import scf as oscf
+    a = 7.65339
+    pos = [[0, 0, 0], [0, 0.5, 0.5], [0.5, 0, 0.5], [0.5, 0.5, 0]]
+    Al = dftk.ElementPsp("Al", functional="pbe")
+    model = dftk.model_DFT(a * np.eye(3), [Al] * 4, pos, functionals=dftk.PBE(), temperature=0.01)
+    basis = dftk.PlaneWaveBasis(model, Ecut=7, kgrid=(2, 2, 2))
+    res = dftk.self_consistent_field(basis, tol=1e-9)                        # mixing = LdosMixing() by default
+    assert res["converged"]
+    om = Model(a * np.eye(3), [Element("Al", functional="pbe")] * 4, pos, functionals=("gga_x_pbe", "gga_c_pbe"), temperature=0.01)
+    ob = OBasis(om, 7, kgrid=(2, 2, 2))
+    ores = oscf.self_consistent_field(ob, tol=1e-9, mixing="ldos")
+    assert abs(res["energies"].total - ores["energies"]["total"]) < 4e-8     # 1e-8 Ha/atom
+    assert abs(res["eF"] - ores["eF"]) < 1e-6
+    assert abs(res["n_iter"] - ores["n_iter"]) <= 2
+    # the LDOS itself: one more density pass with -f' weights (dos.jl:43-65) vs the oracle's
+    ld = dftk.compute_ldos(basis, res["eF"], res["eigenvalues"], res["psi"], temperature=0.1)
+    old = oscf.compute_ldos(ob, ores["eF"], ores["eigenvalues"], ores["psi"], 0.1)
+    assert np.linalg.norm(ld.cpu().numpy() - old) * math.sqrt(basis.dvol) < 1e-6 * np.linalg.norm(old) * math.sqrt(basis.dvol) + 1e-7
+
+
+def test_mixing_helpers_on_device():
+    """dftk_b200_tall_gram (Anderson / GMRES history dot products in one launch) and the device Anderson against NumPy."""
+    import dftk_b200 as dftk
+    from gpu_common import ctx
+    c = ctx()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    A = torch.randn(5, 20000, generator=g, dtype=torch.float64).to(c.device)
+    B = torch.randn(3, 20000, generator=g, dtype=torch.float64).to(c.device)
+    np.testing.assert_allclose(c.real_gram(A, B), (A @ B.T).cpu().numpy(), rtol=1e-12, atol=1e-10)
+    # Anderson on the device reproduces the host path on a linear fixed-point problem (test/anderson.jl)
+    n = 401                                                                    # odd length: exercises the padding
+    M = torch.randn(n, n, generator=g, dtype=torch.float64) * (0.3 / math.sqrt(n))
+    b = torch.randn(n, generator=g, dtype=torch.float64)
+    xs = {}
+    for dev in ("cpu", "cuda"):
+        Md, bd = M.to(dev), b.to(dev)
+        acc = dftk.AndersonAcceleration(m=10, ctx=c if dev == "cuda" else None)
+        x = torch.zeros(n, dtype=torch.float64, device=dev)
+        for _ in range(12):
+            x = acc(x, 0.8, Md @ x + bd - x)
+        xs[dev] = x.cpu()
+    xstar = torch.linalg.solve(torch.eye(n, dtype=torch.float64) - M, b)
+    assert (xs["cuda"] - xstar).abs().max().item() < 1e-8
+    assert (xs["cuda"] - xs["cpu"]).abs().max().item() < 1e-8
+
+
+def test_random_orbitals_are_orthonormal():
+    import dftk_b200 as dftk
+    model = _si_model(dftk, dftk.LDA(), symmetries=False)
+    basis = dftk.PlaneWaveBasis(model, Ecut=8, kgrid=dftk.ExplicitKpoints([[0.2, 0.3, 0.1], [0, 0, 0]], [0.5, 0.5]), fft_size=(18, 18, 18))
+    from dftk_b200.device import random_orbitals_multi
+    Xs = random_orbitals_multi(basis.kblocks, 9, seed=5)
+    for X in Xs:
+        G = X.conj() @ X.T
+        assert (G - torch.eye(9, dtype=G.dtype, device=G.device)).abs().max().item() < 1e-13
+    assert (Xs[0][:, :50] - Xs[1][:, :50]).abs().max().item() > 1e-3            # different blocks, different numbers
+    Y = random_orbitals_multi(basis.kblocks, 9, seed=5)
+    assert torch.equal(Y[0], Xs[0])                                              # deterministic in the seed
+
+
 def test_iron_collinear_spin_matches_oracle():
     # BASELINE config C5 shape (Fe bcc PBE, collinear spin), reduced Ecut / k-grid; test/iron_pbe.jl:53 setup
     import dftk_b200 as dftk
