@@ -34,11 +34,15 @@ SIGNATURES = {
     "dftk_b200_kblock_create": (c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_dbl, P(c_vp)]),
     "dftk_b200_kblock_destroy": (c_int, [c_vp]),
     "dftk_b200_kblock_set_potential": (c_int, [c_vp, c_vp]),
+    "dftk_b200_grid_set_potential": (c_int, [c_vp, c_int, c_vp]),
+    "dftk_b200_kblock_use_grid_potential": (c_int, [c_vp, c_int]),
     "dftk_b200_fft_sphere_to_real": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int]),
     "dftk_b200_fft_real_to_sphere": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int]),
     "dftk_b200_apply_h": (c_int, [c_vp, c_vp, c_vp, c_i64]),
     "dftk_b200_apply_terms": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_int]),
     "dftk_b200_band_energies": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "dftk_b200_band_energies_multi": (c_int, [c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "dftk_b200_density_accumulate_multi": (c_int, [c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dftk_b200_lobpcg": (c_int, [c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp,
                                  P(c_int), P(c_i64), P(c_int)]),
     "dftk_b200_lobpcg_multi": (c_int, [c_i64, c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -51,6 +55,8 @@ SIGNATURES = {
     "dftk_b200_local_forces": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp]),
     "dftk_b200_nonlocal_force_rows": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dftk_b200_ewald": (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp]),
+    "dftk_b200_structure_factor": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
+    "dftk_b200_build_projectors": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "dftk_b200_columnwise_dots": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "dftk_b200_tall_gram": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp]),
     "dftk_b200_zgemm": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp,

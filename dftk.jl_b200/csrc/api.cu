@@ -225,6 +225,7 @@ int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
   else if (n == "band_chunk") ctx->band_chunk = (int)value;
   else if (n == "gemm_stages") ctx->gemm_stages = (value == 3 ? 3 : 2);
   else if (n == "small_dense") ctx->small_dense = (int)value;
+  else if (n == "z_pipeline") ctx->z_pipeline = (int)value;
   else if (n == "force_svd_fallback") ctx->force_svd_fallback = (int)value;
   else if (n == "fft_engine") ctx->fft_engine = (int)value;  // 0 = register two-pass where available, 1 = generic
   else throw Error(DFTK_B200_EINVAL, "set_option: unknown option " + n);
@@ -383,6 +384,7 @@ int dftk_b200_kblock_set_potential(dftk_b200_kblock* kb, const double* V) {
   dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
   API_BEGIN
   REQUIRE(kb, "set_potential: kblock is NULL");
+  kb->grid_V = -1;
   if (!V) {
     kb->has_V = false;
     return DFTK_B200_OK;
@@ -392,6 +394,37 @@ int dftk_b200_kblock_set_potential(dftk_b200_kblock* kb, const double* V) {
   kb->V.ensure(N);
   // pre-scale by fft_normalization * ifft_normalization = 1/N (src/terms/Hamiltonian.jl:152-153)
   LAUNCH(ctx, k_scale_copy, (unsigned)((N + 255) / 256), 256, 0, kb->V.p, d, kb->grid->fft_norm * kb->grid->ifft_norm, N);
+  kb->has_V = true;
+  API_END(ctx)
+}
+
+int dftk_b200_grid_set_potential(dftk_b200_grid* grid, int spin, const double* V) {
+  dftk_b200_ctx* ctx = grid ? grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(grid && (spin == 0 || spin == 1), "grid_set_potential: bad argument");
+  if (!V) {
+    grid->has_Vs[spin] = false;
+    return DFTK_B200_OK;
+  }
+  const int64_t N = grid->N;
+  const double* d = (const double*)stage_in(ctx, V, N * sizeof(double), ctx->stage_in);
+  grid->Vs[spin].ensure(N);
+  LAUNCH(ctx, k_scale_copy, (unsigned)((N + 255) / 256), 256, 0, grid->Vs[spin].p, d, grid->fft_norm * grid->ifft_norm, N);
+  grid->has_Vs[spin] = true;
+  API_END(ctx)
+}
+
+int dftk_b200_kblock_use_grid_potential(dftk_b200_kblock* kb, int spin) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && spin >= -1 && spin <= 1, "kblock_use_grid_potential: bad argument");
+  if (spin < 0) {
+    kb->grid_V = -1;
+    kb->has_V = kb->V.p != nullptr;
+    return DFTK_B200_OK;
+  }
+  REQUIRE(kb->grid->has_Vs[spin], "kblock_use_grid_potential: dftk_b200_grid_set_potential was not called for this spin");
+  kb->grid_V = spin;
   kb->has_V = true;
   API_END(ctx)
 }
@@ -490,6 +523,34 @@ int dftk_b200_band_energies(dftk_b200_kblock* kb, const void* psi, int64_t n_ban
     }
   }
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  API_END(ctx)
+}
+
+int dftk_b200_band_energies_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, const void* const* psi, const int32_t* n_bands,
+                                  int64_t ld_out, double* ekin_host, double* enl_host) {
+  dftk_b200_ctx* ctx = (n_blocks > 0 && kbs && kbs[0]) ? kbs[0]->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(n_blocks >= 0 && (n_blocks == 0 || (kbs && psi && n_bands)), "band_energies_multi: bad argument");
+  for (int64_t i = 0; i < n_blocks; ++i)
+    REQUIRE(kbs[i] && psi[i] && is_device_ptr(psi[i]), "band_energies_multi: orbitals must be device memory");
+  band_energies_multi(n_blocks, kbs, (const cplx* const*)psi, (const int*)n_bands, ld_out, ekin_host, enl_host);
+  API_END(ctx)
+}
+
+int dftk_b200_density_accumulate_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, const void* const* psi,
+                                       const double* occ_w_host, int64_t ld_w, const int32_t* n_bands, double* rho) {
+  dftk_b200_ctx* ctx = (n_blocks > 0 && kbs && kbs[0]) ? kbs[0]->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(n_blocks >= 0 && (n_blocks == 0 || (kbs && psi && n_bands && occ_w_host && rho)), "density_accumulate_multi: bad argument");
+  if (n_blocks == 0) return DFTK_B200_OK;
+  REQUIRE(is_device_ptr(rho), "density_accumulate_multi: rho must be device memory");
+  for (int64_t i = 0; i < n_blocks; ++i)
+    REQUIRE(kbs[i] && psi[i] && is_device_ptr(psi[i]) && n_bands[i] >= 0 && n_bands[i] <= ld_w,
+            "density_accumulate_multi: bad block / orbitals must be device memory");
+  if (!kb_density_accumulate_multi((int)n_blocks, kbs, (const cplx* const*)psi, occ_w_host, ld_w, (const int*)n_bands, rho))
+    for (int64_t i = 0; i < n_blocks; ++i)       // blocks that do not qualify for the batched kernels: one after the other
+      if (n_bands[i] > 0)
+        kb_density_accumulate(kbs[i], (const cplx*)psi[i], occ_w_host + i * ld_w, n_bands[i], rho + (size_t)kbs[i]->spin * kbs[i]->grid->N);
   API_END(ctx)
 }
 
@@ -646,6 +707,26 @@ int dftk_b200_nonlocal_force_rows(dftk_b200_kblock* kb, const void* psi, const d
   REQUIRE(is_device_ptr(gpk), "nonlocal_force_rows: gpk must be device memory");
   const cplx* d = (const cplx*)stage_in(ctx, psi, (size_t)kb->n_pw * n_bands * sizeof(cplx), ctx->stage_in);
   kb_nonlocal_force_rows(kb, d, occ_w_host, n_bands, gpk, rows_host);
+  API_END(ctx)
+}
+
+// ------------------------------------------------------------------ setup kernels
+int dftk_b200_structure_factor(dftk_b200_grid* grid, int n_atoms, const double* positions, const double* coefficients, void* out) {
+  dftk_b200_ctx* ctx = grid ? grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(grid && positions && out && n_atoms >= 1, "structure_factor: bad argument");
+  REQUIRE(is_device_ptr(out) && !is_device_ptr(positions), "structure_factor: positions on the host, result on the device");
+  structure_factor(grid, n_atoms, positions, coefficients, (cplx*)out);
+  API_END(ctx)
+}
+
+int dftk_b200_build_projectors(dftk_b200_ctx* ctx, int64_t n_pw, const double* gpk, int n_atoms, const double* positions,
+                               int n_rows, const void* form_factors, void* P) {
+  API_BEGIN
+  REQUIRE(ctx && gpk && positions && form_factors && P && n_pw >= 1 && n_atoms >= 0 && n_rows >= 0, "build_projectors: bad argument");
+  REQUIRE(is_device_ptr(gpk) && is_device_ptr(form_factors) && is_device_ptr(P) && !is_device_ptr(positions),
+          "build_projectors: gpk / form factors / P on the device, positions on the host");
+  build_projectors(ctx, n_pw, gpk, n_atoms, positions, n_rows, (const cplx*)form_factors, (cplx*)P);
   API_END(ctx)
 }
 

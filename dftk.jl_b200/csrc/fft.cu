@@ -112,8 +112,8 @@ const RegKernels* reg_kernels_for(int n) {
 void reg_set_attributes() {
   for (const RegKernels& k : reg_table())
     for (const void* f : {k.sphere_to_x, k.y_backward, k.z_apply, k.z_to_cube, k.z_from_cube, k.z_density,
-                          k.y_forward, k.x_to_sphere, k.m_sphere_to_x, k.m_y_backward, k.m_z_apply, k.m_y_forward,
-                          k.m_x_to_sphere})
+                          k.y_forward, k.x_to_sphere, k.z_apply_pipe, k.m_sphere_to_x, k.m_y_backward, k.m_z_apply, k.m_y_forward,
+                          k.m_x_to_sphere, k.m_z_density})
       CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
 }
 // must match RegPair<A,B>::L (fft_reg.cuh)
@@ -250,14 +250,25 @@ void kb_apply_local_kinetic(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, i
       int L = reg_L(g->rz), Lp = L + 1;
       const cplx* tw = (const cplx*)g->twz.p;
       cplx* W2 = kb->W2.p;
-      const double* V = kb->V.p;
+      const double* V = kb->Vp();
       void* args[] = {&kb->T, &tw, &W2, &V, &L, &Lp};
-      // single (aliased) exchange buffer on the device, cf. DFTK_Z_ALIAS in fft_reg.cuh
-      launch_ptr(ctx, g->rz->z_apply, dim3(cdiv(g->nx, L), g->ny, nb), L * g->rz->T, reg_smem(g->rz) / 2, args);
+      const size_t sm_pipe = reg_smem(g->rz) / 2 + 2 * (size_t)kb->T.n_zc * L * sizeof(cplx);
+      const int64_t n_tiles = (int64_t)cdiv(g->nx, L) * g->ny * nb;
+      if (ctx->z_pipeline && sm_pipe <= 100 * 1024 && n_tiles >= 2 * (int64_t)ctx->sm_count) {
+        // persistent CTAs (as many as fit an SM by shared memory, at most 4), each loops over tiles with the next tile's
+        // input in flight (cp.async) while the current one is transformed
+        int per_sm = (int)std::min<size_t>(4, (size_t)(220 * 1024) / sm_pipe);
+        unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)per_sm * ctx->sm_count);
+        void* pargs[] = {&kb->T, &tw, &W2, &V, &nb};
+        launch_ptr(ctx, g->rz->z_apply_pipe, dim3(grid), L * g->rz->T, sm_pipe, pargs);
+      } else {
+        // single (aliased) exchange buffer on the device, cf. DFTK_Z_ALIAS in fft_reg.cuh
+        launch_ptr(ctx, g->rz->z_apply, dim3(cdiv(g->nx, L), g->ny, nb), L * g->rz->T, reg_smem(g->rz) / 2, args);
+      }
     } else {
       int L = g->Lz, Lp = L | 1;
       LAUNCH(ctx, k_z_apply_potential, dim3(cdiv(g->nx, L), g->ny, nb), FFT_THREADS, smem_for(g->nz, L),
-             kb->T, g->pz, (const cplx*)g->twz.p, kb->W2.p, (const double*)kb->V.p, L, Lp);
+             kb->T, g->pz, (const cplx*)g->twz.p, kb->W2.p, (const double*)kb->Vp(), L, Lp);
     }
     kb_planes_to_sphere(kb, hpsi + b0 * kb->n_pw, kb->n_pw, nb, 1.0, with_kin ? kb->kin.p : nullptr, p,
                         kb->n_pw, accumulate ? 1 : 0);
@@ -293,7 +304,9 @@ bool kb_apply_local_kinetic_multi(int n, dftk_b200_kblock* const* kbs, const cpl
     it.ldpsi = kb->n_pw;
     it.W1 = kb->W1.p;
     it.W2 = kb->W2.p;
-    it.V = kb->V.p;
+    it.V = kb->Vp();
+    it.wts = nullptr;
+    it.nb = n_bands[i];
     it.out = hpsi[i];
     it.ldout = kb->n_pw;
     it.kin = kb->kin.p;
@@ -331,6 +344,91 @@ bool kb_apply_local_kinetic_multi(int n, dftk_b200_kblock* const* kbs, const cpl
     void* args[] = {&d_items, &d_map, &tw, &L, &Lp};
     launch_ptr(ctx, g->rx->m_x_to_sphere, dim3(cdiv(max_cols, L), total), L * g->rx->T, reg_smem(g->rx) + 5 * L * sizeof(int), args);
   }
+  return true;
+}
+
+bool kb_density_accumulate_multi(int n, dftk_b200_kblock* const* kbs, const cplx* const* psi, const double* occ_w_host,
+                                 int64_t ld_w, const int* n_bands, double* rho) {
+  if (n <= 0) return true;
+  dftk_b200_grid* g = kbs[0]->grid;
+  dftk_b200_ctx* ctx = g->ctx;
+  if (!(g->rx && g->ry && g->rz)) return false;
+  int total = 0, max_cols = 0, max_zc = 0, total_w = 0;
+  for (int i = 0; i < n; ++i) {
+    dftk_b200_kblock* kb = kbs[i];
+    if (kb->grid != g || !kb->T.ranges_ok || kb->spin < 0 || kb->spin > 1) return false;
+    if (n_bands[i] > 0 && band_chunk_for(kb, n_bands[i]) < n_bands[i]) return false;
+    total += n_bands[i];
+    max_cols = std::max(max_cols, kb->T.n_cols);
+    max_zc = std::max(max_zc, kb->T.n_zc);
+  }
+  if (total == 0) return true;
+  if (total > 65535) return false;
+  // device copies: weights (scaled by ifft_norm^2), items, band map -- staged through the context's descriptor ring
+  std::vector<double> w(total);
+  std::vector<FftMultiItem> items;
+  std::vector<int2> bandmap;
+  const double nrm = g->ifft_norm * g->ifft_norm;
+  size_t need = ((size_t)total * sizeof(double) + 255 & ~(size_t)255) + ((size_t)n * sizeof(FftMultiItem) + 255 & ~(size_t)255) +
+                ((size_t)total * sizeof(int2) + 255 & ~(size_t)255) + 1024;
+  char* ring = ctx->batch_ring.ensure(std::max<size_t>(need, (size_t)4 << 20));
+  double* d_w = (double*)ring;
+  size_t off_items = ((size_t)total * sizeof(double) + 255) & ~(size_t)255;
+  for (int i = 0; i < n; ++i) {
+    dftk_b200_kblock* kb = kbs[i];
+    if (n_bands[i] <= 0) continue;
+    ensure_scratch(kb, n_bands[i]);
+    FftMultiItem it{};
+    it.T = kb->T;
+    it.psi = psi[i];
+    it.ldpsi = kb->n_pw;
+    it.W1 = kb->W1.p;
+    it.W2 = kb->W2.p;
+    it.wts = d_w + total_w;
+    it.nb = n_bands[i];
+    it.V = nullptr;
+    it.out = nullptr;
+    it.kin = (const double*)(intptr_t)kb->spin;      // spin channel of the block rides in an unused pointer slot
+    for (int l = 0; l < n_bands[i]; ++l) {
+      w[total_w + l] = occ_w_host[(size_t)i * ld_w + l] * nrm;
+      bandmap.push_back(make_int2((int)items.size(), l));
+    }
+    total_w += n_bands[i];
+    items.push_back(it);
+  }
+  FftMultiItem* d_items = (FftMultiItem*)(ring + off_items);
+  size_t off_map = off_items + (((size_t)items.size() * sizeof(FftMultiItem) + 255) & ~(size_t)255);
+  int2* d_map = (int2*)(ring + off_map);
+  CUDA_CHECK(cudaMemcpyAsync(d_w, w.data(), (size_t)total * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(FftMultiItem), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_CHECK(cudaMemcpyAsync(d_map, bandmap.data(), bandmap.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+  const FftMultiItem* c_items = d_items;
+  const int2* c_map = d_map;
+  {
+    int L = reg_L(g->rx), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twx.p;
+    void* args[] = {&c_items, &c_map, &tw, &L, &Lp};
+    launch_ptr(ctx, g->rx->m_sphere_to_x, dim3(cdiv(max_cols, L), total), L * g->rx->T, reg_smem(g->rx) + 5 * L * sizeof(int), args);
+  }
+  {
+    int L = reg_L(g->ry), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twy.p;
+    void* args[] = {&c_items, &c_map, &tw, &L, &Lp};
+    launch_ptr(ctx, g->ry->m_y_backward, dim3(cdiv(g->nx, L), max_zc, total), L * g->ry->T, reg_smem(g->ry), args);
+  }
+  int n_items = (int)items.size();
+  for (int spin = 0; spin < 2; ++spin) {
+    bool any = false;
+    for (auto& it : items) any = any || (int)(intptr_t)it.kin == spin;
+    if (!any) continue;
+    int L = reg_L(g->rz), Lp = L + 1;
+    const cplx* tw = (const cplx*)g->twz.p;
+    double* r = rho + (size_t)spin * g->N;
+    size_t sm = reg_smem(g->rz) + (size_t)g->nz * L * sizeof(double);
+    void* args[] = {&c_items, &n_items, &spin, &tw, &r, &L, &Lp};
+    launch_ptr(ctx, g->rz->m_z_density, dim3(cdiv(g->nx, L), g->ny), L * g->rz->T, sm, args);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));     // host staging vectors go out of scope
   return true;
 }
 

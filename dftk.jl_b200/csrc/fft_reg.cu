@@ -33,6 +33,11 @@ kr_z_apply(SphereTablesX T, const cplx* tw, cplx* W2, const double* V, int L, in
 }
 template <int A, int B>
 __global__ void __launch_bounds__(REG_MAXT(A, B))
+kr_z_apply_pipe(SphereTablesX T, const cplx* tw, cplx* W2, const double* V, int n_bands) {
+  reg_z_apply_potential_pipe<A, B>(T, tw, W2, V, (cplx*)dyn_smem_reg, n_bands);
+}
+template <int A, int B>
+__global__ void __launch_bounds__(REG_MAXT(A, B))
 kr_z_to_cube(SphereTablesX T, const cplx* tw, const cplx* W2, cplx* cube, double scale, int L, int Lp) {
   reg_z_to_cube<A, B>(T, tw, W2, cube, scale, L, Lp, (cplx*)dyn_smem_reg, Dim3i{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z});
 }
@@ -103,6 +108,19 @@ kr_x_to_sphere_multi(const FftMultiItem* __restrict__ items, const int2* __restr
                         Dim3i{(int)blockIdx.x, bm.y, 0});
 }
 
+// density of all k-blocks of one spin channel: the CTA of a (y, x-tile) accumulates the bands of block after block
+// (single writer per density element, fixed order: deterministic)
+template <int A, int B>
+__global__ void __launch_bounds__(REG_MAXT(A, B))
+kr_z_density_multi(const FftMultiItem* __restrict__ items, int n_items, int spin, const cplx* tw, double* rho, int L, int Lp) {
+  for (int i = 0; i < n_items; ++i) {
+    const FftMultiItem& it = items[i];
+    if ((int)(intptr_t)it.kin != spin) continue;
+    reg_z_density<A, B>(it.T, tw, it.W2, it.wts, it.nb, rho, L, Lp, (cplx*)dyn_smem_reg, Dim3i{(int)blockIdx.x, (int)blockIdx.y, 0});
+    __syncthreads();
+  }
+}
+
 template <int A, int B>
 static RegKernels make_entry() {
   RegKernels k;
@@ -112,6 +130,7 @@ static RegKernels make_entry() {
   k.sphere_to_x = (const void*)kr_sphere_to_x<A, B>;
   k.y_backward = (const void*)kr_y_backward<A, B>;
   k.z_apply = (const void*)kr_z_apply<A, B>;
+  k.z_apply_pipe = (const void*)kr_z_apply_pipe<A, B>;
   k.z_to_cube = (const void*)kr_z_to_cube<A, B>;
   k.z_from_cube = (const void*)kr_z_from_cube<A, B>;
   k.z_density = (const void*)kr_z_density<A, B>;
@@ -122,6 +141,7 @@ static RegKernels make_entry() {
   k.m_z_apply = (const void*)kr_z_apply_multi<A, B>;
   k.m_y_forward = (const void*)kr_y_forward_multi<A, B>;
   k.m_x_to_sphere = (const void*)kr_x_to_sphere_multi<A, B>;
+  k.m_z_density = (const void*)kr_z_density_multi<A, B>;
   return k;
 }
 

@@ -133,6 +133,96 @@ HD void reg_z_apply_potential(const SphereTablesX& T, const cplx* __restrict__ t
   }
 }
 
+#if defined(__CUDACC__)
+// ---- software-pipelined form of the fused z stage (device only).  The plain kernel above is latency bound: one tile per
+// CTA, 12 dependent-free global loads per thread, then nothing to do until they land (ncu: 24 % warps active, top stall
+// long-scoreboard).  Here a CTA is persistent over tiles (x-tile, y, band) and the pruned input column block of tile i+1
+// (n_zc rows of L complex numbers, 12 KB at 192^3) travels global -> shared with cp.async while the butterflies of tile i
+// run; pass 1 then reads its A elements from shared memory.  V(r) (L2 resident, evict-last) and the stores are unchanged.
+__device__ __forceinline__ void zp_cp_async16(void* smem, const void* gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+template <int A, int B>
+__device__ void reg_z_apply_potential_pipe(const SphereTablesX& T, const cplx* __restrict__ tw, cplx* __restrict__ W2,
+                                           const double* __restrict__ V, cplx* sm, int n_bands) {
+  constexpr int n = A * B, TT = RegPair<A, B>::T, L = RegPair<A, B>::L, Lp = RegPair<A, B>::Lp;
+  const int nx = T.nx, ny = T.ny, n_zc = T.n_zc;
+  const int n_xt = (nx + L - 1) / L;
+  const long long n_tiles = (long long)n_xt * ny * n_bands;
+  cplx* bufA = sm;                                // exchange buffer (both exchanges alias, as in the plain kernel)
+  cplx* in0 = sm + (size_t)n * Lp;                // two staged input tiles [n_zc][L]
+  cplx* in1 = in0 + (size_t)n_zc * L;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  const int tid = threadIdx.x, line = tid % L, p = tid / L;
+  auto stage = [&](long long tile, cplx* dst) {
+    const int xt = (int)(tile % n_xt), y = (int)((tile / n_xt) % ny), band = (int)(tile / ((long long)n_xt * ny));
+    const cplx* w2 = W2 + (size_t)band * n_zc * ny * nx;
+    for (int c = tid; c < n_zc * L; c += L * TT) {
+      const int zc = c / L, l = c % L, x = xt * L + l;
+      zp_cp_async16(dst + c, w2 + (unsigned)((zc * ny + y) * nx + (x < nx ? x : 0)), x < nx);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  long long tile = blockIdx.x;
+  if (tile < n_tiles) stage(tile, in0);
+  int it = 0;
+  for (; tile < n_tiles; tile += gridDim.x, ++it) {
+    cplx* cur = (it & 1) ? in1 : in0;
+    cplx* nxt = (it & 1) ? in0 : in1;
+    const long long tn = tile + gridDim.x;
+    if (tn < n_tiles) {
+      stage(tn, nxt);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    const int xt = (int)(tile % n_xt), y = (int)((tile / n_xt) % ny), band = (int)(tile / ((long long)n_xt * ny));
+    const int x = xt * L + line;
+    cplx* w2 = W2 + (size_t)band * n_zc * ny * nx;
+    if (p < B) {
+      cplx v[A];
+#pragma unroll
+      for (int r = 0; r < A; ++r) {
+        const int zc = zc_index(T, p + B * r);
+        v[r] = zc >= 0 ? cur[zc * L + line] : make_double2(0.0, 0.0);
+      }
+      pass1_store<A, B, +1>(v, p, line, bufA, Lp, tw);
+    }
+    __syncthreads();
+    cplx Y[B];
+    if (p < A) {
+      cplx X[B];
+      pass2_load<A, B, +1>(X, p, line, bufA, Lp);
+#pragma unroll
+      for (int d = 0; d < B; ++d) {
+        double vv = ld_pred_hint(V + (unsigned)(((p + A * d) * ny + y) * nx + x), x < nx, pol_keep);
+        X[d] = cscale(X[d], vv);
+      }
+      pass1_compute<B, A, -1>(X, p, tw, Y);
+    }
+    __syncthreads();
+    if (p < A) {
+#pragma unroll
+      for (int c = 0; c < B; ++c) bufA[(c * A + p) * Lp + line] = Y[c];
+    }
+    __syncthreads();
+    if (p < B) {
+      cplx X[A];
+      pass2_load<B, A, -1>(X, p, line, bufA, Lp);
+#pragma unroll
+      for (int f = 0; f < A; ++f) {
+        const int zc = zc_index(T, p + B * f);
+        st_pred_hint(w2 + (unsigned)(((zc < 0 ? 0 : zc) * ny + y) * nx + x), X[f], zc >= 0 && x < nx, pol_stream);
+      }
+    }
+    __syncthreads();     // bufA and `cur` are free again (the next iteration stages into `cur`)
+  }
+}
+#endif
+
 template <int A, int B>
 HD void reg_z_to_cube(const SphereTablesX& T, const cplx* __restrict__ tw, const cplx* __restrict__ W2,
                       cplx* __restrict__ cube, double scale, int L_rt, int Lp_rt, cplx* sm, Dim3i bid) {

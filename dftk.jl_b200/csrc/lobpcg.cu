@@ -1485,6 +1485,75 @@ void random_orbitals_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx*
   run_batched(ctx, L, bodies);
 }
 
+// Per-band kinetic and nonlocal energies of ALL k-blocks of a rank in four launches and one synchronisation
+// (dftk_b200_band_energies does the same for one block): ekin / enl are n x ld_out host arrays.
+void band_energies_multi(int64_t n, dftk_b200_kblock* const* kbs, const cplx* const* psi, const int* n_bands, int64_t ld_out,
+                         double* ekin_host, double* enl_host) {
+  if (n <= 0) return;
+  dftk_b200_ctx* ctx = kbs[0]->grid->ctx;
+  BatchExec exec(ctx);
+  if (ctx->small_counter.cap < (size_t)std::max<int64_t>(n, 256)) {
+    ctx->small_counter.ensure(std::max<size_t>((size_t)n, 256));
+    CUDA_CHECK(cudaMemsetAsync(ctx->small_counter.p, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));
+  }
+  std::vector<KinDotsItem> kd;
+  std::vector<GramItem> gr;
+  std::vector<NlEnergyItem> ne;
+  std::vector<GatherItem> ga;
+  size_t used = 0;
+  std::vector<std::pair<double*, std::pair<size_t, int>>> scatter;
+  int max_cols = 1;
+  for (int64_t i = 0; i < n; ++i) {
+    dftk_b200_kblock* kb = kbs[i];
+    const int nb = n_bands[i];
+    REQUIRE(kb && kb->grid->ctx == ctx && nb >= 0 && nb <= ld_out, "band_energies_multi: bad block");
+    if (nb == 0) continue;
+    REQUIRE(nb <= SMALL_MAX_N && kb->n_proj <= SMALL_MAX_COLS, "band_energies_multi: block too large for the batched path");
+    double* sc = kb->scal.ensure(2 * SMALL_MAX_N + 8);
+    max_cols = std::max(max_cols, nb);
+    if (ekin_host) {
+      REQUIRE(kb->has_kin, "band_energies: no kinetic term");
+      kd.push_back(KinDotsItem{psi[i], (long long)kb->n_pw, (long long)kb->n_pw, nb, kb->kin.p, sc});
+      ga.push_back(GatherItem{sc, nb, (int)used});
+      scatter.push_back({ekin_host + i * ld_out, {used, nb}});
+      used += nb;
+    }
+    if (enl_host) {
+      if (kb->n_proj == 0) {
+        for (int b = 0; b < nb; ++b) enl_host[i * ld_out + b] = 0.0;
+      } else {
+        cplx* proj = kb->proj.ensure((size_t)2 * kb->n_proj * SMALL_MAX_N);
+        GramItem g{};
+        g.A.n = g.B.n = 1;
+        g.A.p[0] = kb->P.p; g.A.ld[0] = kb->n_pw; g.A.cols[0] = (int)kb->n_proj;
+        g.B.p[0] = psi[i]; g.B.ld[0] = kb->n_pw; g.B.cols[0] = nb;
+        for (int q = 1; q < 4; ++q) { g.A.start[q] = (int)kb->n_proj; g.B.start[q] = nb; }
+        g.n_rows = kb->n_pw;
+        BatchExec::small_gram_geometry(ctx, kb->n_pw, &g.n_ctas, &g.rows_per_cta);
+        g.C = proj;
+        g.ldc = kb->n_proj;
+        gr.push_back(g);
+        ne.push_back(NlEnergyItem{proj, kb->Dc.p, (int)kb->n_proj, nb, sc + SMALL_MAX_N});
+        ga.push_back(GatherItem{sc + SMALL_MAX_N, nb, (int)used});
+        scatter.push_back({enl_host + i * ld_out, {used, nb}});
+        used += nb;
+      }
+    }
+  }
+  REQUIRE(used <= exec.gather_cap, "band_energies_multi: gather buffer too small");
+  if (!kd.empty()) LAUNCH(ctx, kb_kin_dots, dim3((unsigned)max_cols, (unsigned)kd.size()), 256, 0, exec.upload(kd));
+  if (!gr.empty()) {
+    exec.gram_batch(gr);
+    LAUNCH(ctx, kb_nl_energy, (unsigned)ne.size(), 64, 0, exec.upload(ne));
+  }
+  if (!ga.empty()) {
+    LAUNCH(ctx, kb_gather, (unsigned)ga.size(), 64, 0, exec.upload(ga), ctx->batch_gather.p);
+    CUDA_CHECK(cudaMemcpyAsync(exec.gather_h, ctx->batch_gather.p, used * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  for (auto& sct : scatter) memcpy(sct.first, exec.gather_h + sct.second.first, sct.second.second * sizeof(double));
+}
+
 // C (nA x nB, host, column-major) = A' B for tall column-major blocks (n_rows >> nA, nB <= SMALL_MAX_COLS): one fused launch
 // (CTA partials + last-CTA reduction, lobpcg_small.cuh).  Used by the host driver for the history dot products of Anderson
 // mixing (src/scf/anderson.jl:81-130) instead of a QR factorisation of the N_fft x m history matrix.

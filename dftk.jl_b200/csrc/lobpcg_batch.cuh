@@ -31,6 +31,8 @@ struct StatsItem { const cplx* A; long long ld; int n_rows, n_cols; double* stat
 struct RandnItem { cplx* x; long long n_rows; unsigned long long seed; };
 struct LambdaItem { const cplx* X; const cplx* AX; long long ld, n_rows; int n_cols; double* lam; };
 struct GatherItem { const double* src; int n; int offset; };
+struct KinDotsItem { const cplx* X; long long ld, n_rows; int n_cols; const double* kin; double* out; };
+struct NlEnergyItem { const cplx* proj; const cplx* D; int np, nb; double* out; };
 
 extern __shared__ __align__(16) unsigned char batch_dyn_smem[];
 
@@ -260,6 +262,40 @@ __global__ void __launch_bounds__(256) kb_randn_col(const RandnItem* __restrict_
     const double u2 = (b >> 11) * (1.0 / 9007199254740992.0);
     const double r = sqrt(-2.0 * log(u1));
     it.x[i] = make_double2(r * cospi(2.0 * u2) * 0.70710678118654752, r * sinpi(2.0 * u2) * 0.70710678118654752);
+  }
+}
+
+// <x_n|kin|x_n> per band (ene_ops(::TermKinetic), src/terms/kinetic.jl:40-57); one CTA per (band, item)
+__global__ void __launch_bounds__(256) kb_kin_dots(const KinDotsItem* __restrict__ items) {
+  const KinDotsItem it = items[blockIdx.y];
+  const int col = blockIdx.x;
+  if (col >= it.n_cols) return;
+  const cplx* x = it.X + it.ld * col;
+  double s = 0.0, z = 0.0;
+  for (long long i = threadIdx.x; i < it.n_rows; i += blockDim.x) {
+    const cplx v = x[i];
+    s += it.kin[i] * (v.x * v.x + v.y * v.y);
+  }
+  block_sum2(s, z);
+  if (threadIdx.x == 0) it.out[col] = s;
+}
+// <psi_n|P D P'|psi_n> = Re sum_ij conj(proj_in) D_ij proj_jn per band (ene_ops(::TermAtomicNonlocal), nonlocal.jl:31-47)
+__global__ void __launch_bounds__(64) kb_nl_energy(const NlEnergyItem* __restrict__ items) {
+  const NlEnergyItem it = items[blockIdx.x];
+  for (int b = threadIdx.x; b < it.nb; b += blockDim.x) {
+    const cplx* p = it.proj + (long long)it.np * b;
+    double e = 0.0;
+    for (int j = 0; j < it.np; ++j) {
+      const cplx pj = p[j];
+      double sx = 0.0, sy = 0.0;               // (D p)_... accumulated as conj(p_i) D_ij, D real symmetric stored complex
+      for (int i = 0; i < it.np; ++i) {
+        const double d = it.D[i + (long long)it.np * j].x;
+        sx += d * p[i].x;
+        sy += d * p[i].y;
+      }
+      e += sx * pj.x + sy * pj.y;
+    }
+    it.out[b] = e;
   }
 }
 

@@ -10,7 +10,8 @@ struct SphereTablesX;
 struct RegKernels {
   int A, B, T;
   const void *sphere_to_x, *y_backward, *z_apply, *z_to_cube, *z_from_cube, *z_density, *y_forward, *x_to_sphere;
-  const void *m_sphere_to_x, *m_y_backward, *m_z_apply, *m_y_forward, *m_x_to_sphere;   // many k-blocks per launch
+  const void* z_apply_pipe;   // persistent, software-pipelined form of z_apply (cp.async staged input tiles)
+  const void *m_sphere_to_x, *m_y_backward, *m_z_apply, *m_y_forward, *m_x_to_sphere, *m_z_density;   // many k-blocks per launch
 };
 // one k-block's share of a batched H-apply launch (local + kinetic part)
 struct FftMultiItem {
@@ -22,6 +23,8 @@ struct FftMultiItem {
   cplx* out;
   long long ldout;
   const double* kin;
+  const double* wts;     // density accumulation: band weights of this block (device) and their number
+  int nb;
 };
 const RegKernels* reg_kernels_for(int n);   // nullptr: use the generic Stockham engine
 void reg_set_attributes();
@@ -37,6 +40,8 @@ struct dftk_b200_grid {
   dftk::DevBuf<double> twx, twy, twz;
   int Lx, Ly, Lz;
   const dftk::RegKernels *rx = nullptr, *ry = nullptr, *rz = nullptr;  // register engine per axis
+  dftk::DevBuf<double> Vs[2];   // total local potential per spin (pre-scaled by 1/N), shared by the k-blocks that opt in
+  bool has_Vs[2] = {false, false};
 };
 
 struct dftk_b200_kblock {
@@ -56,6 +61,8 @@ struct dftk_b200_kblock {
   dftk::DevBuf<dftk::cplx> PD;    // P D (n_pw x n_proj), kept when n_proj is small: Hψ += (P D)(P'ψ) as two batched small products
   dftk::DevBuf<double> V;         // N, pre-scaled by 1/N (fft_norm*ifft_norm)
   bool has_V = false;
+  int grid_V = -1;                // >= 0: use grid->Vs[grid_V] instead of the block's own copy
+  const double* Vp() const { return grid_V >= 0 ? grid->Vs[grid_V].p : V.p; }
   // scratch
   dftk::DevBuf<dftk::cplx> W1, W2;    // pruned intermediates for a chunk of bands
   dftk::DevBuf<dftk::cplx> proj;      // n_proj x n_bands (+ D*proj)
@@ -82,6 +89,10 @@ void kb_sphere_to_real(dftk_b200_kblock* kb, const cplx* psi, cplx* cube, int64_
 void kb_real_to_sphere(dftk_b200_kblock* kb, const cplx* cube, cplx* out, int64_t n_bands, double scale);
 void kb_density_accumulate(dftk_b200_kblock* kb, const cplx* psi, const double* occ_w_host,
                            int64_t n_bands, double* rho);
+// all k-blocks of a rank: stages A, B batched over the blocks, one accumulation launch per spin channel;
+// rho: n_spin x N (device), occ_w_host: n x ld_w.  Returns false (nothing done) when the blocks do not qualify.
+bool kb_density_accumulate_multi(int n, dftk_b200_kblock* const* kbs, const cplx* const* psi, const double* occ_w_host,
+                                 int64_t ld_w, const int* n_bands, double* rho);
 void fft_set_attributes();
 // blas.cu
 void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx alpha, const cplx* A,
@@ -116,6 +127,10 @@ void kb_nonlocal_force_rows(dftk_b200_kblock* kb, const cplx* psi, const double*
                             const double* gpk, double* out_host);
 void ewald(dftk_b200_ctx* ctx, const double* lattice_colmajor, int n_atoms, const double* charges, const double* positions,
            double eta, const int* glims, const int* rlims, double* energy_host, double* forces_host);
+// setup.cu
+void structure_factor(dftk_b200_grid* g, int n_atoms, const double* pos_host, const double* coeff_host, cplx* out);
+void build_projectors(dftk_b200_ctx* ctx, int64_t n_pw, const double* gpk, int n_atoms, const double* pos_host, int n_rows,
+                      const cplx* ff, cplx* P);
 // lobpcg.cu
 int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter, int maxiter,
                int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host,
@@ -124,6 +139,8 @@ int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const
                      int maxiter, int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter,
                      int64_t* n_matvec, int* converged);
 void random_orbitals_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, uint64_t seed);
+void band_energies_multi(int64_t n, dftk_b200_kblock* const* kbs, const cplx* const* psi, const int* n_bands, int64_t ld_out,
+                         double* ekin_host, double* enl_host);
 void tall_gram(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int nA, const cplx* B, int64_t ldb, int nB, int64_t n_rows,
                cplx* out_host);
 void lobpcg_set_attributes();

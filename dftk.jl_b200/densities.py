@@ -16,12 +16,15 @@ def compute_density(basis, psi, occupation, *, occupation_threshold=0.0, packed_
     rho = flat[:n_spin * basis.N].view(n_spin, basis.N)
     if n_tail:
         flat[n_spin * basis.N:] = torch.as_tensor(np.asarray(packed_sums, dtype=np.float64), device=dev)
-    for ik, kb in enumerate(basis.kblocks):
+    from .device import density_accumulate_multi
+    ws = []
+    for ik in range(len(basis.kblocks)):
         occ = np.asarray(occupation[ik], dtype=float)
         w = np.where(np.abs(occ) >= occupation_threshold, occ * basis.kweights[ik], 0.0)
         nb = int(np.max(np.nonzero(w)[0]) + 1) if np.any(w != 0) else 0
-        if nb:
-            kb.density_accumulate(psi[ik][:nb], w[:nb], rho[basis.kpoints[ik].spin])
+        ws.append(w[:nb])
+    # one library call for all blocks of this rank (rows psi[ik][:nb] are contiguous: a band is a row)
+    density_accumulate_multi(basis.kblocks, [p.contiguous() for p in psi], ws, rho)
     if basis.comm_kpts.nranks > 1:
         basis.comm_kpts.n_collectives += 1
         basis.architecture.ctx.allreduce(flat, "sum")          # mpi_sum!(ρ) of densities.jl:46 + the packed scalars

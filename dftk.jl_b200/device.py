@@ -134,6 +134,43 @@ def lobpcg_multi(kblocks, Xs, tol=1e-6, miniter=1, maxiter=100, n_conv_check=Non
                  converged=bool(conv[i])) for i in range(n)]
 
 
+def band_energies_multi(kblocks, psis):
+    """dftk_b200_band_energies_multi: per-band <psi|kin|psi> and <psi|P D P'|psi> of all k-blocks in one call.
+    Returns two lists of host arrays."""
+    n = len(kblocks)
+    if n == 0:
+        return [], []
+    ctx = kblocks[0].ctx
+    nbs = np.array([p.shape[0] for p in psis], dtype=np.int32)
+    ld = int(nbs.max())
+    if ld > 32 or any(kb.n_proj > 96 for kb in kblocks):
+        pairs = [kb.band_energies(p) for kb, p in zip(kblocks, psis)]
+        return [a for a, _ in pairs], [b for _, b in pairs]
+    kb_arr = (c_vp * n)(*[kb.h.value for kb in kblocks])
+    x_arr = (c_vp * n)(*[p.data_ptr() for p in psis])
+    ek, en = np.zeros((n, ld)), np.zeros((n, ld))
+    check(ctx.L.dftk_b200_band_energies_multi(n, kb_arr, x_arr, _ptr(nbs), ld, _ptr(ek), _ptr(en)), ctx.h)
+    return [ek[i, :nbs[i]].copy() for i in range(n)], [en[i, :nbs[i]].copy() for i in range(n)]
+
+
+def density_accumulate_multi(kblocks, psis, weights, rho):
+    """dftk_b200_density_accumulate_multi: rho (n_spin, N) += Σ_blocks Σ_n w_n |IFFT psi_n|² / Ω, each block into the channel
+    of its spin.  psis[i]: (nb_i, n_pw_i) contiguous device tensors, weights[i]: nb_i host numbers."""
+    n = len(kblocks)
+    if n == 0:
+        return rho
+    ctx = kblocks[0].ctx
+    nbs = np.array([len(w) for w in weights], dtype=np.int32)
+    ld = max(1, int(nbs.max()))
+    w = np.zeros((n, ld))
+    for i, wi in enumerate(weights):
+        w[i, :len(wi)] = wi
+    kb_arr = (c_vp * n)(*[kb.h.value for kb in kblocks])
+    x_arr = (c_vp * n)(*[p.data_ptr() for p in psis])
+    check(ctx.L.dftk_b200_density_accumulate_multi(n, kb_arr, x_arr, _ptr(w), ld, _ptr(nbs), _ptr(rho)), ctx.h)
+    return rho
+
+
 def random_orbitals_multi(kblocks, n_bands, seed):
     """dftk_b200_random_orbitals: orthonormal random start vectors (n_bands, n_pw_i) for a list of k-blocks."""
     n = len(kblocks)
@@ -157,6 +194,18 @@ class FFTGrid:
         h = c_vp()
         check(ctx.L.dftk_b200_grid_create(ctx.h, *self.fft_size, float(unit_cell_volume), ctypes.byref(h)), ctx.h)
         self.h = h
+
+    def set_potential(self, spin, V):
+        """One pre-scaled copy of the total local potential per spin channel, shared by the k-blocks that opt in
+        (KBlock.use_grid_potential).  Re-installing the tensor the grid already holds is free."""
+        ref = getattr(self, "_pot_ref", None)
+        if ref is None:
+            ref = self._pot_ref = {}
+        cur = ref.get(spin)
+        if cur is not None and cur[0] is V and cur[1] == V._version:
+            return
+        ref[spin] = (V, V._version)
+        check(self.ctx.L.dftk_b200_grid_set_potential(self.h, int(spin), _ptr(V)), self.ctx.h)
 
     def fft_cube(self, data, direction):
         """In-place unnormalised transform of (batch, N) complex data; -1 forward, +1 backward."""
@@ -204,7 +253,15 @@ class KBlock:
             self._pot_ref, self._pot_version = V, V._version
         else:
             self._pot_ref = None
+        self._grid_pot = None
         check(self.ctx.L.dftk_b200_kblock_set_potential(self.h, _ptr(V)), self.ctx.h)
+
+    def use_grid_potential(self, spin):
+        """Use the grid's shared potential of `spin` (FFTGrid.set_potential) instead of a per-block copy."""
+        if getattr(self, "_grid_pot", None) != spin:
+            check(self.ctx.L.dftk_b200_kblock_use_grid_potential(self.h, int(spin)), self.ctx.h)
+            self._grid_pot = spin
+            self._pot_ref = None
 
     def _new(self, nb):
         return torch.empty((nb, self.n_pw), dtype=torch.complex128, device=self.ctx.device)

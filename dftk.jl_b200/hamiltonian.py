@@ -50,7 +50,12 @@ class DftHamiltonianBlock:
         reference: several may be alive at once (scfres.ham, info.ham of a callback, ham(ρ1) vs ham(ρ2)), so the
         potential travels with the block and is (re)installed before every device call; the k-block skips the copy
         when it already holds this very tensor."""
-        self.kblock.set_potential(self.local_op.potential if self.local_op is not None else None)
+        if self.local_op is None:
+            self.kblock.set_potential(None)
+        else:
+            # all blocks of a spin channel share the summed potential: one device copy per (grid, spin)
+            self.kblock.grid.set_potential(self.kpoint.spin, self.local_op.potential)
+            self.kblock.use_grid_potential(self.kpoint.spin)
         return self.kblock
 
     @property
@@ -86,6 +91,8 @@ def ksum_energy_partials(basis, psi, occupation, eigenvalues, eF):
     names = [n for n in KSUM_TERMS if basis.term(n) is not None]
     basis._be_cache = {}
     try:
+        from .terms import prefetch_band_energies
+        prefetch_band_energies(basis, psi)
         vals = [basis.term(n).local_energy(basis, psi, occupation, eigenvalues=eigenvalues, eF=eF) for n in names]
     finally:
         basis._be_cache = None

@@ -92,6 +92,17 @@ def _band_energies_shared(basis, ik, psik):
     return cache[ik]
 
 
+def prefetch_band_energies(basis, psi):
+    """All k-blocks of this rank in ONE library call (dftk_b200_band_energies_multi) into the evaluation's cache."""
+    cache = getattr(basis, "_be_cache", None)
+    if cache is None or basis.term("Kinetic") is None or basis.term("AtomicNonlocal") is None or len(cache):
+        return
+    from .device import band_energies_multi
+    ek, en = band_energies_multi(basis.kblocks, [p.contiguous() for p in psi])
+    for ik in range(len(basis.kblocks)):
+        cache[ik] = (ek[ik], en[ik])
+
+
 class TermAtomicLocal:
     """local.jl:108-138: V(G) = sum_atoms e^{-iG·r} v_loc(|G|)/sqrt(Ω), real-space via our own FFT."""
 
@@ -102,12 +113,7 @@ class TermAtomicLocal:
         pot = torch.zeros(basis.N, dtype=torch.complex128, device=pn.device)
         for group in model.atom_groups:
             ff = model.atoms[group[0]].psp.eval_psp_local_fourier(pn)
-            pos = torch.as_tensor(np.array([model.positions[i] for i in group]), device=pn.device)
-            # structure factor summed over the atoms of the group, in chunks to bound memory
-            sf = torch.zeros(basis.N, dtype=torch.complex128, device=pn.device)
-            for c in range(0, len(group), 16):
-                ph = -2 * math.pi * (Gf @ pos[c:c + 16].T)
-                sf += torch.polar(torch.ones_like(ph), ph).sum(dim=1)
+            sf = structure_factor(basis, [model.positions[i] for i in group])     # Σ_a e^{-2πi G·r_a}, one kernel
             pot += sf * ff / math.sqrt(model.unit_cell_volume)
         self.potential_values = basis.irfft(basis.enforce_real(pot)).reshape(-1)
 
@@ -115,6 +121,19 @@ class TermAtomicLocal:
         ops = [RealSpaceMultiplication(basis, k, self.potential_values) for k in basis.kpoints]
         E = math.inf if rho is None else float((rho.sum(dim=0) * self.potential_values).sum() * basis.dvol)
         return E, ops
+
+
+def structure_factor(basis, positions, coefficients=None):
+    """Σ_a c_a exp(-2πi G·r_a) on the whole FFT cube: one fused kernel over (cube point, atom)
+    (dftk_b200_structure_factor) instead of chunked N × n_atoms phase tables."""
+    from ._lib import check
+    from .device import _ptr
+    ctx = basis.architecture.ctx
+    pos = np.ascontiguousarray(np.array([np.asarray(p, dtype=np.float64) for p in positions]))
+    cf = None if coefficients is None else np.ascontiguousarray(coefficients, dtype=np.float64)
+    out = torch.empty(basis.N, dtype=torch.complex128, device=ctx.device)
+    check(ctx.L.dftk_b200_structure_factor(basis.fft_grid.h, len(pos), _ptr(pos), _ptr(cf), _ptr(out)), ctx.h)
+    return out
 
 
 def build_projection_coefficients(psp):
@@ -156,16 +175,26 @@ class TermAtomicNonlocal:
             if key not in cache:
                 Gpk = basis.Gplusk_vectors(kpt)
                 Gpk_cart = basis.Gplusk_vectors_cart(kpt)
-                blocks, Ds = [], []
+                from ._lib import check
+                from .device import _ptr
+                ctx = basis.architecture.ctx
+                Ds = []
+                n_rows_total = sum(len(g) * model.atoms[g[0]].psp.count_n_proj() for g in model.atom_groups)
+                P = torch.empty((n_rows_total, kpt.n_G), dtype=torch.complex128, device=Gpk.device) if n_rows_total else None
+                gpk_t = Gpk.T.contiguous()                               # (3, n_pw) reduced G+k, component-major
+                row = 0
                 for group in model.atom_groups:
                     psp = model.atoms[group[0]].psp
-                    ff = build_projector_form_factors(psp, Gpk_cart) / math.sqrt(model.unit_cell_volume)
+                    ff = (build_projector_form_factors(psp, Gpk_cart) / math.sqrt(model.unit_cell_volume)).contiguous()
                     Dat = build_projection_coefficients(psp)
-                    for ia in group:
-                        ph = -2 * math.pi * (Gpk @ torch.as_tensor(model.positions[ia], device=Gpk.device))
-                        blocks.append(torch.polar(torch.ones_like(ph), ph)[None, :] * ff)
-                        Ds.append(Dat)
-                P = torch.cat(blocks, dim=0).contiguous() if blocks else None
+                    nr = ff.shape[0]
+                    if nr:
+                        # P[(a, p), G] = e^{-2πi (G+k)·r_a} ff[p, G] for all atoms of the species: one fused kernel
+                        pos = np.ascontiguousarray(np.array([model.positions[ia] for ia in group], dtype=np.float64))
+                        check(ctx.L.dftk_b200_build_projectors(ctx.h, kpt.n_G, _ptr(gpk_t), len(group), _ptr(pos), nr, _ptr(ff),
+                                                               _ptr(P[row:row + nr * len(group)])), ctx.h)
+                        row += nr * len(group)
+                    Ds += [Dat] * len(group)
                 n = sum(d.shape[0] for d in Ds)
                 D = np.zeros((n, n))
                 o = 0
@@ -401,12 +430,8 @@ def guess_density(basis, magnetic_moments=None):
             a0 = model.atoms[group[0]]
             L = atom_decay_length(a0.n_elec_core(), a0.n_elec_valence())
             ff = a0.charge_ionic() * torch.exp(-(pn * L) ** 2)
-            for c in range(0, len(group), 16):
-                idx = group[c:c + 16]
-                pos = torch.as_tensor(np.array([model.positions[i] for i in idx]), device=pn.device)
-                cf = torch.as_tensor([coeffs[i] for i in idx], device=pn.device, dtype=torch.float64)
-                ph = -2 * math.pi * (Gf @ pos.T)
-                rho += (torch.polar(torch.ones_like(ph), ph) * cf[None, :]).sum(dim=1) * ff / math.sqrt(model.unit_cell_volume)
+            sf = structure_factor(basis, [model.positions[i] for i in group], [coeffs[i] for i in group])
+            rho += sf * ff / math.sqrt(model.unit_cell_volume)
         return basis.irfft(basis.enforce_real(rho)).reshape(-1)
 
     rtot = superposition([1.0] * len(model.atoms))

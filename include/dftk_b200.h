@@ -87,6 +87,12 @@ int dftk_b200_kblock_destroy(dftk_b200_kblock* kb);
  * RealSpaceMultiplication operators, src/terms/operators.jl:213-222); N_fft doubles.  NULL = none */
 int dftk_b200_kblock_set_potential(dftk_b200_kblock* kb, const double* V);
 
+/* The same potential for all k-blocks of one spin channel: ONE pre-scaled copy per (grid, spin) instead of one per block
+ * (all blocks of a spin share the term potentials, src/terms/Hamiltonian.jl:200-227).  A block opts in with
+ * dftk_b200_kblock_use_grid_potential(kb, spin) (spin = -1: back to its own copy). */
+int dftk_b200_grid_set_potential(dftk_b200_grid* grid, int spin, const double* V);
+int dftk_b200_kblock_use_grid_potential(dftk_b200_kblock* kb, int spin);
+
 /* ---- sphere <-> real-space transforms (ifft!/fft! with Gvec_mapping, src/fft.jl:110-122,162-172) */
 int dftk_b200_fft_sphere_to_real(dftk_b200_kblock* kb, const void* psi /*n_pw×n_bands*/,
                                  void* out_real /*N_fft×n_bands complex*/, int64_t n_bands,
@@ -105,6 +111,11 @@ int dftk_b200_apply_terms(dftk_b200_kblock* kb, const void* psi, void* hpsi, int
 /* per-band <psi|kin|psi> and <psi|P D P'|psi> (ene_ops, kinetic.jl:40-57, nonlocal.jl:31-47); host out */
 int dftk_b200_band_energies(dftk_b200_kblock* kb, const void* psi, int64_t n_bands,
                             double* ekin_host, double* enl_host);
+
+/* the same for all k-blocks of a rank in four launches and ONE synchronisation (blocks of <= 32 bands and <= 96 projectors);
+ * ekin_host / enl_host: n_blocks × ld_out, either may be NULL */
+int dftk_b200_band_energies_multi(int64_t n_blocks, dftk_b200_kblock* const* kblocks, const void* const* psi,
+                                  const int32_t* n_bands, int64_t ld_out, double* ekin_host, double* enl_host);
 
 /* ---- LOBPCG (lobpcg_hyper, src/eigen/diag_lobpcg_hyper.jl:5-18 -> LOBPCG,
  *      src/eigen/lobpcg_hyper_impl.jl:354-582, PreconditionerTPA src/eigen/preconditioners.jl:27-78) ----
@@ -132,6 +143,12 @@ int dftk_b200_random_orbitals(int64_t n_blocks, dftk_b200_kblock* const* kblocks
  *      rho[:,:,:] += sum_n occ_w[n] |IFFT psi_n|² / Ω   with occ_w[n] = occupation·kweight (host) ---- */
 int dftk_b200_density_accumulate(dftk_b200_kblock* kb, const void* psi, const double* occ_w_host,
                                  int64_t n_bands, double* rho /*dev: N_fft doubles of this spin*/);
+
+/* compute_density's loop over the k-blocks of a rank in one call: rho (n_spin × N_fft, device) += contributions of all
+ * blocks (each into the channel of its spin); occ_w_host: n_blocks × ld_w.  Blocks that share the grid's register FFT engine
+ * are transformed together (two launches for all of them) and accumulated by one launch per spin channel. */
+int dftk_b200_density_accumulate_multi(int64_t n_blocks, dftk_b200_kblock* const* kblocks, const void* const* psi,
+                                       const double* occ_w_host, int64_t ld_w, const int32_t* n_bands, double* rho);
 
 /* ---- collectives (mpi_sum!/mpi_min/mpi_max over basis.comm_kpts, src/common/mpi.jl:19-31) ---- */
 int dftk_b200_allreduce(dftk_b200_ctx* ctx, void* buf /*dev*/, int64_t count, int dtype,
@@ -172,6 +189,18 @@ int dftk_b200_nonlocal_force_rows(dftk_b200_kblock* kb, const void* psi, const d
  * the caller's (ewald.jl:86-104).  energy_host: 1 double (Hartree); forces_host: 3·n_atoms, reduced coordinates; either NULL. */
 int dftk_b200_ewald(dftk_b200_ctx* ctx, const double* lattice, int n_atoms, const double* charges, const double* positions,
                     double eta, const int32_t* glims, const int32_t* rlims, double* energy_host, double* forces_host);
+
+/* ---- setup kernels: the O(n_atoms × N) structure-factor work before the first SCF step ----
+ * out[G] = Σ_a c_a exp(-2πi G·r_a) on the whole FFT cube (G from the cube index, src/fft.jl:24-31): the atomic sums of
+ * build_local_potential (src/terms/local.jl:108-138) and guess_density (src/density_methods.jl:103-181).
+ * positions: 3·n_atoms fractional (host), coefficients: n_atoms (host) or NULL = 1, out: N_fft complex (device). */
+int dftk_b200_structure_factor(dftk_b200_grid* grid, int n_atoms, const double* positions, const double* coefficients, void* out);
+/* P[(a, p), G] = exp(-2πi (G+k)·r_a) · ff[p, G]: the projector table of one species for one k-block
+ * (build_projection_vectors, src/terms/nonlocal.jl:166-199).  gpk: 3 × n_pw reduced G+k, component-major (device);
+ * positions: 3·n_atoms (host); form_factors: n_rows × n_pw complex, row = projector (l, m, i) already divided by sqrt(Ω)
+ * (device); P: (n_atoms·n_rows) × n_pw complex, i.e. the column-major n_pw × n_proj block of these atoms (device). */
+int dftk_b200_build_projectors(dftk_b200_ctx* ctx, int64_t n_pw, const double* gpk, int n_atoms, const double* positions,
+                               int n_rows, const void* form_factors, void* P);
 
 /* ---- small dense helpers used by the host driver (columnwise_dots, src/common/linalg.jl:2-15) ---- */
 int dftk_b200_columnwise_dots(dftk_b200_ctx* ctx, const void* A, const void* B, int64_t n_rows,

@@ -50,4 +50,24 @@ with open(f"profiles/ncu_full_{tag}.csv", "w") as f:
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace(", ", "x")
         f.write(name + "," + ",".join(r[idx[w]].replace(",", "") for w in want) + "\n")
+# measured DRAM traffic of the Hpsi-local kernel group per band (bench.py reports it as roofline.traffic): the capture runs
+# M_FULL bands in one chunk, one launch of each of the five pipeline kernels
+import json
+import os
+m_full = int(os.environ.get("M_FULL", 51))
+group = ("kr_sphere_to_x", "kr_y_backward", "kr_z_apply", "kr_y_forward", "kr_x_to_sphere")
+seen, total = set(), 0.0
+for r in rows[2:]:
+    name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("dftk::", "").split("<")[0]
+    if name in group and name not in seen:
+        seen.add(name)
+        def val(col):
+            v = float(r[idx[col]].replace(",", ""))
+            return v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[idx[col]]]
+        total += val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+if len(seen) == len(group):
+    json.dump(dict(hpsi_local_dram_bytes_per_band=total / m_full, bands_per_launch=m_full, kernels=list(group),
+                   source=f"profiles/ncu_full_{tag}.csv (dram__bytes_read.sum + dram__bytes_write.sum of one launch of each of the five "
+                          f"kernels at {m_full} bands, ncu --set full --clock-control none)"),
+              open("profiles/ncu_traffic.json", "w"), indent=1)
 print(open(f"profiles/launches_{tag}.csv").read())
