@@ -120,6 +120,7 @@ static int ctx_create_common(int device, dftk_b200_ctx** out) {
   reg_set_attributes();
   blas_set_attributes();
   i8tc_set_attributes();
+  i8tc2_set_attributes();
   lobpcg_set_attributes();
   *out = c;
   return 0;
@@ -225,6 +226,7 @@ int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
   else if (n == "band_chunk") ctx->band_chunk = (int)value;
   else if (n == "gemm_stages") ctx->gemm_stages = (value == 3 ? 3 : 2);
   else if (n == "small_dense") ctx->small_dense = (int)value;
+  else if (n == "i8_min_rows") ctx->i8_min_rows = value;
   else if (n == "z_pipeline") ctx->z_pipeline = (int)value;
   else if (n == "force_svd_fallback") ctx->force_svd_fallback = (int)value;
   else if (n == "fft_engine") ctx->fft_engine = (int)value;  // 0 = register two-pass where available, 1 = generic

@@ -387,9 +387,9 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
     ctx->launches++;
     return;
   }
-  if ((ctx->gemm_backend == 2 || ctx->gemm_backend == 3) && transA == 2 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.x == 0.0 && beta.y == 0.0) {
+  if ((ctx->gemm_backend == 2 || ctx->gemm_backend == 3 || (ctx->gemm_backend == 4 && k >= ctx->i8_min_rows && m >= 32 && n >= 32)) && transA == 2 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.x == 0.0 && beta.y == 0.0) {
     // experimental: FP64 by INT8 residues + CRT (i8emu.cu; reference pipeline, groundwork for a tcgen05 kind::i8 kernel)
-    zgemm_i8_cn(ctx, m, n, k, A, lda, B, ldb, C, ldc, ctx->gemm_backend == 3);
+    zgemm_i8_cn(ctx, m, n, k, A, lda, B, ldb, C, ldc, ctx->gemm_backend - 2);
     return;
   }
   if (ctx->gemm_backend == 2 && transA == 0 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.y == 0.0 &&
@@ -452,7 +452,16 @@ void kb_apply_nonlocal(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_
   cplx* proj = kb->proj.ensure((size_t)2 * np * n_bands);
   cplx* dproj = proj + (size_t)np * n_bands;
   const cplx one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
-  zgemm(ctx, 2, np, n_bands, kb->n_pw, one, kb->P.p, kb->n_pw, psi, kb->n_pw, zero, proj, np);
+  if (ctx->gemm_backend == 4 && np >= 64 && n_bands >= 64 && kb->n_pw >= ctx->i8_min_rows) {
+    // P' psi on the INT8 tensor cores (tcgen05.mma.kind::i8, TMA-fed; i8tc2.cu) with the residue planes of P cached per k-block
+    if (!kb->i8_P) {
+      int n_mod = 0;
+      i8_build_planes(ctx, kb->P.p, kb->n_pw, np, kb->n_pw, &kb->i8_P, &kb->i8_eP, kb->i8_planes, kb->i8_exps, &n_mod);
+    }
+    zgemm_i8_cn(ctx, np, n_bands, kb->n_pw, kb->P.p, kb->n_pw, psi, kb->n_pw, proj, np, 2, kb->i8_P, kb->i8_eP);
+  } else {
+    zgemm(ctx, 2, np, n_bands, kb->n_pw, one, kb->P.p, kb->n_pw, psi, kb->n_pw, zero, proj, np);
+  }
   zgemm(ctx, 0, np, n_bands, np, one, kb->Dc.p, np, proj, np, zero, dproj, np);
   zgemm(ctx, 0, kb->n_pw, n_bands, np, one, kb->P.p, kb->n_pw, dproj, np, one, hpsi, kb->n_pw);
 }

@@ -5,7 +5,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["fft.cu", "blas.cu", "lobpcg.cu", "api.cu", "xc.cu", "forces.cu", "setup.cu", "i8emu.cu", "i8tc.cu"]
+SOURCES = ["fft.cu", "blas.cu", "lobpcg.cu", "api.cu", "xc.cu", "forces.cu", "setup.cu", "i8emu.cu", "i8tc.cu", "i8tc2.cu"]
 REG_NGROUPS = 4
 HEADERS = ["common.cuh", "structs.cuh", "fft_core.cuh", "fft_plan.h", "fft_reg.cuh", "fft_reg_fwd.cuh", "fft_reg.cu",
            "fft_radix_gen.cuh", "xc_core.cuh", "forces_core.cuh", "lobpcg_small.cuh", "lobpcg_batch.cuh", "i8emu_core.cuh", os.path.join("..", "..", "include", "dftk_b200.h")]

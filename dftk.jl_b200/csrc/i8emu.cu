@@ -47,6 +47,53 @@ k_i8_residues_ld(const cplx* __restrict__ X, int64_t ld, int64_t n_rows, int64_t
   i8_residues_entry(X[r + ld * col], e[col], n_mod, planes + (r + ldk * col), (long long)ldk * n_cols);
 }
 
+// The same planes four K entries per thread: the rounded operand a' (at most 55 bits + sign) is split into three 20-bit
+// limbs once, every residue is then a few 32-bit integer operations (limb * (2^20k mod p) summed, one remainder by a
+// constant) instead of six FP64 operations, and the four int8 residues of a plane leave as one 32-bit store (a warp writes
+// 128 contiguous bytes per plane instead of 32).  ldk % 4 == 0; rows [n_rows, ldk) of a column are zero padding.
+__device__ __forceinline__ void i8_limbs(double a, int& l0, int& l1, int& l2) {
+  long long v = (long long)a;                     // |a'| < 2^56: exact
+  const long long s = v >> 63;                    // limbs of |v| with the sign folded into each (C remainder semantics)
+  long long u = (v ^ s) - s;
+  const int sg = (int)(1 | s);
+  l0 = sg * (int)(u & 0xFFFFF);
+  l1 = sg * (int)((u >> 20) & 0xFFFFF);
+  l2 = sg * (int)(u >> 40);
+}
+__global__ void __launch_bounds__(256)
+k_i8_residues_ld4(const cplx* __restrict__ X, int64_t ld, int64_t n_rows, int64_t n_cols, int64_t ldk, const int* __restrict__ e,
+                  int n_mod, signed char* __restrict__ planes) {
+  const int64_t r4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t col = blockIdx.y;
+  if (r4 >= ldk) return;
+  const int ex = e[col];
+  int lr[4][3], li[4][3];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    cplx x = make_double2(0.0, 0.0);
+    if (r4 + q < n_rows) x = X[r4 + q + ld * col];
+    i8_limbs(rint(ldexp(x.x, ex)), lr[q][0], lr[q][1], lr[q][2]);
+    i8_limbs(rint(ldexp(x.y, ex)), li[q][0], li[q][1], li[q][2]);
+  }
+  const long long plane_stride = (long long)ldk * n_cols;
+  signed char* out = planes + (r4 + ldk * col);
+  for (int t = 0; t < n_mod; ++t) {
+    const int p = i8_modulus(t);
+    const int c1 = (1 << 20) % p, c2 = (int)((1ll << 40) % p);
+    unsigned wr = 0, wi = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // |l0 + l1 c1 + l2 c2| < 2^20 + 2^28 + 2^24: int32
+      const int rr = i8_sym(lr[q][0] + lr[q][1] * c1 + lr[q][2] * c2, p);
+      const int ri = i8_sym(li[q][0] + li[q][1] * c1 + li[q][2] * c2, p);
+      wr |= (unsigned)(rr & 0xFF) << (8 * q);
+      wi |= (unsigned)(ri & 0xFF) << (8 * q);
+    }
+    *reinterpret_cast<unsigned*>(out + (long long)(2 * t) * plane_stride) = wr;
+    *reinterpret_cast<unsigned*>(out + (long long)(2 * t + 1) * plane_stride) = wi;
+  }
+}
+
 // one warp per (i, j, t): residues of conj(a_i) . b_j modulo p_t;  res[(2 t + part)][j][i]
 __global__ void __launch_bounds__(256)
 k_i8_dot_ref(const signed char* __restrict__ ra, const signed char* __restrict__ rb, int64_t m, int64_t n, int64_t k,
@@ -153,8 +200,61 @@ static I8Tables tables_for(int64_t K) {
 }
 
 // C (m x n) = A^H B,  A: k x m, B: k x n (column-major, complex).  tensor_cores: integer products by k_i8_gemm_tc (i8tc.cu)
+// Residue planes + column exponents of an operand that does not change between calls (the projector table P of a k-block):
+// built once, reused by every later product with the same contraction length.
+void i8_build_planes(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int64_t m, int64_t k, signed char** planes_out, int** exps_out,
+                     DevBuf<signed char>& store, DevBuf<int>& estore, int* n_mod_out) {
+  const I8Tables T = tables_for(2 * k);
+  const int64_t ldk = (k + 127) / 128 * 128;
+  signed char* ra = store.ensure(2 * (size_t)T.n_mod * m * ldk + 16);
+  ra += (16 - ((uintptr_t)ra & 15)) & 15;
+  int* ea = estore.ensure((size_t)m);
+  LAUNCH(ctx, k_i8_col_exponent, (unsigned)m, 256, 0, A, lda, k, T.bits, ea);
+  LAUNCH(ctx, k_i8_residues_ld4, dim3((unsigned)((ldk / 4 + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, ldk, (const int*)ea, T.n_mod, ra);
+  *planes_out = ra;
+  *exps_out = ea;
+  *n_mod_out = T.n_mod;
+}
+
+// ---- prepared operands: an operand (a block of columns along the contraction index) is converted ONCE and then enters any
+//      number of products C = A^H B (the block Gram matrices of LOBPCG reuse every block three times)
+I8Operand i8_prepare(dftk_b200_ctx* ctx, const cplx* X, int64_t ld, int64_t cols, int64_t k, DevBuf<signed char>& store,
+                     DevBuf<int>& estore) {
+  I8Operand op;
+  const I8Tables T = tables_for(2 * k);
+  op.cols = cols;
+  op.k = k;
+  op.ldk = (k + 127) / 128 * 128;
+  op.n_mod = T.n_mod;
+  signed char* r = store.ensure(2 * (size_t)T.n_mod * cols * op.ldk + 16);
+  r += (16 - ((uintptr_t)r & 15)) & 15;
+  int* e = estore.ensure((size_t)cols);
+  LAUNCH(ctx, k_i8_col_exponent, (unsigned)cols, 256, 0, X, ld, k, T.bits, e);
+  LAUNCH(ctx, k_i8_residues_ld4, dim3((unsigned)((op.ldk / 4 + 255) / 256), (unsigned)cols), 256, 0, X, ld, k, cols, op.ldk, (const int*)e,
+         T.n_mod, r);
+  op.planes = r;
+  op.exps = e;
+  return op;
+}
+// C (A.cols x B.cols, leading dimension ldc) = A^H B from prepared operands: TMA-fed tcgen05.mma.kind::i8 products, chunk sums, CRT.
+// upper_only: tiles strictly below the diagonal are skipped (their entries of C are unspecified), as in the DMMA kernel.
+void i8_gram(dftk_b200_ctx* ctx, const I8Operand& A, const I8Operand& B, cplx* C, int64_t ldc, bool upper_only) {
+  REQUIRE(A.k == B.k && A.ldk == B.ldk && A.n_mod == B.n_mod, "i8_gram: operands prepared for different contraction lengths");
+  const int64_t m = A.cols, n = B.cols;
+  if (m == 0 || n == 0) return;
+  const I8Tables T = tables_for(2 * A.k);
+  const int n_chunks = (int)((A.ldk + I8_K_CHUNK - 1) / I8_K_CHUNK);
+  const size_t n_res = 2 * (size_t)T.n_mod * m * n;
+  char* ws = (char*)ctx->gemm_ws.ensure(n_res * sizeof(int) + n_res * n_chunks * sizeof(short) + 256);
+  int* res = (int*)ws;
+  short* part = (short*)(res + n_res);
+  i8tc2_products(ctx, A.planes, B.planes, m, n, A.ldk, T.n_mod, part, res, upper_only);
+  LAUNCH(ctx, k_i8_crt, (unsigned)((m * n + 127) / 128), 128, 0, (const int*)res, m, n, T, A.exps, B.exps, C, ldc, 0);
+}
+
 void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
-                 cplx* C, int64_t ldc, bool tensor_cores) {
+                 cplx* C, int64_t ldc, int tc_mode, const signed char* ra_cached, const int* ea_cached) {
+  const bool tensor_cores = tc_mode != 0;      // 1: cp.async-fed kernel (i8tc.cu), 2: TMA-fed kernel (i8tc2.cu)
   if (m == 0 || n == 0) return;
   REQUIRE(k >= 1 && m <= 65535 && n <= 65535, "zgemm_i8: unsupported shape");
   const I8Tables T = tables_for(2 * k);
@@ -162,25 +262,33 @@ void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx
   const int n_chunks = (int)((ldk + I8_K_CHUNK - 1) / I8_K_CHUNK);
   const size_t plane_a = (size_t)m * ldk, plane_b = (size_t)n * ldk;
   const size_t n_res = 2 * (size_t)T.n_mod * m * n;
-  const size_t bytes = (size_t)(m + n) * sizeof(int) + 64 + n_res * sizeof(int) + 2 * (size_t)T.n_mod * (plane_a + plane_b) + 256 +
+  const bool cached = ra_cached != nullptr && tensor_cores;
+  const size_t bytes = (size_t)(m + n) * sizeof(int) + 64 + n_res * sizeof(int) + 2 * (size_t)T.n_mod * ((cached ? 0 : plane_a) + plane_b) + 256 +
                        (tensor_cores ? n_res * n_chunks * sizeof(short) : 0);
   char* ws = (char*)ctx->gemm_ws.ensure(bytes);
   int* ea = (int*)ws;
   int* eb = ea + m;
   int* res = eb + n;
   signed char* ra = (signed char*)(res + n_res);
-  ra += (16 - ((uintptr_t)ra & 15)) & 15;                       // cp.async needs 16-byte aligned rows
-  signed char* rb = ra + 2 * (size_t)T.n_mod * plane_a;
+  ra += (16 - ((uintptr_t)ra & 15)) & 15;                       // cp.async / TMA need 16-byte aligned rows
+  signed char* rb = ra + (cached ? 0 : 2 * (size_t)T.n_mod * plane_a);
   short* part = (short*)(rb + 2 * (size_t)T.n_mod * plane_b);
-  LAUNCH(ctx, k_i8_col_exponent, (unsigned)m, 256, 0, A, lda, k, T.bits, ea);
+  if (cached) {
+    ra = const_cast<signed char*>(ra_cached);
+    ea = const_cast<int*>(ea_cached);
+  } else {
+    LAUNCH(ctx, k_i8_col_exponent, (unsigned)m, 256, 0, A, lda, k, T.bits, ea);
+  }
   LAUNCH(ctx, k_i8_col_exponent, (unsigned)n, 256, 0, B, ldb, k, T.bits, eb);
   if (tensor_cores) {
-    CUDA_CHECK(cudaMemsetAsync(ra, 0, 2 * (size_t)T.n_mod * (plane_a + plane_b), ctx->stream));      // zero K padding
-    LAUNCH(ctx, k_i8_residues_ld, dim3((unsigned)((k + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, ldk, (const int*)ea,
-           T.n_mod, ra);
-    LAUNCH(ctx, k_i8_residues_ld, dim3((unsigned)((k + 255) / 256), (unsigned)n), 256, 0, B, ldb, k, n, ldk, (const int*)eb,
+    // (the four-per-thread kernel writes the zero K padding itself)
+    if (!cached)
+      LAUNCH(ctx, k_i8_residues_ld4, dim3((unsigned)((ldk / 4 + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, ldk, (const int*)ea,
+             T.n_mod, ra);
+    LAUNCH(ctx, k_i8_residues_ld4, dim3((unsigned)((ldk / 4 + 255) / 256), (unsigned)n), 256, 0, B, ldb, k, n, ldk, (const int*)eb,
            T.n_mod, rb);
-    i8tc_products(ctx, ra, rb, m, n, ldk, T.n_mod, part, res);
+    if (tc_mode == 2) i8tc2_products(ctx, ra, rb, m, n, ldk, T.n_mod, part, res, false);
+    else i8tc_products(ctx, ra, rb, m, n, ldk, T.n_mod, part, res);
   } else {
     LAUNCH(ctx, k_i8_residues, dim3((unsigned)((k + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, (const int*)ea, T.n_mod, ra);
     LAUNCH(ctx, k_i8_residues, dim3((unsigned)((k + 255) / 256), (unsigned)n), 256, 0, B, ldb, k, n, (const int*)eb, T.n_mod, rb);

@@ -837,6 +837,38 @@ struct Lobpcg {
   // C = op(A)' * B accumulated over block lists (LazyHcat products, :90-137)
   void gram(const std::vector<Mat>& A, const std::vector<Mat>& B, cplx* C, int64_t ldc, bool upper_only) {
     if (small) return small_gram(A, B, C, ldc, upper_only);
+    if (ctx->gemm_backend == 4 && !A.empty() && A[0].rows >= ctx->i8_min_rows) {
+      // INT8 tensor cores (tcgen05.mma.kind::i8, TMA-fed; i8emu.cu / i8tc2.cu): every distinct block is converted to residue
+      // planes once and enters all its block products
+      bool ok = A.size() + B.size() <= 6;
+      for (auto& a : A) ok = ok && a.cols >= 32;
+      for (auto& b : B) ok = ok && b.cols >= 32;
+      if (ok) {
+        std::vector<I8Operand> opA(A.size()), opB(B.size());
+        int slot = 0;
+        for (size_t ia = 0; ia < A.size(); ++ia)
+          opA[ia] = i8_prepare(ctx, A[ia].p, A[ia].ld, A[ia].cols, A[ia].rows, kb->i8_pool[slot], kb->i8_epool[slot]), ++slot;
+        for (size_t ib = 0; ib < B.size(); ++ib) {
+          bool shared = false;
+          for (size_t ia = 0; ia < A.size() && !shared; ++ia)
+            if (A[ia].p == B[ib].p && A[ia].cols == B[ib].cols && A[ia].ld == B[ib].ld) {
+              opB[ib] = opA[ia];
+              shared = true;
+            }
+          if (!shared) opB[ib] = i8_prepare(ctx, B[ib].p, B[ib].ld, B[ib].cols, B[ib].rows, kb->i8_pool[slot], kb->i8_epool[slot]), ++slot;
+        }
+        int64_t oc = 0;
+        for (size_t ib = 0; ib < B.size(); ++ib) {
+          int64_t orow = 0;
+          for (size_t ia = 0; ia < A.size(); ++ia) {
+            if (!(upper_only && ib < ia)) i8_gram(ctx, opA[ia], opB[ib], C + orow + ldc * oc, ldc, upper_only && ia == ib);
+            orow += A[ia].cols;
+          }
+          oc += B[ib].cols;
+        }
+        return;
+      }
+    }
     const cplx one = make_double2(1, 0), zero = make_double2(0, 0);
     int64_t oc = 0;
     for (size_t ib = 0; ib < B.size(); ++ib) {

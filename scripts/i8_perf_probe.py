@@ -51,3 +51,24 @@ for name, m, n in SHAPES:
     torch.cuda.empty_cache()
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/i8_perf_probe.json", "w"), indent=1)
+
+# ---- the nonlocal term of a k-block (P' psi with cached residue planes of P under backend 4; P (D P'psi) stays on the DMMA kernel)
+if os.environ.get("NONLOCAL_APPLY", "1") == "1":
+    m, n = 1250, 503
+    g = torch.Generator(device=dev).manual_seed(1)
+    P = torch.view_as_complex(torch.randn(m, K, 2, generator=g, device=dev, dtype=torch.float64)) / np.sqrt(K)
+    grid = dftk_b200.FFTGrid(ctx, (192, 192, 192), 1000.0)
+    mapping = np.arange(K, dtype=np.int64)
+    kb = dftk_b200.KBlock(grid, mapping, kin=np.ones(K), P=P, D=np.diag(np.linspace(0.5, 1.5, m)))
+    psi = torch.view_as_complex(torch.randn(n, K, 2, generator=g, device=dev, dtype=torch.float64))
+    outs = {}
+    for backend in (0, 4):
+        ctx.set_option("gemm_backend", backend)
+        out = torch.zeros_like(psi)
+        t = timeit(lambda: kb.apply_terms(psi, 4, out=out), n=3)
+        outs[backend] = out.clone()
+        res[f"nonlocal_apply_backend{backend}"] = dict(ms=t, TFLOPs_equiv=16.0 * K * m * n / t / 1e9)
+        print("nonlocal apply", backend, res[f"nonlocal_apply_backend{backend}"], flush=True)
+    ctx.set_option("gemm_backend", 0)
+    print("nonlocal apply: max |difference| backend 4 vs 0:", float((outs[4] - outs[0]).abs().max() / outs[0].abs().max()))
+    json.dump(res, open("gpurun_out/i8_perf_probe.json", "w"), indent=1)

@@ -25,7 +25,7 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k},{v[0]},{v[1]:.3f},{v[1] / v[0]:.3f},{v[1] / tot:.3f}")
 open(f"profiles/launches_{tag}.csv", "w").write("\n".join(out) + "\n")
 
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}

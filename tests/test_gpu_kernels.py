@@ -121,7 +121,7 @@ def test_band_energies_and_density(si):
     np.testing.assert_allclose(rho.cpu().numpy(), ref, atol=1e-12 * ref.max())
 
 
-@pytest.mark.parametrize("backend", [2, 3])      # 2: integer products on CUDA cores, 3: tcgen05.mma.kind::i8 (i8tc.cu)
+@pytest.mark.parametrize("backend", [2, 3, 4])   # 2: integer products on CUDA cores, 3 / 4: tcgen05.mma.kind::i8 (cp.async-fed i8tc.cu / TMA-fed i8tc2.cu)
 @pytest.mark.parametrize("shape", [(3000, 7, 5), (70000, 20, 9), (140000, 150, 130)])
 def test_i8_emulated_gemm_matches_fp64(shape, backend):
     from gpu_common import ctx

@@ -300,6 +300,31 @@ def test_supercell_identity(rep, Ecut, fft):
     assert abs(float(rs["rho"].sum() * bs.dvol) - 8.0 * n) < 1e-9
 
 
+def test_supercell_identity_on_int8_tensor_cores():
+    """The same identity (rep = 3: 54 atoms, 111 bands, 72^3 grid) with the Gram products of LOBPCG and the P'psi projection
+    on the INT8 tensor cores (gemm_backend 4: FP64 emulated by INT8 residues + CRT, tcgen05.mma.kind::i8 fed by TMA): the
+    converged energy must still equal 27 x the primitive cell's to 1e-8 Ha per cell."""
+    import dftk_b200 as dftk
+    Si = dftk.ElementPsp("Si")
+    rep, Ecut, fft, n = 3, 12, 24, 27
+    unit = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), symmetries=False)
+    bu = dftk.PlaneWaveBasis(unit, Ecut=Ecut, kgrid=(rep, rep, rep), fft_size=(fft, fft, fft))
+    ru = dftk.self_consistent_field(bu, tol=1e-9)
+    pos = [(np.asarray(p) + np.array([i, j, k])) / rep for i in range(rep) for j in range(rep) for k in range(rep) for p in POSITIONS]
+    sup = dftk.model_DFT(rep * LATTICE, [Si] * (2 * n), pos, functionals=dftk.LDA(), symmetries=False)
+    bs = dftk.PlaneWaveBasis(sup, Ecut=Ecut, kgrid=(1, 1, 1), fft_size=(rep * fft,) * 3)
+    ctx = bs.architecture.ctx
+    ctx.set_option("gemm_backend", 4)
+    ctx.set_option("i8_min_rows", 2048)
+    try:
+        rs = dftk.self_consistent_field(bs, tol=1e-9)
+    finally:
+        ctx.set_option("gemm_backend", 0)
+        ctx.set_option("i8_min_rows", 32768)
+    assert rs["converged"] and ru["converged"]
+    assert abs(rs["energies"].total - n * ru["energies"].total) < n * 1e-8
+
+
 def _golden(name):
     import json
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "baseline_configs.json")
