@@ -392,6 +392,12 @@ void zgemm(dftk_b200_ctx* ctx, int transA, int64_t m, int64_t n, int64_t k, cplx
     zgemm_i8_cn(ctx, m, n, k, A, lda, B, ldb, C, ldc, ctx->gemm_backend - 2);
     return;
   }
+  if (ctx->gemm_backend == 4 && transA == 0 && m >= ctx->i8_min_rows && k >= 32 && n >= 16 && alpha.y == 0.0 && beta.y == 0.0 && !upper_only) {
+    // update-type product on the INT8 tensor cores: A prepared here (callers with reusable operands use i8_update directly)
+    const I8Operand opA = i8_prepare(ctx, A, lda, k, m, ctx->i8_tmp_planes, ctx->i8_tmp_exps);
+    i8_update(ctx, 1, &opA, B, ldb, n, C, ldc, alpha.x, beta.x);
+    return;
+  }
   if (ctx->gemm_backend == 2 && transA == 0 && k > 0 && alpha.x == 1.0 && alpha.y == 0.0 && beta.y == 0.0 &&
       (beta.x == 0.0 || beta.x == 1.0) && !upper_only) {
     if (zgemm_i8_nn(ctx, m, n, k, A, lda, B, ldb, C, ldc, beta.x == 1.0)) return;     // too large: DMMA kernel below
@@ -452,16 +458,17 @@ void kb_apply_nonlocal(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_
   cplx* proj = kb->proj.ensure((size_t)2 * np * n_bands);
   cplx* dproj = proj + (size_t)np * n_bands;
   const cplx one = make_double2(1.0, 0.0), zero = make_double2(0.0, 0.0);
-  if (ctx->gemm_backend == 4 && np >= 64 && n_bands >= 64 && kb->n_pw >= ctx->i8_min_rows) {
-    // P' psi on the INT8 tensor cores (tcgen05.mma.kind::i8, TMA-fed; i8tc2.cu) with the residue planes of P cached per k-block
-    if (!kb->i8_P) {
-      int n_mod = 0;
-      i8_build_planes(ctx, kb->P.p, kb->n_pw, np, kb->n_pw, &kb->i8_P, &kb->i8_eP, kb->i8_planes, kb->i8_exps, &n_mod);
-    }
-    zgemm_i8_cn(ctx, np, n_bands, kb->n_pw, kb->P.p, kb->n_pw, psi, kb->n_pw, proj, np, 2, kb->i8_P, kb->i8_eP);
-  } else {
-    zgemm(ctx, 2, np, n_bands, kb->n_pw, one, kb->P.p, kb->n_pw, psi, kb->n_pw, zero, proj, np);
+  if (ctx->gemm_backend == 4 && np >= 64 && n_bands >= 32 && kb->n_pw >= ctx->i8_min_rows) {
+    // both projector products on the INT8 tensor cores (tcgen05.mma.kind::i8, TMA-fed; i8emu.cu / i8tc2.cu): the residue
+    // planes of P are prepared once per k-block and serve P'psi (K-major operand) and P (D P'psi) (MN-major operand)
+    if (!kb->i8_Pop.planes) kb->i8_Pop = i8_prepare(ctx, kb->P.p, kb->n_pw, np, kb->n_pw, kb->i8_planes, kb->i8_exps);
+    const I8Operand op_psi = i8_prepare(ctx, psi, kb->n_pw, n_bands, kb->n_pw, kb->i8_pool[7], kb->i8_epool[7]);
+    i8_gram(ctx, kb->i8_Pop, op_psi, proj, np, false);
+    zgemm(ctx, 0, np, n_bands, np, one, kb->Dc.p, np, proj, np, zero, dproj, np);
+    i8_update(ctx, 1, &kb->i8_Pop, dproj, np, n_bands, hpsi, kb->n_pw, 1.0, 1.0);
+    return;
   }
+  zgemm(ctx, 2, np, n_bands, kb->n_pw, one, kb->P.p, kb->n_pw, psi, kb->n_pw, zero, proj, np);
   zgemm(ctx, 0, np, n_bands, np, one, kb->Dc.p, np, proj, np, zero, dproj, np);
   zgemm(ctx, 0, kb->n_pw, n_bands, np, one, kb->P.p, kb->n_pw, dproj, np, one, hpsi, kb->n_pw);
 }

@@ -117,6 +117,8 @@ struct dftk_b200_ctx {
   dftk::DevBuf<double> batch_gather;
   char* batch_ring_h = nullptr;
   double* batch_gather_h = nullptr;
+  dftk::DevBuf<signed char> i8_tmp_planes;   // gemm_backend 4: planes of an operand prepared inside a generic zgemm call
+  dftk::DevBuf<int> i8_tmp_exps;
   int64_t batch_rounds = 0;   // scheduler rounds (= host synchronisations) of the batched solves since creation / reset
 };
 

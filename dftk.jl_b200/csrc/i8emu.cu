@@ -77,7 +77,9 @@ k_i8_residues_ld4(const cplx* __restrict__ X, int64_t ld, int64_t n_rows, int64_
   }
   const long long plane_stride = (long long)ldk * n_cols;
   signed char* out = planes + (r4 + ldk * col);
-  for (int t = 0; t < n_mod; ++t) {
+#pragma unroll
+  for (int t = 0; t < I8_MAX_MODULI; ++t) {          // unrolled: p, c1, c2 are compile-time constants (no integer division)
+    if (t >= n_mod) break;
     const int p = i8_modulus(t);
     const int c1 = (1 << 20) % p, c2 = (int)((1ll << 40) % p);
     unsigned wr = 0, wi = 0;
@@ -139,9 +141,13 @@ k_i8_crt(const int* __restrict__ res, int64_t m, int64_t n, I8Tables T, const in
   if (idx >= m * n) return;
   const int64_t i = idx % m, j = idx / m;
   int rre[I8_MAX_MODULI], rim[I8_MAX_MODULI];
-  for (int t = 0; t < T.n_mod; ++t) {
-    rre[t] = res[((size_t)(2 * t) * n + j) * m + i];
-    rim[t] = res[((size_t)(2 * t + 1) * n + j) * m + i];
+#pragma unroll
+  for (int t = 0; t < I8_MAX_MODULI; ++t) {
+    rre[t] = rim[t] = 0;
+    if (t < T.n_mod) {
+      rre[t] = res[((size_t)(2 * t) * n + j) * m + i];
+      rim[t] = res[((size_t)(2 * t + 1) * n + j) * m + i];
+    }
   }
   const int sh = -(ea[i] + eb[j]);
   cplx v = make_double2(ldexp(i8_crt(rre, T), sh), ldexp(i8_crt(rim, T), sh));
@@ -200,22 +206,6 @@ static I8Tables tables_for(int64_t K) {
 }
 
 // C (m x n) = A^H B,  A: k x m, B: k x n (column-major, complex).  tensor_cores: integer products by k_i8_gemm_tc (i8tc.cu)
-// Residue planes + column exponents of an operand that does not change between calls (the projector table P of a k-block):
-// built once, reused by every later product with the same contraction length.
-void i8_build_planes(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int64_t m, int64_t k, signed char** planes_out, int** exps_out,
-                     DevBuf<signed char>& store, DevBuf<int>& estore, int* n_mod_out) {
-  const I8Tables T = tables_for(2 * k);
-  const int64_t ldk = (k + 127) / 128 * 128;
-  signed char* ra = store.ensure(2 * (size_t)T.n_mod * m * ldk + 16);
-  ra += (16 - ((uintptr_t)ra & 15)) & 15;
-  int* ea = estore.ensure((size_t)m);
-  LAUNCH(ctx, k_i8_col_exponent, (unsigned)m, 256, 0, A, lda, k, T.bits, ea);
-  LAUNCH(ctx, k_i8_residues_ld4, dim3((unsigned)((ldk / 4 + 255) / 256), (unsigned)m), 256, 0, A, lda, k, m, ldk, (const int*)ea, T.n_mod, ra);
-  *planes_out = ra;
-  *exps_out = ea;
-  *n_mod_out = T.n_mod;
-}
-
 // ---- prepared operands: an operand (a block of columns along the contraction index) is converted ONCE and then enters any
 //      number of products C = A^H B (the block Gram matrices of LOBPCG reuse every block three times)
 I8Operand i8_prepare(dftk_b200_ctx* ctx, const cplx* X, int64_t ld, int64_t cols, int64_t k, DevBuf<signed char>& store,
@@ -250,6 +240,131 @@ void i8_gram(dftk_b200_ctx* ctx, const I8Operand& A, const I8Operand& B, cplx* C
   short* part = (short*)(res + n_res);
   i8tc2_products(ctx, A.planes, B.planes, m, n, A.ldk, T.n_mod, part, res, upper_only);
   LAUNCH(ctx, k_i8_crt, (unsigned)((m * n + 127) / 128), 128, 0, (const int*)res, m, n, T, A.exps, B.exps, C, ldc, 0);
+}
+
+// ---- update-type products from prepared tall operands:  C (m x n) = alpha sum_b A_b B[rows of b, :] + beta C.
+// A_b's planes hold a'[G,k] = round(A[G,k] 2^{e_k}) with one scale per COLUMN k (as prepared for the Gram products); the scale
+// moves into the small matrix, B~[k,j] = B[k,j] 2^{-e_k}, whose columns get their own scales f_j:  C = 2^{-f_j} sum a' b'
+// exactly.  (Errors: the two operand roundings, relative to the column maxima of A and of B~ -- a norm-wise bound like the
+// FP64 GEMM's, not a component-wise one.)
+struct I8BBlocks {
+  int n_blocks;
+  int k0[3];        // first row of block b in B
+  int kc[3];        // its number of rows (= columns of A_b)
+  int pad0[3];      // first padded contraction index of block b in the planes (multiple of 128)
+  const int* exps[3];
+};
+// f[j]: scale exponent of column j of B~ (one CTA per column)
+__global__ void __launch_bounds__(256)
+k_i8_bscale_exponent(const cplx* __restrict__ B, int64_t ldb, I8BBlocks bl, int bits, int* __restrict__ f) {
+  const int64_t j = blockIdx.x;
+  double mx = 0.0;
+  for (int b = 0; b < bl.n_blocks; ++b)
+    for (int k = threadIdx.x; k < bl.kc[b]; k += blockDim.x) {
+      const cplx v = B[bl.k0[b] + k + ldb * j];
+      mx = fmax(mx, ldexp(fmax(fabs(v.x), fabs(v.y)), -bl.exps[b][k]));
+    }
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+    f[j] = i8_scale_exponent(mx, bits);
+  }
+}
+// planes[(2 t + part)][j][ldkb]: residues of round(B[k,j] 2^{f_j - e_k}) at the padded contraction index, zeros in the padding
+__global__ void __launch_bounds__(256)
+k_i8_bscale_residues(const cplx* __restrict__ B, int64_t ldb, int64_t n, I8BBlocks bl, int64_t ldkb, const int* __restrict__ f,
+                     int n_mod, signed char* __restrict__ planes) {
+  const int64_t kp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (kp >= ldkb) return;
+  cplx x = make_double2(0.0, 0.0);
+  int e = 0;
+  for (int b = 0; b < bl.n_blocks; ++b)
+    if (kp >= bl.pad0[b] && kp < bl.pad0[b] + bl.kc[b]) {
+      const int k = (int)(kp - bl.pad0[b]);
+      x = B[bl.k0[b] + k + ldb * j];
+      e = f[j] - bl.exps[b][k];
+    }
+  i8_residues_entry(x, e, n_mod, planes + (kp + ldkb * j), (long long)ldkb * n);
+}
+// C[G, j] = alpha 2^{-f_j} CRT(residues) + beta C[G, j];  resid: int8 [(2 t + part)][j][ldm].  Four consecutive rows per thread:
+// one 32-bit load per residue plane, 64 contiguous bytes of C.
+__global__ void __launch_bounds__(128)
+k_i8_crt_nn(const signed char* __restrict__ resid, int64_t m, int64_t n, int64_t ldm, I8Tables T, const int* __restrict__ f,
+            cplx* __restrict__ C, int64_t ldc, double alpha, double beta) {
+  const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t j = blockIdx.y;
+  if (i4 >= m) return;
+  unsigned wre[I8_MAX_MODULI], wim[I8_MAX_MODULI];
+#pragma unroll
+  for (int t = 0; t < I8_MAX_MODULI; ++t) {          // unrolled: the residue words stay in registers
+    wre[t] = wim[t] = 0;
+    if (t < T.n_mod) {
+      wre[t] = *reinterpret_cast<const unsigned*>(resid + ((size_t)(2 * t) * n + j) * ldm + i4);        // ldm % 128 == 0: aligned
+      wim[t] = *reinterpret_cast<const unsigned*>(resid + ((size_t)(2 * t + 1) * n + j) * ldm + i4);
+    }
+  }
+  const int sh = -f[j];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (i4 + q >= m) break;
+    int rre[I8_MAX_MODULI], rim[I8_MAX_MODULI];
+#pragma unroll
+    for (int t = 0; t < I8_MAX_MODULI; ++t) {
+      rre[t] = (int)(signed char)((wre[t] >> (8 * q)) & 0xFF);
+      rim[t] = (int)(signed char)((wim[t] >> (8 * q)) & 0xFF);
+    }
+    cplx v = make_double2(alpha * ldexp(i8_crt(rre, T), sh), alpha * ldexp(i8_crt(rim, T), sh));
+    if (beta != 0.0) {
+      const cplx o = C[i4 + q + ldc * j];
+      v.x += beta * o.x;
+      v.y += beta * o.y;
+    }
+    C[i4 + q + ldc * j] = v;
+  }
+}
+
+void i8_update(dftk_b200_ctx* ctx, int n_blocks, const I8Operand* A, const cplx* B, int64_t ldb, int64_t n, cplx* C, int64_t ldc,
+               double alpha, double beta) {
+  REQUIRE(n_blocks >= 1 && n_blocks <= 3 && n >= 1, "i8_update: 1..3 blocks");
+  const int64_t m = A[0].k, ldm = A[0].ldk;       // the operands' contraction length is the output's row count
+  const I8Tables T = tables_for(2 * m);
+  I8BBlocks bl{};
+  bl.n_blocks = n_blocks;
+  int k0 = 0, pad = 0;
+  int kcols[3], k_off[3];
+  const signed char* ra[3];
+  for (int b = 0; b < n_blocks; ++b) {
+    REQUIRE(A[b].k == m && A[b].ldk == ldm && A[b].n_mod == T.n_mod, "i8_update: blocks prepared differently");
+    bl.k0[b] = k0;
+    bl.kc[b] = (int)A[b].cols;
+    bl.pad0[b] = pad;
+    bl.exps[b] = A[b].exps;
+    kcols[b] = (int)A[b].cols;
+    k_off[b] = pad;
+    ra[b] = A[b].planes;
+    k0 += (int)A[b].cols;
+    pad += (int)((A[b].cols + 127) / 128 * 128);
+  }
+  const int64_t ldkb = pad;
+  // K 2^(2 bits) <= P / 4 holds a fortiori: the tables were sized for the (much longer) contraction of the Gram products
+  const size_t plane_b = (size_t)n * ldkb;
+  const size_t bytes = (size_t)n * sizeof(int) + 64 + 2 * (size_t)T.n_mod * plane_b + 64 + 2 * (size_t)T.n_mod * n * ldm + 64;
+  char* ws = (char*)ctx->gemm_ws.ensure(bytes);
+  int* f = (int*)ws;
+  signed char* rb = (signed char*)(f + n);
+  rb += (16 - ((uintptr_t)rb & 15)) & 15;
+  signed char* resid = rb + 2 * (size_t)T.n_mod * plane_b;
+  resid += (16 - ((uintptr_t)resid & 15)) & 15;
+  LAUNCH(ctx, k_i8_bscale_exponent, (unsigned)n, 256, 0, B, ldb, bl, T.bits, f);
+  LAUNCH(ctx, k_i8_bscale_residues, dim3((unsigned)((ldkb + 255) / 256), (unsigned)n), 256, 0, B, ldb, n, bl, ldkb, (const int*)f,
+         T.n_mod, rb);
+  i8tc2_products_nn(ctx, n_blocks, ra, kcols, k_off, ldm, rb, ldkb, m, n, T.n_mod, resid);
+  LAUNCH(ctx, k_i8_crt_nn, dim3((unsigned)((m + 511) / 512), (unsigned)n), 128, 0, (const signed char*)resid, m, n, ldm, T, (const int*)f,
+         C, ldc, alpha, beta);
 }
 
 void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,

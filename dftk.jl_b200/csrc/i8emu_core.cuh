@@ -59,6 +59,17 @@ HD int i8_residue_fast(double a, int p) {
   if (r < -(double)(p / 2)) r += dp;
   return (int)r;
 }
+// Barrett reduction of |s| < 2^27 modulo p in [173, 256] to the symmetric representative: no integer division.
+// magic = ceil(2^36 / p), precomputed once per thread for the modulus of its CTA.
+HD unsigned long long i8_barrett_magic(int p) { return ((1ull << 36) + (unsigned long long)p - 1) / (unsigned long long)p; }
+HD int i8_reduce_sym(int s, int p, unsigned long long magic) {
+  const unsigned long long u = (unsigned long long)((long long)s + ((long long)p << 19));   // >= 0, < 2^28
+  const unsigned long long q = (u * magic) >> 36;
+  int r = (int)(u - q * (unsigned long long)p);                  // in [-p, p): the rounded-up magic may overshoot by one
+  if (r < 0) r += p;
+  if (r > (p - 1) / 2) r -= p;
+  return r;
+}
 HD int i8_sym(int r, int p) {            // symmetric representative of any int
   r %= p;
   if (r > (p - 1) / 2) r -= p;
@@ -133,10 +144,20 @@ HD double i8_crt(const int* __restrict__ r, const I8Tables& T) {
   const double B40 = 1099511627776.0;    // 2^40
   double S[I8_LIMBS + 1];
   for (int j = 0; j <= I8_LIMBS; ++j) S[j] = 0.0;
-  for (int t = 0; t < T.n_mod; ++t) {
-    const int p = i8_modulus(t);
-    const int s = i8_sym(i8_sym(r[t], p) * T.q[t], p);          // |s| <= 128
-    for (int j = 0; j < I8_LIMBS; ++j) S[j] += (double)s * T.w[t][j];   // |S_j| <= 20 * 128 * 2^40 < 2^52: exact
+  // fully unrolled over the table of moduli: every p is a compile-time constant, so the remainders are multiply-shift
+  // sequences instead of integer divisions
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int t = 0; t < I8_MAX_MODULI; ++t) {
+    if (t < T.n_mod) {
+      const int p = i8_modulus(t);
+      const int s = i8_sym(i8_sym(r[t], p) * T.q[t], p);          // |s| <= 128
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < I8_LIMBS; ++j) S[j] += (double)s * T.w[t][j];   // |S_j| <= 20 * 128 * 2^40 < 2^52: exact
+    }
   }
   // quotient estimate (|Q| <= 20 * 128 / 2; the FP64 Horner value is accurate to 2^-50 |V| << P / 4)
   double top = 0.0;

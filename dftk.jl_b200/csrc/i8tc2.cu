@@ -101,6 +101,7 @@ k_i8_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = blockIdx.z % n_mod, chunk = blockIdx.z / n_mod;
   const int p = i8_modulus(t);
+  const unsigned long long magic = i8_barrett_magic(p);
   const int64_t i0 = (int64_t)blockIdx.x * T2_M, j0 = (int64_t)blockIdx.y * T2_N;
   const int64_t k_begin = (int64_t)chunk * chunk_len;
   const int64_t k_end = k_begin + chunk_len < ldk ? k_begin + chunk_len : ldk;
@@ -189,12 +190,160 @@ k_i8_gemm_tc2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         for (int c = 0; c < 32; ++c) {
           const int64_t j = j0 + c0 + c;
           if (j < n) {
-            const int re = ((int)x1[c] % p + (int)x2[c] % p) % p;
-            const int im = ((int)x3[c] % p - (int)x4[c] % p) % p;
+            // |x| <= 2^16 x 2^14: reduce each accumulator first (the sum of two would overflow int32)
+            const int re = i8_reduce_sym(i8_reduce_sym((int)x1[c] >> 4, p, magic) * 16 + ((int)x1[c] & 15) +
+                                         i8_reduce_sym((int)x2[c] >> 4, p, magic) * 16 + ((int)x2[c] & 15), p, magic);
+            const int im = i8_reduce_sym(i8_reduce_sym((int)x3[c] >> 4, p, magic) * 16 + ((int)x3[c] & 15) -
+                                         i8_reduce_sym((int)x4[c] >> 4, p, magic) * 16 - ((int)x4[c] & 15), p, magic);
             out_re[(size_t)j * m + i] = (short)re;
             out_im[(size_t)j * m + i] = (short)im;
           }
         }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Update-type products  C (m x n) = sum over blocks  A_b (m x K_b) B_b (K_b x n)  (LazyHcat * matrix of LOBPCG, P (D P'psi)):
+// the tall operand A_b is consumed in its stored orientation as the MN-major UMMA operand -- its residue planes
+// [plane][column k][row G] are the ones the Gram products already prepared (G contiguous) -- and the small matrix B as the
+// K-major operand.  Complex product without conjugation: re = X1 - X2, im = X3 + X4.  All blocks accumulate in TMEM
+// (|sum| <= 1536 x 2^14: no int32 overflow); the epilogue writes the symmetric residues as int8.
+// grid (n tiles, m tiles, n_mod): the n tiles of one G tile are neighbours in launch order and share the A tile in L2.
+struct T2NnBlocks {
+  int n_blocks;
+  int kcols[3];      // columns of A_b = rows of its planes
+  int n_iters[3];    // ceil(kcols / 128)
+  int k_off[3];      // first (padded) contraction index of the block in B's planes (multiple of 128)
+};
+
+constexpr int T2NN_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
+
+// The product is formed transposed, D[j, G] = sum_k B~[k, j] A[G, k]: the small matrix is the K-major "A" operand of the MMA
+// (128 rows j), the tall operand the MN-major "B" operand (128 columns G).  A TMEM lane then holds one row j of the output and
+// 32 consecutive G per tcgen05.ld: the residues leave as 16-byte stores (the straightforward orientation needed one byte store
+// per value and was bound by its epilogue: ncu 15 % tensor-pipe active, 4.7e9 instructions).
+__global__ void __launch_bounds__(T2NN_THREADS, 1)
+k_i8_gemm_tc2_nn(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b, T2NnBlocks blocks,
+                 int64_t m, int64_t n, int n_mod, signed char* __restrict__ resid, int64_t ldm) {
+  extern __shared__ unsigned char t2_raw[];
+  unsigned char* sm = (unsigned char*)(((uintptr_t)t2_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[T2_STAGES], empty_bar[T2_STAGES], accum_bar;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = blockIdx.z;
+  const int p = i8_modulus(t);
+  const unsigned long long magic = i8_barrett_magic(p);
+  const int64_t j0 = (int64_t)blockIdx.x * T2_M, i0 = (int64_t)blockIdx.y * T2_N;      // j: MMA rows, G: MMA columns
+  int total_iters = 0;
+  for (int b = 0; b < blocks.n_blocks; ++b) total_iters += blocks.n_iters[b];
+
+  if (tid == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) {
+      t2_mbar_init(&full_bar[s], 1);
+      t2_mbar_init(&empty_bar[s], 1);
+    }
+    t2_mbar_init(&accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(t2_smem_u32(&tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int row_br = (int)((int64_t)(2 * t) * n + j0), row_bi = (int)((int64_t)(2 * t + 1) * n + j0);
+      int it = 0;
+      for (int b = 0; b < blocks.n_blocks; ++b) {
+        const CUtensorMap* ma = b == 0 ? &map_a0 : (b == 1 ? &map_a1 : &map_a2);
+        const int kc = blocks.kcols[b];
+        for (int q = 0; q < blocks.n_iters[b]; ++q, ++it) {
+          const int s = it % T2_STAGES;
+          if (it >= T2_STAGES) t2_mbar_wait(&empty_bar[s], (uint32_t)((it / T2_STAGES - 1) & 1));
+          unsigned char* stage = sm + (size_t)s * T2_STAGE_BYTES;
+          t2_mbar_expect_tx(&full_bar[s], (uint32_t)T2_STAGE_BYTES);
+          // tall operand: 128 contraction rows (plane rows k) x 128 bytes of G; small matrix: 128 rows j x 128 bytes of k
+          t2_tma_load(stage + 0 * T2_TILE_BYTES, ma, (int)i0, (2 * t) * kc + q * T2_BK, &full_bar[s]);
+          t2_tma_load(stage + 1 * T2_TILE_BYTES, ma, (int)i0, (2 * t + 1) * kc + q * T2_BK, &full_bar[s]);
+          t2_tma_load(stage + 2 * T2_TILE_BYTES, &map_b, blocks.k_off[b] + q * T2_BK, row_br, &full_bar[s]);
+          t2_tma_load(stage + 3 * T2_TILE_BYTES, &map_b, blocks.k_off[b] + q * T2_BK, row_bi, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D = s32, A = B = s8; MMA-A (small matrix) K-major, MMA-B (tall operand) MN-major (bit 16); N = 128, M = 128
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(T2_N >> 3) << 17) | ((uint32_t)(T2_M >> 4) << 24);
+    for (int it = 0; it < total_iters; ++it) {
+      const int s = it % T2_STAGES;
+      t2_mbar_wait(&full_bar[s], (uint32_t)((it / T2_STAGES) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t base = t2_smem_u32(sm + (size_t)s * T2_STAGE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < T2_BK / 32; ++kk) {
+          // tall operand (MN-major, SWIZZLE_128B): a K = 32 step is 32 rows of 128 bytes = 4096 bytes; small matrix (K-major): 32 bytes
+          const uint64_t dTr = t2_desc(base + 0 * T2_TILE_BYTES + (uint32_t)kk * 4096u);
+          const uint64_t dTi = t2_desc(base + 1 * T2_TILE_BYTES + (uint32_t)kk * 4096u);
+          const uint64_t dSr = t2_desc(base + 2 * T2_TILE_BYTES + (uint32_t)kk * 32u);
+          const uint64_t dSi = t2_desc(base + 3 * T2_TILE_BYTES + (uint32_t)kk * 32u);
+          const uint32_t acc = (uint32_t)(it > 0 || kk > 0);
+          t2_mma_i8(tmem + 0 * T2_N, dSr, dTr, idesc, acc);      // X1 = Sr Tr
+          t2_mma_i8(tmem + 1 * T2_N, dSi, dTi, idesc, acc);      // X2 = Si Ti
+          t2_mma_i8(tmem + 2 * T2_N, dSi, dTr, idesc, acc);      // X3 = Si Tr   (tall re x small im)
+          t2_mma_i8(tmem + 3 * T2_N, dSr, dTi, idesc, acc);      // X4 = Sr Ti   (tall im x small re)
+        }
+        t2_commit(&empty_bar[s]);
+        if (it == total_iters - 1) t2_commit(&accum_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue: lane = row j; warps 2..9 = (quarter = warp % 4, half of the 128 G columns = (warp - 2) / 4)
+    t2_mbar_wait(&accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int64_t j = j0 + quarter * 32 + lane;
+    signed char* out_re = resid + ((size_t)(2 * t) * n + (j < n ? j : 0)) * ldm + i0;
+    signed char* out_im = resid + ((size_t)(2 * t + 1) * n + (j < n ? j : 0)) * ldm + i0;
+    for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 32) {
+      uint32_t x1[32], x2[32], x3[32], x4[32];
+      const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0;
+      t2_ld32(lane_base + 0 * T2_N, x1);
+      t2_ld32(lane_base + 1 * T2_N, x2);
+      t2_ld32(lane_base + 2 * T2_N, x3);
+      t2_ld32(lane_base + 3 * T2_N, x4);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (j < n) {
+        // |x| <= 1536 x 2^14 < 2^25: sums and differences of two accumulators stay below 2^26
+        uint32_t wre[8], wim[8];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          uint32_t a = 0, b = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            a |= (uint32_t)(i8_reduce_sym((int)x1[c + q] - (int)x2[c + q], p, magic) & 0xFF) << (8 * q);
+            b |= (uint32_t)(i8_reduce_sym((int)x3[c + q] + (int)x4[c + q], p, magic) & 0xFF) << (8 * q);
+          }
+          wre[c >> 2] = a;
+          wim[c >> 2] = b;
+        }
+        // 32 consecutive G of row j: two 16-byte stores per part (ldm and i0 are multiples of 128: aligned)
+        uint4* pr = reinterpret_cast<uint4*>(out_re + c0);
+        uint4* pi = reinterpret_cast<uint4*>(out_im + c0);
+        pr[0] = make_uint4(wre[0], wre[1], wre[2], wre[3]);
+        pr[1] = make_uint4(wre[4], wre[5], wre[6], wre[7]);
+        pi[0] = make_uint4(wim[0], wim[1], wim[2], wim[3]);
+        pi[1] = make_uint4(wim[4], wim[5], wim[6], wim[7]);
       }
     }
   }
@@ -215,6 +364,7 @@ __global__ void k_i8_sum_chunks2(const short* __restrict__ part, int n_chunks, i
 
 void i8tc2_set_attributes() {
   if (cudaFuncSetAttribute(k_i8_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM) != cudaSuccess) cudaGetLastError();
+  if (cudaFuncSetAttribute(k_i8_gemm_tc2_nn, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM) != cudaSuccess) cudaGetLastError();
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -231,6 +381,30 @@ static EncodeTiledFn encode_tiled() {
   }
   return fn;
 }
+static CUtensorMap plane_map(const signed char* base, int64_t rows_total, int64_t ldk);
+// integer stage of the update-type product: blocks of prepared tall operands (planes [plane][col][ldm], ldm = padded rows) against
+// the planes of the small matrix rb ([plane][j][ldkb], contraction index padded per block); resid: int8 [(2 t + part)][j][ldm]
+void i8tc2_products_nn(dftk_b200_ctx* ctx, int n_blocks, const signed char* const* ra, const int* kcols, const int* k_off,
+                       int64_t ldm, const signed char* rb, int64_t ldkb, int64_t m, int64_t n, int n_mod, signed char* resid) {
+  REQUIRE(n_blocks >= 1 && n_blocks <= 3, "i8tc2_nn: 1..3 blocks");
+  T2NnBlocks bl{};
+  bl.n_blocks = n_blocks;
+  CUtensorMap maps[3];
+  for (int b = 0; b < n_blocks; ++b) {
+    REQUIRE(((uintptr_t)ra[b] & 15) == 0 && ldm % T2_BK == 0 && k_off[b] % T2_BK == 0, "i8tc2_nn: alignment");
+    bl.kcols[b] = kcols[b];
+    bl.n_iters[b] = (kcols[b] + T2_BK - 1) / T2_BK;
+    bl.k_off[b] = k_off[b];
+    maps[b] = plane_map(ra[b], 2 * (int64_t)n_mod * kcols[b], ldm);
+  }
+  for (int b = n_blocks; b < 3; ++b) maps[b] = maps[0];
+  const CUtensorMap map_b = plane_map(rb, 2 * (int64_t)n_mod * n, ldkb);
+  const int64_t m_tiles = (m + T2_M - 1) / T2_M;
+  REQUIRE(m_tiles <= 65535, "i8tc2_nn: too many row tiles");
+  dim3 grid((unsigned)((n + T2_N - 1) / T2_N), (unsigned)m_tiles, (unsigned)n_mod);
+  LAUNCH(ctx, k_i8_gemm_tc2_nn, grid, T2NN_THREADS, T2_SMEM, maps[0], maps[1], maps[2], map_b, bl, m, n, n_mod, resid, ldm);
+}
+
 static CUtensorMap plane_map(const signed char* base, int64_t rows_total, int64_t ldk) {
   CUtensorMap map;
   const cuuint64_t gdim[2] = {(cuuint64_t)ldk, (cuuint64_t)rows_total};

@@ -706,6 +706,43 @@ struct Lobpcg {
   int64_t ldBYX = 0;
   int64_t n_chol_total = 0;
 
+  // ---- INT8 tensor-core path of the large solves (gemm_backend 4): residue planes of the N_pw-sized blocks, prepared once
+  //      and reused by every Gram and update product until the block's data changes (`touch`)
+  struct PlaneEntry {
+    const cplx* p = nullptr;
+    int64_t ld = 0, cols = 0;
+    I8Operand op;
+    uint64_t stamp = 0;
+    bool valid = false;
+  };
+  static constexpr int N_PLANE_SLOTS = 8;
+  PlaneEntry planes[N_PLANE_SLOTS];
+  uint64_t plane_clock = 0;
+  bool use_i8(int64_t rows) const { return !small && ctx->gemm_backend == 4 && rows >= ctx->i8_min_rows; }
+  I8Operand planes_for(const Mat& X) {
+    for (auto& e : planes)
+      if (e.valid && e.p == X.p && e.ld == X.ld && e.cols == X.cols) {
+        e.stamp = ++plane_clock;
+        return e.op;
+      }
+    int slot = 0;
+    for (int i = 0; i < N_PLANE_SLOTS; ++i) {
+      if (!planes[i].valid) { slot = i; break; }
+      if (planes[i].stamp < planes[slot].stamp) slot = i;
+    }
+    PlaneEntry& e = planes[slot];
+    e.op = i8_prepare(ctx, X.p, X.ld, X.cols, X.rows, kb->i8_pool[slot], kb->i8_epool[slot]);
+    e.p = X.p; e.ld = X.ld; e.cols = X.cols; e.valid = true; e.stamp = ++plane_clock;
+    return e.op;
+  }
+  // the n complex numbers from p on are about to be (or have been) overwritten: planes of overlapping blocks are stale
+  void touch(const cplx* p, int64_t n) {
+    if (small || ctx->gemm_backend != 4) return;
+    for (auto& e : planes)
+      if (e.valid && p < e.p + e.ld * e.cols && e.p < p + n) e.valid = false;
+  }
+  void touch(const Mat& X) { touch(X.p, X.ld * X.cols); }
+
   Op& newop(int type) {
     co->ops.emplace_back();
     Op& o = co->ops.back();
@@ -781,6 +818,7 @@ struct Lobpcg {
       newop(OP_COPY2D).u.copy2d = Copy2dItem{dst.p, dst.ld, src.p, src.ld, src.rows, (int)src.cols};
       return;
     }
+    touch(dst.p, dst.ld * src.cols);
     LAUNCH(ctx, k_copy2d, nblk(src.rows * src.cols), 256, 0, dst.p, dst.ld, (const cplx*)src.p, src.ld,
            src.rows, src.cols);
   }
@@ -791,6 +829,7 @@ struct Lobpcg {
       newop(OP_COPY2D).u.copy2d = Copy2dItem{dst, n, src, n, n, 1};
       return;
     }
+    touch(dst, n);
     if (src) CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToDevice, ctx->stream));
     else CUDA_CHECK(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(cplx), ctx->stream));
   }
@@ -808,6 +847,7 @@ struct Lobpcg {
       newop(OP_SCALE).u.scale = ScaleItem{X.p, X.ld, X.rows, (int)X.cols, norms};
       return;
     }
+    touch(X);
     LAUNCH(ctx, k_scale_cols_inv, nblk(X.rows * X.cols), 256, 0, X.p, X.ld, X.rows, X.cols, norms);
   }
   void matrix_stats(const cplx* A, int64_t ld, int64_t r, int64_t c, double* out) {
@@ -822,6 +862,7 @@ struct Lobpcg {
       newop(OP_RANDN).u.randn = RandnItem{x, n_rows, seed};
       return;
     }
+    touch(x, n_rows);
     LAUNCH(ctx, k_randn_col, nblk(n_rows), 256, 0, x, n_rows, seed);
   }
   void stats(const cplx* A, int64_t ld, int64_t r, int64_t c, double* out4) {
@@ -837,26 +878,16 @@ struct Lobpcg {
   // C = op(A)' * B accumulated over block lists (LazyHcat products, :90-137)
   void gram(const std::vector<Mat>& A, const std::vector<Mat>& B, cplx* C, int64_t ldc, bool upper_only) {
     if (small) return small_gram(A, B, C, ldc, upper_only);
-    if (ctx->gemm_backend == 4 && !A.empty() && A[0].rows >= ctx->i8_min_rows) {
+    if (!A.empty() && use_i8(A[0].rows)) {
       // INT8 tensor cores (tcgen05.mma.kind::i8, TMA-fed; i8emu.cu / i8tc2.cu): every distinct block is converted to residue
       // planes once and enters all its block products
-      bool ok = A.size() + B.size() <= 6;
+      bool ok = A.size() + B.size() <= N_PLANE_SLOTS;
       for (auto& a : A) ok = ok && a.cols >= 32;
       for (auto& b : B) ok = ok && b.cols >= 32;
       if (ok) {
         std::vector<I8Operand> opA(A.size()), opB(B.size());
-        int slot = 0;
-        for (size_t ia = 0; ia < A.size(); ++ia)
-          opA[ia] = i8_prepare(ctx, A[ia].p, A[ia].ld, A[ia].cols, A[ia].rows, kb->i8_pool[slot], kb->i8_epool[slot]), ++slot;
-        for (size_t ib = 0; ib < B.size(); ++ib) {
-          bool shared = false;
-          for (size_t ia = 0; ia < A.size() && !shared; ++ia)
-            if (A[ia].p == B[ib].p && A[ia].cols == B[ib].cols && A[ia].ld == B[ib].ld) {
-              opB[ib] = opA[ia];
-              shared = true;
-            }
-          if (!shared) opB[ib] = i8_prepare(ctx, B[ib].p, B[ib].ld, B[ib].cols, B[ib].rows, kb->i8_pool[slot], kb->i8_epool[slot]), ++slot;
-        }
+        for (size_t ia = 0; ia < A.size(); ++ia) opA[ia] = planes_for(A[ia]);
+        for (size_t ib = 0; ib < B.size(); ++ib) opB[ib] = planes_for(B[ib]);
         int64_t oc = 0;
         for (size_t ib = 0; ib < B.size(); ++ib) {
           int64_t orow = 0;
@@ -886,6 +917,18 @@ struct Lobpcg {
   void blocks_times(const std::vector<Mat>& Y, const cplx* c, int64_t ldc, int64_t ncols, Mat out,
                     double alpha, double beta) {
     if (small) return small_blocks_times(Y, c, ldc, ncols, out, alpha, beta);
+    if (!Y.empty() && use_i8(Y[0].rows) && Y.size() <= 3 && ncols >= 16) {
+      bool ok = true;
+      for (auto& y : Y) ok = ok && y.cols >= 32;
+      if (ok) {
+        I8Operand ops[3];
+        for (size_t i = 0; i < Y.size(); ++i) ops[i] = planes_for(Y[i]);
+        i8_update(ctx, (int)Y.size(), ops, c, ldc, ncols, out.p, out.ld, alpha, beta);
+        touch(out.p, out.ld * ncols);
+        return;
+      }
+    }
+    touch(out.p, out.ld * ncols);
     int64_t off = 0;
     for (size_t i = 0; i < Y.size(); ++i) {
       zgemm(ctx, 0, Y[i].rows, ncols, Y[i].cols, make_double2(alpha, 0), Y[i].p, Y[i].ld, c + off, ldc,
@@ -975,8 +1018,15 @@ struct Lobpcg {
         continue;
       }
       // X <- X * invR   (rmul!(X, invR))
-      zgemm(ctx, 0, X.rows, n, n, make_double2(1, 0), X.p, X.ld, invR, S3, make_double2(0, 0), tmp, ldtmp,
-            /*invR is upper triangular*/ true);
+      if (use_i8(X.rows) && n >= 32) {
+        const I8Operand opX = planes_for(X);        // prepared for the Gram product above
+        touch(tmp, ldtmp * n);
+        i8_update(ctx, 1, &opX, invR, S3, n, tmp, ldtmp, 1.0, 0.0);
+      } else {
+        touch(tmp, ldtmp * n);
+        zgemm(ctx, 0, X.rows, n, n, make_double2(1, 0), X.p, X.ld, invR, S3, make_double2(0, 0), tmp, ldtmp,
+              /*invR is upper triangular*/ true);
+      }
       copy2d(X, Mat{tmp, ldtmp, X.rows, n});
       double norminvR = normest(invR, S3, n);
       growth *= norminvR;
@@ -1149,6 +1199,7 @@ void Lobpcg::ortho_svd_fallback(Mat X, cplx* tmp, int64_t ldtmp) {
     }
     LAUNCH(ctx, k_conj_transpose, nblk(n * n), 256, 0, (const cplx*)Ochol, S3, invR, S3, (int)n);   // V'
     zgemm(ctx, 0, X.rows, n, n, one, tmp, ldtmp, invR, S3, zero, X.p, X.ld);                          // X = U V'
+    touch(X);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   } catch (...) {
     small = was_small;
@@ -1204,6 +1255,7 @@ void Lobpcg::body(SolveArgs& a) {
       newop(OP_APPLYH).u.applyh = ApplyHItem{kb, in.p, out.p, (int)in.cols};
       return;
     }
+    touch(out);
     kb_apply_local_kinetic(kb, in.p, out.p, in.cols, kb->has_V, kb->has_kin, false);
     kb_apply_nonlocal(kb, in.p, out.p, in.cols);
   };
@@ -1279,6 +1331,7 @@ void Lobpcg::body(SolveArgs& a) {
       if (niter > 0 && both[(d_stats - d_norms) + 4] == 0.0)
         throw Error(DFTK_B200_ENUM, "rayleigh_ritz: Jacobi eigensolver did not converge");
     } else {
+      touch(nR + N * a0, N * Ma);
       LAUNCH(ctx, k_residual, (unsigned)Ma, 256, 0, (const cplx*)(nAX + N * a0), (const cplx*)(nX + N * a0),
              (const double*)(d_lam + a0), nR + N * a0, N, N, use_prec ? (const double*)kb->kin.p : nullptr,
              d_norms, d_meankin);
@@ -1289,6 +1342,7 @@ void Lobpcg::body(SolveArgs& a) {
       if (small) {
         newop(OP_PRECOND).u.precond = PrecondItem{nR + N * a0, N, N, (int)Ma, kb->kin.p, d_meankin};
       } else {
+        touch(nR + N * a0, N * Ma);
         LAUNCH(ctx, k_precondition, nblk(N * Ma), 256, 0, nR + N * a0, N, N, Ma, (const double*)kb->kin.p,
                (const double*)d_meankin);
       }

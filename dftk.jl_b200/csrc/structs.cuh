@@ -30,6 +30,15 @@ const RegKernels* reg_kernels_for(int n);   // nullptr: use the generic Stockham
 void reg_set_attributes();
 }  // namespace dftk
 
+namespace dftk {
+struct I8Operand {                  // an operand of C = A^H B converted to INT8 residue planes (i8emu.cu)
+  const signed char* planes = nullptr;
+  const int* exps = nullptr;
+  int64_t cols = 0, k = 0, ldk = 0;
+  int n_mod = 0;
+};
+}  // namespace dftk
+
 struct dftk_b200_grid {
   dftk_b200_ctx* ctx;
   int nx, ny, nz;
@@ -58,12 +67,11 @@ struct dftk_b200_kblock {
   dftk::DevBuf<dftk::cplx> P;     // n_pw x n_proj
   std::vector<double> D_host;     // n_proj x n_proj
   dftk::DevBuf<dftk::cplx> Dc;    // complex copy of D on the device (n_proj x n_proj)
-  dftk::DevBuf<signed char> i8_pool[6];  // gemm_backend 4: residue planes of the LOBPCG blocks of one Gram product
-  dftk::DevBuf<int> i8_epool[6];
+  dftk::DevBuf<signed char> i8_pool[8];  // gemm_backend 4: residue planes of the LOBPCG blocks (cache slots of a solve)
+  dftk::DevBuf<int> i8_epool[8];
+  dftk::I8Operand i8_Pop;                // prepared projector table (kept for the lifetime of the block)
   dftk::DevBuf<signed char> i8_planes;   // gemm_backend 4: cached INT8 residue planes of P (built at first use)
   dftk::DevBuf<int> i8_exps;
-  signed char* i8_P = nullptr;
-  int* i8_eP = nullptr;
   dftk::DevBuf<dftk::cplx> PD;    // P D (n_pw x n_proj), kept when n_proj is small: Hψ += (P D)(P'ψ) as two batched small products
   dftk::DevBuf<double> V;         // N, pre-scaled by 1/N (fft_norm*ifft_norm)
   bool has_V = false;
@@ -121,19 +129,16 @@ void symmetrize_fourier(dftk_b200_grid* g, const cplx* in, cplx* out, int n_sym,
 // i8emu.cu (experimental, option gemm_backend = 2)
 void zgemm_i8_cn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
                  cplx* C, int64_t ldc, int tc_mode, const signed char* ra_cached = nullptr, const int* ea_cached = nullptr);
-void i8_build_planes(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int64_t m, int64_t k, signed char** planes_out, int** exps_out,
-                     DevBuf<signed char>& store, DevBuf<int>& estore, int* n_mod_out);
 void i8tc2_products(dftk_b200_ctx* ctx, const signed char* ra, const signed char* rb, int64_t m, int64_t n, int64_t ldk,
                     int n_mod, short* part, int* res, bool upper_only);
-struct I8Operand {                  // an operand of C = A^H B converted to INT8 residue planes (i8emu.cu)
-  const signed char* planes = nullptr;
-  const int* exps = nullptr;
-  int64_t cols = 0, k = 0, ldk = 0;
-  int n_mod = 0;
-};
 I8Operand i8_prepare(dftk_b200_ctx* ctx, const cplx* X, int64_t ld, int64_t cols, int64_t k, DevBuf<signed char>& store,
                      DevBuf<int>& estore);
 void i8_gram(dftk_b200_ctx* ctx, const I8Operand& A, const I8Operand& B, cplx* C, int64_t ldc, bool upper_only);
+// C (rows x n) = alpha sum_b A_b B[rows of b, :] + beta C from prepared tall operands (update-type products)
+void i8_update(dftk_b200_ctx* ctx, int n_blocks, const I8Operand* A, const cplx* B, int64_t ldb, int64_t n, cplx* C, int64_t ldc,
+               double alpha, double beta);
+void i8tc2_products_nn(dftk_b200_ctx* ctx, int n_blocks, const signed char* const* ra, const int* kcols, const int* k_off,
+                       int64_t ldm, const signed char* rb, int64_t ldkb, int64_t m, int64_t n, int n_mod, signed char* resid);
 void i8tc2_set_attributes();
 bool zgemm_i8_nn(dftk_b200_ctx* ctx, int64_t m, int64_t n, int64_t k, const cplx* A, int64_t lda, const cplx* B, int64_t ldb,
                  cplx* C, int64_t ldc, bool accumulate);

@@ -134,12 +134,33 @@ def test_i8_emulated_gemm_matches_fp64(shape, backend):
     ref = torch.zeros((n, m), dtype=torch.complex128, device=c.device)
     c.zgemm("C", A, B, ref)
     c.set_option("gemm_backend", backend)
+    c.set_option("i8_min_rows", 1024)
     try:
         C = torch.zeros_like(ref)
         c.zgemm("C", A, B, C)
     finally:
         c.set_option("gemm_backend", 0)
+        c.set_option("i8_min_rows", 32768)
     assert (C - ref).abs().max().item() < 1e-14 * ref.abs().max().item() * K ** 0.5
+    if backend == 4:
+        # update type on the tensor cores (A as the MN-major UMMA operand, its column scales folded into S): X = A S (+ X0)
+        S = torch.view_as_complex(torch.randn(n, m, 2, generator=g, dtype=torch.float64)).to(c.device)
+        X0 = torch.view_as_complex(torch.randn(n, K, 2, generator=g, dtype=torch.float64)).to(c.device)
+        want = torch.zeros_like(X0)
+        c.zgemm("N", A, S, want)
+        c.set_option("gemm_backend", 4)
+        c.set_option("i8_min_rows", 1024)
+        try:
+            X = torch.zeros_like(X0)
+            c.zgemm("N", A, S, X)
+            Xa = X0.clone()
+            c.zgemm("N", A, S, Xa, -1.0, 1.0)
+        finally:
+            c.set_option("gemm_backend", 0)
+            c.set_option("i8_min_rows", 32768)
+        scale = (A.abs().max(dim=1).values[None, :] * S.abs()).sum(dim=1).max().item()      # sum_k |A[:,k]|max |S[k,j]|
+        assert (X - want).abs().max().item() < 1e-14 * scale
+        assert (Xa - X0 + want).abs().max().item() < 1e-14 * scale
     if backend == 2 and m * K < 3_000_000:
         # update type: X (K x n) = A (K x m) S (m x n), and the accumulating form, through the reference pipeline
         S = torch.view_as_complex(torch.randn(n, m, 2, generator=g, dtype=torch.float64)).to(c.device)
