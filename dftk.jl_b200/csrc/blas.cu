@@ -462,7 +462,7 @@ void kb_apply_nonlocal(dftk_b200_kblock* kb, const cplx* psi, cplx* hpsi, int64_
     // both projector products on the INT8 tensor cores (tcgen05.mma.kind::i8, TMA-fed; i8emu.cu / i8tc2.cu): the residue
     // planes of P are prepared once per k-block and serve P'psi (K-major operand) and P (D P'psi) (MN-major operand)
     if (!kb->i8_Pop.planes) kb->i8_Pop = i8_prepare(ctx, kb->P.p, kb->n_pw, np, kb->n_pw, kb->i8_planes, kb->i8_exps);
-    const I8Operand op_psi = i8_prepare(ctx, psi, kb->n_pw, n_bands, kb->n_pw, kb->i8_pool[7], kb->i8_epool[7]);
+    const I8Operand op_psi = i8_prepare(ctx, psi, kb->n_pw, n_bands, kb->n_pw, kb->i8_psi_planes, kb->i8_psi_exps);
     i8_gram(ctx, kb->i8_Pop, op_psi, proj, np, false);
     zgemm(ctx, 0, np, n_bands, np, one, kb->Dc.p, np, proj, np, zero, dproj, np);
     i8_update(ctx, 1, &kb->i8_Pop, dproj, np, n_bands, hpsi, kb->n_pw, 1.0, 1.0);

@@ -90,7 +90,9 @@ struct dftk_b200_ctx {
   ncclComm_t nccl = nullptr;
   int rank = 0, nranks = 1;
   int64_t launches = 0;
-  int gemm_backend = 0;   // 0 = own DMMA kernels, 1 = cuBLAS (A/B comparison only), 2 = experimental INT8-residue emulation (i8emu.cu)
+  int gemm_backend = 4;   // 4 (default) = INT8 tensor cores (tcgen05.mma.kind::i8, TMA-fed; i8emu.cu / i8tc2.cu) for contractions of at least
+                          // i8_min_rows rows, own FP64 DMMA kernels otherwise; 0 = DMMA kernels only; 1 = cuBLAS (A/B comparison only);
+                          // 2 / 3 = checkers of the INT8 scheme (CUDA-core pipeline / cp.async-fed tensor-core kernel)
   int band_chunk = 0;     // 0 = auto
   int fft_engine = 0;     // 0 = register two-pass engine where a factor pair exists, 1 = generic Stockham (applies to grids created afterwards)
   int gemm_stages = 2;    // cp.async ring depth of the DMMA GEMMs (2 -> 4 CTAs/SM, 3 -> 2 CTAs/SM)

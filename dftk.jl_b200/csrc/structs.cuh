@@ -70,6 +70,8 @@ struct dftk_b200_kblock {
   dftk::DevBuf<signed char> i8_pool[8];  // gemm_backend 4: residue planes of the LOBPCG blocks (cache slots of a solve)
   dftk::DevBuf<int> i8_epool[8];
   dftk::I8Operand i8_Pop;                // prepared projector table (kept for the lifetime of the block)
+  dftk::DevBuf<signed char> i8_psi_planes;   // planes of the orbitals entering P'psi (own buffer: the pool slots belong to LOBPCG's cache)
+  dftk::DevBuf<int> i8_psi_exps;
   dftk::DevBuf<signed char> i8_planes;   // gemm_backend 4: cached INT8 residue planes of P (built at first use)
   dftk::DevBuf<int> i8_exps;
   dftk::DevBuf<dftk::cplx> PD;    // P D (n_pw x n_proj), kept when n_proj is small: Hψ += (P D)(P'ψ) as two batched small products

@@ -55,13 +55,15 @@ int dftk_b200_mem_info(dftk_b200_ctx* ctx, int64_t* free_bytes, int64_t* total_b
 int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset);
 /* number of scheduler rounds (= host synchronisations) of the batched LOBPCG solves since creation / last reset */
 int64_t dftk_b200_sync_count(dftk_b200_ctx* ctx, int reset);
-/* tuning knobs: "gemm_backend" (0 = own DMMA kernels, 1 = cuBLAS, for A/B comparison and peak calibration only,
- * 2 / 3 = experimental INT8-residue emulation of C = A'B with the integer products on CUDA cores / on the tensor cores
- * (tcgen05.mma.kind::i8); groundwork that has not been validated on hardware yet),
- * "gemm_stages" (cp.async ring depth 2|3), "band_chunk" (bands per batched-FFT launch, 0 = auto),
- * "fft_engine" (0 = register two-pass engine where a factor pair exists, 1 = generic Stockham; applies to grids
- * created afterwards), "small_dense" (1 = fused small-matrix kernels for LOBPCG solves with <= 32 bands, 0 = the
- * GEMM + cuSOLVER sequence of the large path) */
+/* tuning knobs: "gemm_backend" (4 = default: the Gram-type and update-type products of contractions with at least
+ * "i8_min_rows" (32768) rows run on the INT8 tensor cores -- tcgen05.mma.kind::i8 fed by TMA, FP64-equivalent results through
+ * INT8 residues + CRT -- and everything smaller on the own FP64 DMMA kernels; 0 = DMMA kernels only; 1 = cuBLAS, for A/B
+ * comparison and peak calibration only; 2 / 3 = checkers of the INT8 scheme: integer products on CUDA cores / cp.async-fed
+ * tensor-core kernel), "gemm_stages" (cp.async ring depth 2|3 of the DMMA kernels), "band_chunk" (bands per batched-FFT
+ * launch, 0 = auto), "fft_engine" (0 = register two-pass engine where a factor pair exists, 1 = generic Stockham; applies to
+ * grids created afterwards), "small_dense" (1 = batched small-matrix path for LOBPCG solves with <= 32 bands, 0 = the GEMM +
+ * cuSOLVER sequence of the large path), "z_pipeline" (1 = persistent cp.async-pipelined fused z stage; default 0),
+ * "force_svd_fallback" (test hook) */
 int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value);
 
 /* ---- FFT grid (FFTGrid + build_fft_plans!, src/fft.jl:57-98,343-362) ---- */

@@ -33,6 +33,7 @@ for name, m, n in SHAPES:
     A = torch.view_as_complex(torch.randn(m, K, 2, generator=g, device=dev, dtype=torch.float64)) * decay.sqrt() / np.sqrt(K)
     B = torch.view_as_complex(torch.randn(n, K, 2, generator=g, device=dev, dtype=torch.float64)) * decay
     ref = torch.zeros((n, m), dtype=torch.complex128, device=dev)
+    ctx.set_option("gemm_backend", 0)
     ctx.zgemm("C", A, B, ref)
     fl = 8.0 * K * m * n
     for backend in BACKENDS:
@@ -45,7 +46,7 @@ for name, m, n in SHAPES:
         except Exception as e:
             res[f"{name}_backend{backend}"] = dict(error=repr(e))
         finally:
-            ctx.set_option("gemm_backend", 0)
+            ctx.set_option("gemm_backend", 4)
         print(name, backend, res[f"{name}_backend{backend}"], flush=True)
     del A, B, ref, C
     torch.cuda.empty_cache()
@@ -69,6 +70,6 @@ if os.environ.get("NONLOCAL_APPLY", "1") == "1":
         outs[backend] = out.clone()
         res[f"nonlocal_apply_backend{backend}"] = dict(ms=t, TFLOPs_equiv=16.0 * K * m * n / t / 1e9)
         print("nonlocal apply", backend, res[f"nonlocal_apply_backend{backend}"], flush=True)
-    ctx.set_option("gemm_backend", 0)
+    ctx.set_option("gemm_backend", 4)
     print("nonlocal apply: max |difference| backend 4 vs 0:", float((outs[4] - outs[0]).abs().max() / outs[0].abs().max()))
     json.dump(res, open("gpurun_out/i8_perf_probe.json", "w"), indent=1)

@@ -30,7 +30,7 @@ for backend in [int(b) for b in os.environ.get("BACKENDS", "0").split(",")]:
     lams[backend] = res["λ"]
     print("gemm_backend", backend, "lobpcg", dt, "s", res["n_iter"], "iterations ->", dt / max(1, res["n_iter"]), "s/iteration", res["n_matvec"],
           res["converged"], "max resid", float(np.max(res["residual_norms"][:M - 3])), flush=True)
-ctx.set_option("gemm_backend", 0)
+ctx.set_option("gemm_backend", 4)
 if len(lams) > 1:
     ks = sorted(lams)
     print("max |eigenvalue difference| between backends", ks, ":", float(np.abs(lams[ks[0]] - lams[ks[-1]]).max()))

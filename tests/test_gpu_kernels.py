@@ -76,7 +76,7 @@ def test_apply_h_terms(si, backend):
         check(kb.ctx.L.dftk_b200_apply_h(kb.h, _ptr(psi), _ptr(hout), psi.shape[0]), kb.ctx.h)
         np.testing.assert_allclose(hout, blk.matmul(psi.T).T, atol=1e-12 * scale)
     finally:
-        ctx().set_option("gemm_backend", 0)
+        ctx().set_option("gemm_backend", 4)
 
 
 @pytest.mark.parametrize("shape", [(1000, 7, 5), (4099, 70, 33), (129, 64, 32), (20000, 130, 1), (515, 3, 97)])
@@ -132,6 +132,7 @@ def test_i8_emulated_gemm_matches_fp64(shape, backend):
     A = (torch.view_as_complex(torch.randn(m, K, 2, generator=g, dtype=torch.float64)) * decay).to(c.device)
     B = (torch.view_as_complex(torch.randn(n, K, 2, generator=g, dtype=torch.float64)) * decay.sqrt()).to(c.device)
     ref = torch.zeros((n, m), dtype=torch.complex128, device=c.device)
+    c.set_option("gemm_backend", 0)                  # reference: the FP64 DMMA kernels
     c.zgemm("C", A, B, ref)
     c.set_option("gemm_backend", backend)
     c.set_option("i8_min_rows", 1024)
@@ -139,7 +140,7 @@ def test_i8_emulated_gemm_matches_fp64(shape, backend):
         C = torch.zeros_like(ref)
         c.zgemm("C", A, B, C)
     finally:
-        c.set_option("gemm_backend", 0)
+        c.set_option("gemm_backend", 4)
         c.set_option("i8_min_rows", 32768)
     assert (C - ref).abs().max().item() < 1e-14 * ref.abs().max().item() * K ** 0.5
     if backend == 4:
@@ -147,6 +148,7 @@ def test_i8_emulated_gemm_matches_fp64(shape, backend):
         S = torch.view_as_complex(torch.randn(n, m, 2, generator=g, dtype=torch.float64)).to(c.device)
         X0 = torch.view_as_complex(torch.randn(n, K, 2, generator=g, dtype=torch.float64)).to(c.device)
         want = torch.zeros_like(X0)
+        c.set_option("gemm_backend", 0)
         c.zgemm("N", A, S, want)
         c.set_option("gemm_backend", 4)
         c.set_option("i8_min_rows", 1024)
@@ -156,7 +158,7 @@ def test_i8_emulated_gemm_matches_fp64(shape, backend):
             Xa = X0.clone()
             c.zgemm("N", A, S, Xa, -1.0, 1.0)
         finally:
-            c.set_option("gemm_backend", 0)
+            c.set_option("gemm_backend", 4)
             c.set_option("i8_min_rows", 32768)
         scale = (A.abs().max(dim=1).values[None, :] * S.abs()).sum(dim=1).max().item()      # sum_k |A[:,k]|max |S[k,j]|
         assert (X - want).abs().max().item() < 1e-14 * scale
@@ -174,7 +176,7 @@ def test_i8_emulated_gemm_matches_fp64(shape, backend):
             Xa = X0.clone()
             c.zgemm("N", A, S, Xa, 1.0, 1.0)
         finally:
-            c.set_option("gemm_backend", 0)
+            c.set_option("gemm_backend", 4)
         scale = (A.abs().max(dim=0).values[:, None] * S.abs().max()).max().item() * m
         assert (X - want).abs().max().item() < 1e-14 * scale
         assert (Xa - X0 - want).abs().max().item() < 1e-14 * scale
@@ -216,7 +218,7 @@ def test_lobpcg_matches_oracle(si, backend, small):
         assert res3["converged"]
         np.testing.assert_allclose(res3["λ"], ref["λ"][:6], atol=1e-7)
     finally:
-        ctx().set_option("gemm_backend", 0)
+        ctx().set_option("gemm_backend", 4)
         ctx().set_option("small_dense", 1)
 
 

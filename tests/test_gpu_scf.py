@@ -319,7 +319,7 @@ def test_supercell_identity_on_int8_tensor_cores():
     try:
         rs = dftk.self_consistent_field(bs, tol=1e-9)
     finally:
-        ctx.set_option("gemm_backend", 0)
+        ctx.set_option("gemm_backend", 4)
         ctx.set_option("i8_min_rows", 32768)
     assert rs["converged"] and ru["converged"]
     assert abs(rs["energies"].total - n * ru["energies"].total) < n * 1e-8
