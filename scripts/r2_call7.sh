@@ -4,7 +4,7 @@ set -x
 mkdir -p gpurun_out
 export CUDA_VISIBLE_DEVICES=0
 M=102 REPS=2 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_|kr_|kb_' -c 400 --csv --log-file gpurun_out/launches_r2.csv python scripts/profile_probe.py > gpurun_out/ncu_a.log 2>&1
-M=51 REPS=1 timeout 900 ncu --set full --clock-control none -k regex:'kr_|k_zgemm' -c 12 -f -o /tmp/prof_r2 python scripts/profile_probe.py > gpurun_out/ncu_b.log 2>&1
+M=51 REPS=1 timeout 900 ncu --set full --clock-control none -k regex:'kr_|k_zgemm|k_i8_gemm|k_i8_crt_nn|k_i8_residues_ld4' -c 16 -f -o /tmp/prof_r2 python scripts/profile_probe.py > gpurun_out/ncu_b.log 2>&1
 ncu -i /tmp/prof_r2.ncu-rep --page raw --csv > gpurun_out/prof_r2_raw.csv 2>> gpurun_out/ncu_b.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_|kr_|kb_' -c 3000 --csv --log-file gpurun_out/launches_small_r2.csv python scripts/sync_probe.py > gpurun_out/ncu_c.log 2>&1
 tail -3 gpurun_out/ncu_a.log gpurun_out/ncu_b.log gpurun_out/ncu_c.log
