@@ -488,6 +488,43 @@ def run_gpu(args):
                                tol=args.scf_tol, s_per_iter=dt / max(1, res["n_iter"]))
         del X
 
+    # ---- single-k multi-GPU: the SAME Gamma block solved by all ranks together (plane-wave slabs: local Gram
+    #      products + NCCL allreduce, rows <-> bands exchange around H) against one GPU solving it alone, same start vectors
+    if world > 1 and args.scf and not args.no_slab:
+        try:
+            bs = dftk.PlaneWaveBasis(model, Ecut=w["Ecut"], kgrid=(1, 1, 1), architecture=arch, comm_slab=comm)
+            hs = dftk.energy_hamiltonian(bs, None, None, rho=dftk.guess_density(bs))[1]
+            kbs = hs[0].bind()
+            gs = torch.Generator(device=dev).manual_seed(4242)
+            X0 = torch.view_as_complex(torch.randn(M, kbs.n_pw, 2, generator=gs, device=dev, dtype=torch.float64))
+            X = X0.clone()
+            kbs.lobpcg_slab(X, tol=args.scf_tol, maxiter=1, n_conv_check=M - 3)      # untimed: workspaces, handles
+            out = {}
+            for name, solve in (("slab", kbs.lobpcg_slab), ("one_gpu", kbs.lobpcg)):
+                X.copy_(X0)
+                barrier()
+                t = time.perf_counter()
+                r = solve(X, tol=args.scf_tol, maxiter=args.scf_maxiter, n_conv_check=M - 3)
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device=dev)
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                out[name] = dict(seconds=float(dt.item()), n_iter=r["n_iter"], s_per_iter=float(dt.item()) / max(1, r["n_iter"]),
+                                 lam=r["λ"].copy(), exchange_GB=r.get("exchange_bytes", 0.0) / 1e9)
+            dl = float(np.abs(out["slab"]["lam"] - out["one_gpu"]["lam"]).max())
+            for v in out.values():
+                del v["lam"]
+            extra["single_k_slab"] = dict(n_ranks=world, n_pw=int(kbs.n_pw), n_bands=M, slab=out["slab"], one_gpu=out["one_gpu"],
+                                          speedup_vs_one_gpu=out["one_gpu"]["s_per_iter"] / out["slab"]["s_per_iter"],
+                                          max_dlambda_vs_one_gpu=dl,
+                                          what="LOBPCG on ONE k-point (C3 Gamma block) by all ranks: plane-wave slabs, Gram "
+                                               "products completed by ncclAllReduce, H applied band-wise after a rows<->bands exchange")
+            del X, X0, bs, hs, kbs
+            torch.cuda.empty_cache()
+        except Exception as e:
+            extra["single_k_slab"] = dict(error=repr(e))
+            if world > 1:
+                raise       # a rank that left a collective solve early would hang the others: fail loudly instead
+
     # ---- real SCF iterations on this workload (energy_hamiltonian + LOBPCG + occupations + density [+ allreduce]
     #      + consistent energies + mixing): the "SCF iteration time" half of the metric
     if args.scf_steps > 0:
@@ -654,6 +691,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-library", action="store_true", help="skip the cuFFT/cuBLAS formulation of the same H apply")
     ap.add_argument("--no-small", action="store_true", help="skip the full SCF of BASELINE config C2")
+    ap.add_argument("--no-slab", action="store_true", help="skip the single-k multi-GPU (plane-wave slab) LOBPCG section at N > 1")
     ap.add_argument("--no-sharded", action="store_true", help="skip the sharded SCFs of the BASELINE metal configs")
     ap.add_argument("--sharded", default="C5,C4", help="BASELINE configs whose (k, spin) blocks are sharded over the ranks")
     ap.add_argument("--no-scf", dest="scf", action="store_false",

@@ -45,6 +45,7 @@ SIGNATURES = {
     "dftk_b200_density_accumulate_multi": (c_int, [c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "dftk_b200_lobpcg": (c_int, [c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp,
                                  P(c_int), P(c_i64), P(c_int)]),
+    "dftk_b200_lobpcg_slab": (c_int, [c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dftk_b200_lobpcg_multi": (c_int, [c_i64, c_vp, c_vp, c_i64, c_dbl, c_int, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "dftk_b200_random_orbitals": (c_int, [c_i64, c_vp, c_vp, c_i64, ctypes.c_uint64]),
     "dftk_b200_density_accumulate": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),

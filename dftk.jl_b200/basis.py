@@ -126,15 +126,25 @@ class Kpoint:
 
 class PlaneWaveBasis:
     def __init__(self, model, *, Ecut, kgrid=(1, 1, 1), kshift=(0, 0, 0), fft_size=None, supersampling=2.0,
-                 architecture=None, comm_kpts=None, use_symmetries_for_kpoint_reduction=True,
+                 architecture=None, comm_kpts=None, comm_slab=None, use_symmetries_for_kpoint_reduction=True,
                  variational=True):
+        """`comm_kpts`: shard the (k, spin) blocks over the ranks (the reference's only distribution).
+        `comm_slab`: instead, let ALL ranks work on every k-block together (single-k multi-GPU, e.g. a Γ-only supercell):
+        the eigensolver cuts the plane-wave rows into one slab per rank (dftk_b200_lobpcg_slab), compute_density splits
+        the bands; everything else runs replicated on identical data."""
         from .architecture import B200
         if not variational:
             raise NotImplementedError("Non-variational calculations are not supported")
         self.model = model
         self.Ecut = float(Ecut)
         self.comm_kpts = comm_kpts or KpointComm()
-        self.architecture = architecture or B200(comm=self.comm_kpts if self.comm_kpts.nranks > 1 else None)
+        self.comm_slab = comm_slab if (comm_slab is not None and comm_slab.nranks > 1) else None
+        if self.comm_slab is not None and self.comm_kpts.nranks > 1:
+            raise NotImplementedError("comm_kpts and comm_slab cannot be combined yet: choose one distribution")
+        dist_comm = self.comm_slab or (self.comm_kpts if self.comm_kpts.nranks > 1 else None)
+        self.architecture = architecture or B200(comm=dist_comm)
+        if self.comm_slab is not None and getattr(self.architecture.ctx, "nranks", 1) != self.comm_slab.nranks:
+            raise ValueError("comm_slab needs an architecture whose context spans the same ranks (B200(comm=comm_slab))")
         dev = self.architecture.device
         self.kgrid = kgrid if isinstance(kgrid, (MonkhorstPack, ExplicitKpoints)) else MonkhorstPack(kgrid, kshift)
         symmetries_respect_rgrid = fft_size is None

@@ -594,6 +594,19 @@ int dftk_b200_lobpcg_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, void*
   API_END(ctx)
 }
 
+int dftk_b200_lobpcg_slab(dftk_b200_kblock* kb, void* X, int64_t n_bands, double tol, int miniter, int maxiter,
+                          int64_t n_conv_check, int use_tpa_preconditioner, double* lambda_host, double* resid_host,
+                          int* n_iter, int64_t* n_matvec, int* converged, double* exchange_bytes) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb && X && lambda_host && resid_host && n_iter && n_matvec && converged, "lobpcg_slab: NULL argument");
+  REQUIRE(maxiter >= 0 && miniter >= 0, "lobpcg_slab: bad iteration limits");
+  REQUIRE(is_device_ptr(X), "lobpcg_slab: orbitals must be device memory");
+  lobpcg_run_slab(kb, (cplx*)X, n_bands, tol, miniter, maxiter, n_conv_check, use_tpa_preconditioner != 0, lambda_host,
+                  resid_host, n_iter, n_matvec, converged, exchange_bytes);
+  API_END(ctx)
+}
+
 int dftk_b200_random_orbitals(int64_t n_blocks, dftk_b200_kblock* const* kbs, void* const* X, int64_t n_bands, uint64_t seed) {
   dftk_b200_ctx* ctx = (n_blocks > 0 && kbs && kbs[0]) ? kbs[0]->grid->ctx : nullptr;
   API_BEGIN

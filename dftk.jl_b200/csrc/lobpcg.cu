@@ -29,8 +29,9 @@ struct Mat {
 __global__ void k_residual(const cplx* __restrict__ AX, const cplx* __restrict__ X,
                            const double* __restrict__ lam, cplx* __restrict__ R, int64_t ld,
                            int64_t n_rows, const double* __restrict__ kin, double* __restrict__ norms,
-                           double* __restrict__ meankin) {
+                           double* __restrict__ meankin, int squared) {
   // one CTA per column: R = AX - X*lam; norms = ||R||; meankin = <X|kin|X>   (:443-445, precondprep!)
+  // squared != 0: norms = ||R||^2 of this rank's rows (slab solves: summed over the ranks, then k_sqrt_n)
   const int64_t col = blockIdx.x;
   const cplx* ax = AX + ld * col;
   const cplx* x = X + ld * col;
@@ -63,7 +64,7 @@ __global__ void k_residual(const cplx* __restrict__ AX, const cplx* __restrict__
       mk += __shfl_down_sync(0xffffffffu, mk, o);
     }
     if (threadIdx.x == 0) {
-      norms[col] = sqrt(s);
+      norms[col] = squared ? s : sqrt(s);
       meankin[col] = mk;
     }
   }
@@ -81,8 +82,12 @@ __global__ void k_precondition(cplx* __restrict__ R, int64_t ld, int64_t n_rows,
   R[i + ld * c] = make_double2(v.x * f, v.y * f);
 }
 
+__global__ void k_sqrt_n(double* __restrict__ v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = sqrt(v[i]);
+}
 __global__ void k_col_norms(const cplx* __restrict__ X, int64_t ld, int64_t n_rows,
-                            double* __restrict__ norms) {
+                            double* __restrict__ norms, int squared) {
   const int64_t col = blockIdx.x;
   const cplx* x = X + ld * col;
   double s = 0.0;
@@ -98,7 +103,7 @@ __global__ void k_col_norms(const cplx* __restrict__ X, int64_t ld, int64_t n_ro
     int nw = blockDim.x >> 5;
     s = threadIdx.x < nw ? rs[threadIdx.x] : 0.0;
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) norms[col] = sqrt(s);
+    if (threadIdx.x == 0) norms[col] = squared ? s : sqrt(s);
   }
 }
 
@@ -718,6 +723,28 @@ struct Lobpcg {
   static constexpr int N_PLANE_SLOTS = 8;
   PlaneEntry planes[N_PLANE_SLOTS];
   uint64_t plane_clock = 0;
+  // ---- plane-wave slabs of ONE k-block over the ranks of the context (single-k multi-GPU): every tall
+  //      block holds the rows [row0, row0 + N) of the n_pw coefficients.  Gram products, norms and dots are completed by an
+  //      NCCL allreduce on the solve's stream, the small dense algebra runs replicated on identical data, and H is applied
+  //      band-wise after a rows <-> bands exchange (grouped ncclSend/ncclRecv) -- `apply_h_slab` below.
+  bool slab = false;
+  int64_t Nfull = 0, row0 = 0;
+  std::vector<int64_t> row_off;            // first row of every rank (+ end)
+  cplx *slab_in = nullptr, *slab_out = nullptr, *slab_stage = nullptr;
+  int64_t slab_exchange_bytes = 0;
+  const double* kinp() const { return kb->kin.p + row0; }
+  void reduce(void* dev, size_t n_doubles) {
+    if (!slab || n_doubles == 0) return;
+    NCCL_CHECK(ncclAllReduce(dev, dev, n_doubles, ncclFloat64, ncclSum, ctx->nccl, ctx->stream));
+  }
+  // tall blocks are distributed, the small dense matrices (at most 3M < N rows) are replicated
+  bool is_dist(int64_t rows) const { return slab && rows == N; }
+  void reduce_block(cplx* C, int64_t ldc, int64_t rows, int64_t cols) {
+    if (!slab || rows == 0 || cols == 0) return;
+    reduce(C, (size_t)(2 * (ldc * (cols - 1) + rows)));
+  }
+  void apply_h_slab(Mat in, Mat out);
+
   bool use_i8(int64_t rows) const { return !small && ctx->gemm_backend == 4 && rows >= ctx->i8_min_rows; }
   I8Operand planes_for(const Mat& X) {
     for (auto& e : planes)
@@ -757,6 +784,9 @@ struct Lobpcg {
       coro_yield(co);
       return;
     }
+    // slab solves: what steers the iteration on the host is taken from rank 0, so that all ranks take the same branches
+    // even if their replicated small dense results differed in the last bit
+    if (slab) NCCL_CHECK(ncclBroadcast(dev, (void*)dev, bytes / sizeof(double), ncclFloat64, 0, ctx->nccl, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   }
@@ -839,7 +869,12 @@ struct Lobpcg {
       newop(OP_COLNORMS).u.colnorm = ColnormItem{X.p, X.ld, X.rows, (int)X.cols, out};
       return;
     }
-    LAUNCH(ctx, k_col_norms, (unsigned)X.cols, 256, 0, (const cplx*)X.p, X.ld, X.rows, out);
+    const bool dist = is_dist(X.rows);
+    LAUNCH(ctx, k_col_norms, (unsigned)X.cols, 256, 0, (const cplx*)X.p, X.ld, X.rows, out, dist ? 1 : 0);
+    if (dist) {
+      reduce(out, (size_t)X.cols);
+      LAUNCH(ctx, k_sqrt_n, nblk(X.cols), 256, 0, out, X.cols);
+    }
   }
   void scale_cols_inv(Mat X, const double* norms) {
     if (X.cols == 0) return;
@@ -863,7 +898,7 @@ struct Lobpcg {
       return;
     }
     touch(x, n_rows);
-    LAUNCH(ctx, k_randn_col, nblk(n_rows), 256, 0, x, n_rows, seed);
+    LAUNCH(ctx, k_randn_col, nblk(n_rows), 256, 0, x, n_rows, seed + (is_dist(n_rows) ? 2 * (uint64_t)row0 : 0));   // slabs: one global random column
   }
   void stats(const cplx* A, int64_t ld, int64_t r, int64_t c, double* out4) {
     matrix_stats(A, ld, r, c, d_stats);
@@ -897,6 +932,7 @@ struct Lobpcg {
           }
           oc += B[ib].cols;
         }
+        if (is_dist(A[0].rows)) reduce_block(C, ldc, orow_total(A), oc);
         return;
       }
     }
@@ -912,6 +948,12 @@ struct Lobpcg {
       }
       oc += B[ib].cols;
     }
+    if (!A.empty() && is_dist(A[0].rows)) reduce_block(C, ldc, orow_total(A), oc);
+  }
+  static int64_t orow_total(const std::vector<Mat>& A) {
+    int64_t n = 0;
+    for (auto& a : A) n += a.cols;
+    return n;
   }
   // out (=|+=) alpha * [Y blocks] * c     (mul!(res, ::LazyHcat, B, α, β), :124-132)
   void blocks_times(const std::vector<Mat>& Y, const cplx* c, int64_t ldc, int64_t ncols, Mat out,
@@ -1191,7 +1233,7 @@ void Lobpcg::ortho_svd_fallback(Mat X, cplx* tmp, int64_t ldtmp) {
         for (int64_t o = 0; o < n; ++o) {
           if (o == c || (std::find(bad.begin(), bad.end(), o) != bad.end() && o > c)) continue;
           Mat to = T.cols_range(o, 1);
-          zgemm(ctx, 2, 1, 1, X.rows, one, to.p, to.ld, tc.p, tc.ld, zero, tmpS, S3);
+          gram({to}, {tc}, tmpS, S3, false);
           zgemm(ctx, 0, X.rows, 1, 1, make_double2(-1, 0), to.p, to.ld, tmpS, S3, one, tc.p, tc.ld);
         }
       col_norms(tc, d_norms);
@@ -1208,11 +1250,58 @@ void Lobpcg::ortho_svd_fallback(Mat X, cplx* tmp, int64_t ldtmp) {
   small = was_small;
 }
 
+// H on a block of slab-distributed columns: rows <-> bands exchange, band-wise apply with the k-block's own kernels, and back.
+// Rank r applies H to the columns [c_r, c_r+1) of the block (split evenly); what it sends to rank q -- its rows of q's
+// columns -- is one contiguous piece of the column-major slab, what it receives is placed by a strided copy.
+static inline int64_t split_start(int64_t n, int parts, int i) { return (n / parts) * i + std::min<int64_t>(i, n % parts); }
+void Lobpcg::apply_h_slab(Mat in, Mat out) {
+  const int R = ctx->nranks, me = ctx->rank;
+  const int64_t nc = in.cols;
+  REQUIRE(in.ld == N && out.ld == N, "slab apply: unexpected leading dimension");
+  auto c0 = [&](int r) { return split_start(nc, R, r); };
+  const int64_t my_c0 = c0(me), my_nc = c0(me + 1) - my_c0;
+  // rows -> bands
+  NCCL_CHECK(ncclGroupStart());
+  for (int r = 0; r < R; ++r) {
+    const int64_t ncr = c0(r + 1) - c0(r), nr = row_off[r + 1] - row_off[r];
+    if (ncr > 0) NCCL_CHECK(ncclSend(in.p + N * c0(r), (size_t)(2 * N * ncr), ncclFloat64, r, ctx->nccl, ctx->stream));
+    if (my_nc > 0) NCCL_CHECK(ncclRecv(slab_stage + row_off[r] * my_nc, (size_t)(2 * nr * my_nc), ncclFloat64, r, ctx->nccl, ctx->stream));
+  }
+  NCCL_CHECK(ncclGroupEnd());
+  slab_exchange_bytes += 16 * (N * (nc - my_nc) + (Nfull - N) * my_nc);   // sent by this rank, both directions
+  if (my_nc > 0) {
+    for (int r = 0; r < R; ++r) {
+      const int64_t nr = row_off[r + 1] - row_off[r];
+      LAUNCH(ctx, k_copy2d, nblk(nr * my_nc), 256, 0, slab_in + row_off[r], Nfull, (const cplx*)(slab_stage + row_off[r] * my_nc), nr, nr, my_nc);
+    }
+    kb_apply_local_kinetic(kb, slab_in, slab_out, my_nc, kb->has_V, kb->has_kin, false);
+    kb_apply_nonlocal(kb, slab_in, slab_out, my_nc);
+    for (int r = 0; r < R; ++r) {
+      const int64_t nr = row_off[r + 1] - row_off[r];
+      LAUNCH(ctx, k_copy2d, nblk(nr * my_nc), 256, 0, slab_stage + row_off[r] * my_nc, nr, (const cplx*)(slab_out + row_off[r]), Nfull, nr, my_nc);
+    }
+  }
+  // bands -> rows
+  NCCL_CHECK(ncclGroupStart());
+  for (int r = 0; r < R; ++r) {
+    const int64_t ncr = c0(r + 1) - c0(r), nr = row_off[r + 1] - row_off[r];
+    if (my_nc > 0) NCCL_CHECK(ncclSend(slab_stage + row_off[r] * my_nc, (size_t)(2 * nr * my_nc), ncclFloat64, r, ctx->nccl, ctx->stream));
+    if (ncr > 0) NCCL_CHECK(ncclRecv(out.p + N * c0(r), (size_t)(2 * N * ncr), ncclFloat64, r, ctx->nccl, ctx->stream));
+  }
+  NCCL_CHECK(ncclGroupEnd());
+}
+
 void Lobpcg::prepare(SolveArgs& a) {
   (void)a;
   S3 = 3 * M;
   ldBYX = 2 * M > S3 ? 2 * M : S3;
-  cplx* big = kb->lobpcg_ws.ensure((size_t)11 * N * M);
+  const int64_t slab_cols = slab ? (M + ctx->nranks - 1) / ctx->nranks : 0;
+  cplx* big = kb->lobpcg_ws.ensure((size_t)11 * N * M + (size_t)3 * Nfull * slab_cols);
+  if (slab) {
+    slab_in = big + 11 * N * M;
+    slab_out = slab_in + Nfull * slab_cols;
+    slab_stage = slab_out + Nfull * slab_cols;
+  }
   AX = big; R = big + N * M; AR = big + 2 * N * M; P = big + 3 * N * M; AP = big + 4 * N * M;
   nX = big + 5 * N * M; nAX = big + 6 * N * M; nR = big + 7 * N * M; nP = big + 8 * N * M; nAP = big + 9 * N * M;
   tmpN = big + 10 * N * M;
@@ -1256,6 +1345,7 @@ void Lobpcg::body(SolveArgs& a) {
       return;
     }
     touch(out);
+    if (slab) return apply_h_slab(in, out);
     kb_apply_local_kinetic(kb, in.p, out.p, in.cols, kb->has_V, kb->has_kin, false);
     kb_apply_nonlocal(kb, in.p, out.p, in.cols);
   };
@@ -1282,6 +1372,7 @@ void Lobpcg::body(SolveArgs& a) {
   } else {
     columnwise_dots(ctx, Xio, N, AX, N, N, M, d_cdots);
     columnwise_dots(ctx, Xio, N, Xio, N, N, M, d_cdots + M);
+    reduce(d_cdots, (size_t)(4 * M));
     LAUNCH(ctx, k_compute_lambda, nblk(M), 256, 0, (const cplx*)d_cdots, (const cplx*)(d_cdots + M), d_lam, M);
   }
 
@@ -1333,8 +1424,12 @@ void Lobpcg::body(SolveArgs& a) {
     } else {
       touch(nR + N * a0, N * Ma);
       LAUNCH(ctx, k_residual, (unsigned)Ma, 256, 0, (const cplx*)(nAX + N * a0), (const cplx*)(nX + N * a0),
-             (const double*)(d_lam + a0), nR + N * a0, N, N, use_prec ? (const double*)kb->kin.p : nullptr,
-             d_norms, d_meankin);
+             (const double*)(d_lam + a0), nR + N * a0, N, N, use_prec ? kinp() : nullptr,
+             d_norms, d_meankin, slab ? 1 : 0);
+      if (slab) {
+        reduce(d_norms, (size_t)(M + Ma));          // [d_norms, d_norms + M) and the Ma entries of d_meankin behind it
+        LAUNCH(ctx, k_sqrt_n, nblk(Ma), 256, 0, d_norms, Ma);
+      }
       get(norms.data(), d_norms, Ma * sizeof(double));
     }
     for (int64_t i = 0; i < Ma; ++i) RH(a0 + i, niter) = norms[i];
@@ -1343,7 +1438,7 @@ void Lobpcg::body(SolveArgs& a) {
         newop(OP_PRECOND).u.precond = PrecondItem{nR + N * a0, N, N, (int)Ma, kb->kin.p, d_meankin};
       } else {
         touch(nR + N * a0, N * Ma);
-        LAUNCH(ctx, k_precondition, nblk(N * Ma), 256, 0, nR + N * a0, N, N, Ma, (const double*)kb->kin.p,
+        LAUNCH(ctx, k_precondition, nblk(N * Ma), 256, 0, nR + N * a0, N, N, Ma, kinp(),
                (const double*)d_meankin);
       }
     }
@@ -1666,6 +1761,48 @@ void tall_gram(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int nA, const cpl
   exec.gram_batch(v);
   CUDA_CHECK(cudaMemcpyAsync(out_host, C, (size_t)nA * nB * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// One k-block solved by all ranks of the context together (single-k multi-GPU): X (n_pw x M, identical on every rank on
+// entry) is cut into row slabs, the slab solve runs (Lobpcg with slab = true), and the converged slabs are put together
+// again on every rank by one broadcast per rank.
+int lobpcg_run_slab(dftk_b200_kblock* kb, cplx* Xfull, int64_t M, double tol, int miniter, int maxiter, int64_t n_conv_check,
+                    bool use_prec, double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec, int* converged,
+                    double* exchange_bytes) {
+  dftk_b200_ctx* ctx = kb->grid->ctx;
+  REQUIRE(ctx->nccl != nullptr, "lobpcg_slab: the context has no communicator (use ctx_create_dist)");
+  const int R = ctx->nranks, me = ctx->rank;
+  const int64_t Nf = kb->n_pw;
+  Lobpcg L;
+  init_solver(L, kb, M, use_prec);
+  L.small = false;
+  L.slab = true;
+  L.Nfull = Nf;
+  L.row_off.resize(R + 1);
+  for (int r = 0; r <= R; ++r) L.row_off[r] = split_start(Nf, R, r);
+  L.row0 = L.row_off[me];
+  L.N = L.row_off[me + 1] - L.row_off[me];
+  REQUIRE(split_start(Nf, R, R) - split_start(Nf, R, R - 1) > 3 * M,
+          "lobpcg_slab: every rank needs more than 3 n_bands plane-wave rows");
+  SolveArgs A{nullptr, tol, miniter, maxiter, n_conv_check, lambda_host, resid_host, n_iter, n_matvec, converged};
+  L.prepare(A);
+  // the slab of X lives behind the solver's workspace
+  cplx* Xloc = kb->slab_x.ensure((size_t)L.N * M);
+  LAUNCH(ctx, k_copy2d, nblk(L.N * M), 256, 0, Xloc, L.N, (const cplx*)(Xfull + L.row0), Nf, L.N, M);
+  A.X = Xloc;
+  L.body(A);
+  // reassemble: the staging area (Nfull x ceil(M/R) x 3 complex numbers behind the workspace) takes one rank's slab at a time
+  int64_t max_rows = 0;
+  for (int r = 0; r < R; ++r) max_rows = std::max(max_rows, L.row_off[r + 1] - L.row_off[r]);
+  cplx* stage = kb->slab_stage.ensure((size_t)max_rows * M);
+  for (int r = 0; r < R; ++r) {
+    const int64_t nr = L.row_off[r + 1] - L.row_off[r];
+    NCCL_CHECK(ncclBroadcast(Xloc, stage, (size_t)(2 * nr * M), ncclFloat64, r, ctx->nccl, ctx->stream));
+    LAUNCH(ctx, k_copy2d, nblk(nr * M), 256, 0, Xfull + L.row_off[r], Nf, (const cplx*)stage, nr, nr, M);
+  }
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (exchange_bytes) *exchange_bytes = (double)L.slab_exchange_bytes;
+  return 0;
 }
 
 void lobpcg_set_attributes() {

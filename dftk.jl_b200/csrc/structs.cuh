@@ -84,6 +84,7 @@ struct dftk_b200_kblock {
   dftk::DevBuf<dftk::cplx> proj;      // n_proj x n_bands (+ D*proj)
   dftk::DevBuf<dftk::cplx> lobpcg_ws; // big LOBPCG workspace
   dftk::DevBuf<dftk::cplx> small_ws;  // small dense LOBPCG workspace
+  dftk::DevBuf<dftk::cplx> slab_x, slab_stage;   // slab-distributed solve (lobpcg_run_slab): this rank's rows of X, reassembly staging
   dftk::DevBuf<double> wts;
   dftk::DevBuf<double> scal;          // per-block scalars of a LOBPCG solve (several blocks are solved side by side)
 };
@@ -165,6 +166,9 @@ int lobpcg_run(dftk_b200_kblock* kb, cplx* X, int64_t M, double tol, int miniter
 int lobpcg_run_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, double tol, int miniter,
                      int maxiter, int64_t n_conv_check, bool use_prec, double* lambda_host, double* resid_host, int* n_iter,
                      int64_t* n_matvec, int* converged);
+int lobpcg_run_slab(dftk_b200_kblock* kb, cplx* Xfull, int64_t M, double tol, int miniter, int maxiter, int64_t n_conv_check,
+                    bool use_prec, double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec, int* converged,
+                    double* exchange_bytes);
 void random_orbitals_multi(int64_t n_blocks, dftk_b200_kblock* const* kbs, cplx* const* Xs, int64_t M, uint64_t seed);
 void band_energies_multi(int64_t n, dftk_b200_kblock* const* kbs, const cplx* const* psi, const int* n_bands, int64_t ld_out,
                          double* ekin_host, double* enl_host);

@@ -14,18 +14,31 @@ def compute_density(basis, psi, occupation, *, occupation_threshold=0.0, packed_
     n_tail = 0 if packed_sums is None else len(packed_sums)
     flat = torch.zeros(n_spin * basis.N + n_tail, dtype=torch.float64, device=dev)
     rho = flat[:n_spin * basis.N].view(n_spin, basis.N)
+    slab = getattr(basis, "comm_slab", None)
     if n_tail:
-        flat[n_spin * basis.N:] = torch.as_tensor(np.asarray(packed_sums, dtype=np.float64), device=dev)
+        tail = np.asarray(packed_sums, dtype=np.float64)
+        if slab is not None:
+            tail = tail / slab.nranks        # replicated partial sums: the allreduce below adds them up again
+        flat[n_spin * basis.N:] = torch.as_tensor(tail, device=dev)
     from .device import density_accumulate_multi
-    ws = []
+    ws, psis = [], []
     for ik in range(len(basis.kblocks)):
         occ = np.asarray(occupation[ik], dtype=float)
         w = np.where(np.abs(occ) >= occupation_threshold, occ * basis.kweights[ik], 0.0)
         nb = int(np.max(np.nonzero(w)[0]) + 1) if np.any(w != 0) else 0
+        if slab is not None:                 # every rank accumulates its share of the bands of every block
+            lo, hi = (nb * slab.rank) // slab.nranks, (nb * (slab.rank + 1)) // slab.nranks
+            ws.append(w[lo:hi])
+            psis.append(psi[ik].contiguous()[lo:hi])
+            continue
         ws.append(w[:nb])
+        psis.append(psi[ik].contiguous())
     # one library call for all blocks of this rank (rows psi[ik][:nb] are contiguous: a band is a row)
-    density_accumulate_multi(basis.kblocks, [p.contiguous() for p in psi], ws, rho)
-    if basis.comm_kpts.nranks > 1:
+    density_accumulate_multi(basis.kblocks, psis, ws, rho)
+    if slab is not None:
+        slab.n_collectives += 1
+        basis.architecture.ctx.allreduce(flat, "sum")
+    elif basis.comm_kpts.nranks > 1:
         basis.comm_kpts.n_collectives += 1
         basis.architecture.ctx.allreduce(flat, "sum")          # mpi_sum!(ρ) of densities.jl:46 + the packed scalars
     sums = flat[n_spin * basis.N:].cpu().numpy() if n_tail else None

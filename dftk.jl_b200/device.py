@@ -306,6 +306,19 @@ class KBlock:
         return dict(λ=lam, X=X, residual_norms=res, n_iter=nit.value, n_matvec=nmv.value,
                     converged=bool(conv.value))
 
+    def lobpcg_slab(self, X, tol=1e-6, miniter=1, maxiter=100, n_conv_check=None, prec=True):
+        """dftk_b200_lobpcg_slab: this k-block solved by ALL ranks of the context together (plane-wave slabs; collective).
+        X (n_bands, n_pw) must be identical on every rank; it holds the eigenvectors on every rank afterwards."""
+        nb = X.shape[0]
+        lam, res = np.zeros(nb), np.zeros(nb)
+        nit, conv, nmv, xb = c_int(), c_int(), c_i64(), ctypes.c_double()
+        check(self.ctx.L.dftk_b200_lobpcg_slab(self.h, _ptr(X), nb, float(tol), miniter, maxiter,
+                                               nb if n_conv_check is None else int(n_conv_check), int(prec),
+                                               _ptr(lam), _ptr(res), ctypes.byref(nit), ctypes.byref(nmv),
+                                               ctypes.byref(conv), ctypes.byref(xb)), self.ctx.h)
+        return dict(λ=lam, X=X, residual_norms=res, n_iter=nit.value, n_matvec=nmv.value,
+                    converged=bool(conv.value), exchange_bytes=xb.value)
+
     def density_accumulate(self, psi, occ_w, rho):
         occ_w = np.ascontiguousarray(occ_w, dtype=np.float64)
         check(self.ctx.L.dftk_b200_density_accumulate(self.h, _ptr(psi), _ptr(occ_w), psi.shape[0], _ptr(rho)),

@@ -26,8 +26,20 @@ def lobpcg_hyper(A, X0, *, prec=True, tol=None, maxiter=100, miniter=1, n_conv_c
     returns (; λ, X, residual_norms, n_iter, converged, n_matvec).  X0 is consumed (updated in place)."""
     if tol is None:
         tol = 20 * A.shape[1] * np.finfo(float).eps
-    return A.bind().lobpcg(X0, tol=tol, miniter=miniter, maxiter=maxiter, n_conv_check=n_conv_check,
-                           prec=bool(prec))
+    kw = dict(tol=tol, miniter=miniter, maxiter=maxiter, n_conv_check=n_conv_check, prec=bool(prec))
+    if _use_slabs(A, X0):
+        return A.bind().lobpcg_slab(X0, **kw)
+    return A.bind().lobpcg(X0, **kw)
+
+
+def _use_slabs(A, X0):
+    """Plane-wave-slab solve over all ranks of basis.comm_slab: for blocks of the large-solve regime whose slabs keep more
+    than 3 n_bands rows each (the solver's own size requirement); small blocks stay replicated."""
+    comm = getattr(A.basis, "comm_slab", None)
+    if comm is None:
+        return False
+    nb, n_pw = X0.shape
+    return nb > 32 and n_pw // comm.nranks > 3 * nb
 
 
 def _lobpcg_hyper_batched(blocks, X0s, *, prec=True, tol=None, maxiter=100, miniter=1, n_conv_check=None):
@@ -36,6 +48,9 @@ def _lobpcg_hyper_batched(blocks, X0s, *, prec=True, tol=None, maxiter=100, mini
     from .device import lobpcg_multi
     if tol is None:
         tol = 20 * blocks[0].shape[1] * np.finfo(float).eps
+    if blocks and _use_slabs(blocks[0], X0s[0]):
+        return [lobpcg_hyper(b, x, prec=prec, tol=tol, maxiter=maxiter, miniter=miniter, n_conv_check=n_conv_check)
+                for b, x in zip(blocks, X0s)]
     return lobpcg_multi([b.bind() for b in blocks], X0s, tol=tol, miniter=miniter, maxiter=maxiter,
                         n_conv_check=n_conv_check, prec=bool(prec))
 

@@ -136,6 +136,18 @@ int dftk_b200_lobpcg_multi(int64_t n_blocks, dftk_b200_kblock* const* kblocks, v
                            double tol, int miniter, int maxiter, int64_t n_conv_check, int use_tpa_preconditioner,
                            double* lambda_host, double* resid_host, int* n_iter, int64_t* n_matvec, int* converged);
 
+/* ONE k-block solved by all ranks of a distributed context together (single-k multi-GPU; the reference cannot use more
+ * than one process for one k-point, docs/src/tricks/parallelization.md:83-84).  Collective: every rank of the context calls
+ * it with its own k-block handle of the SAME k-point and the same X (n_pw × n_bands, device, identical on all ranks).
+ * The plane-wave rows of every tall block of lobpcg_hyper_impl.jl are cut into one slab per rank: Gram products, norms and
+ * Rayleigh quotients are local products completed by ncclAllReduce, the small dense algebra (Cholesky, Rayleigh-Ritz) runs
+ * replicated, and H is applied band-wise after a rows <-> bands exchange over NCCL point-to-point.  On return X holds the
+ * eigenvectors on every rank; the other outputs are those of dftk_b200_lobpcg.  exchange_bytes (may be NULL): bytes this
+ * rank sent in the rows <-> bands exchanges. */
+int dftk_b200_lobpcg_slab(dftk_b200_kblock* kb, void* X, int64_t n_bands, double tol, int miniter, int maxiter,
+                          int64_t n_conv_check, int use_tpa_preconditioner, double* lambda_host, double* resid_host,
+                          int* n_iter, int64_t* n_matvec, int* converged, double* exchange_bytes);
+
 /* Start vectors (random_orbitals, src/common/orbitals.jl:82-87: orthonormalised complex normal numbers) for several
  * k-blocks at once: X[i] (n_pw_i × n_bands, device) is filled and orthonormalised on the device. */
 int dftk_b200_random_orbitals(int64_t n_blocks, dftk_b200_kblock* const* kblocks, void* const* X, int64_t n_bands,
