@@ -498,11 +498,14 @@ def run_gpu(args):
             gs = torch.Generator(device=dev).manual_seed(4242)
             X0 = torch.view_as_complex(torch.randn(M, kbs.n_pw, 2, generator=gs, device=dev, dtype=torch.float64))
             X = X0.clone()
-            kbs.lobpcg_slab(X, tol=args.scf_tol, maxiter=1, n_conv_check=M - 3)      # untimed: workspaces, handles
             out = {}
             for name, solve in (("slab", kbs.lobpcg_slab), ("one_gpu", kbs.lobpcg)):
+                # untimed first pass: workspaces, residue-plane pools of all blocks (P / AP appear from the 2nd iteration),
+                # cuSOLVER handles, NCCL point-to-point connections
+                solve(X, tol=args.scf_tol, maxiter=args.scf_maxiter, n_conv_check=M - 3)
                 X.copy_(X0)
                 barrier()
+                dist.barrier()
                 t = time.perf_counter()
                 r = solve(X, tol=args.scf_tol, maxiter=args.scf_maxiter, n_conv_check=M - 3)
                 torch.cuda.synchronize()

@@ -732,6 +732,8 @@ struct Lobpcg {
   std::vector<int64_t> row_off;            // first row of every rank (+ end)
   cplx *slab_in = nullptr, *slab_out = nullptr, *slab_stage = nullptr;
   int64_t slab_exchange_bytes = 0;
+  bool slab_timing = false;                // DFTK_B200_PROFILE: synchronising wall clock of the exchange / apply phases
+  double slab_t_exchange = 0, slab_t_apply = 0;
   const double* kinp() const { return kb->kin.p + row0; }
   void reduce(void* dev, size_t n_doubles) {
     if (!slab || n_doubles == 0) return;
@@ -1260,6 +1262,15 @@ void Lobpcg::apply_h_slab(Mat in, Mat out) {
   REQUIRE(in.ld == N && out.ld == N, "slab apply: unexpected leading dimension");
   auto c0 = [&](int r) { return split_start(nc, R, r); };
   const int64_t my_c0 = c0(me), my_nc = c0(me + 1) - my_c0;
+  double t0 = 0;
+  auto tick = [&]() {
+    if (!slab_timing) return 0.0;
+    cudaStreamSynchronize(ctx->stream);
+    const double t = SectionProf::now(), dt = t - t0;
+    t0 = t;
+    return dt;
+  };
+  tick();
   // rows -> bands
   NCCL_CHECK(ncclGroupStart());
   for (int r = 0; r < R; ++r) {
@@ -1269,6 +1280,7 @@ void Lobpcg::apply_h_slab(Mat in, Mat out) {
   }
   NCCL_CHECK(ncclGroupEnd());
   slab_exchange_bytes += 16 * (N * (nc - my_nc) + (Nfull - N) * my_nc);   // sent by this rank, both directions
+  slab_t_exchange += tick();
   if (my_nc > 0) {
     for (int r = 0; r < R; ++r) {
       const int64_t nr = row_off[r + 1] - row_off[r];
@@ -1281,6 +1293,7 @@ void Lobpcg::apply_h_slab(Mat in, Mat out) {
       LAUNCH(ctx, k_copy2d, nblk(nr * my_nc), 256, 0, slab_stage + row_off[r] * my_nc, nr, (const cplx*)(slab_out + row_off[r]), Nfull, nr, my_nc);
     }
   }
+  slab_t_apply += tick();
   // bands -> rows
   NCCL_CHECK(ncclGroupStart());
   for (int r = 0; r < R; ++r) {
@@ -1289,6 +1302,7 @@ void Lobpcg::apply_h_slab(Mat in, Mat out) {
     if (ncr > 0) NCCL_CHECK(ncclRecv(out.p + N * c0(r), (size_t)(2 * N * ncr), ncclFloat64, r, ctx->nccl, ctx->stream));
   }
   NCCL_CHECK(ncclGroupEnd());
+  slab_t_exchange += tick();
 }
 
 void Lobpcg::prepare(SolveArgs& a) {
@@ -1334,6 +1348,7 @@ void Lobpcg::body(SolveArgs& a) {
   prof.on = !small && getenv("DFTK_B200_PROFILE") != nullptr;
   prof.aggregate = prof.on && atoi(getenv("DFTK_B200_PROFILE")) == 2;
   prof.st = ctx->stream;
+  slab_timing = slab && prof.on;
 
   Mat X{Xio, N, N, M};
   auto mat = [&](cplx* p) { return Mat{p, N, N, M}; };
@@ -1499,6 +1514,9 @@ void Lobpcg::body(SolveArgs& a) {
     niter++;
   }
   prof.report(niter);
+  if (slab_timing)
+    fprintf(stderr, "[dftk_b200 slab rank %d] H applies: exchange %.3f s (%.2f GB sent), band-wise apply incl. staging copies %.3f s\n",
+            ctx->rank, slab_t_exchange, slab_exchange_bytes / 1e9, slab_t_apply);
   // final_retval :325-338
   get(lam_h.data(), d_lam, M * sizeof(double));
   std::vector<int64_t> perm(M);
