@@ -170,6 +170,12 @@ int dftk_b200_ctx_destroy(dftk_b200_ctx* ctx) {
   }
   if (ctx->batch_ring_h) cudaFreeHost(ctx->batch_ring_h);
   if (ctx->batch_gather_h) cudaFreeHost(ctx->batch_gather_h);
+  if (ctx->batch_ring_h2) cudaFreeHost(ctx->batch_ring_h2);
+  if (ctx->batch_gather_h2) cudaFreeHost(ctx->batch_gather_h2);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->batch_streams[i]) cudaStreamDestroy(ctx->batch_streams[i]);
+    if (ctx->batch_events[i]) cudaEventDestroy(ctx->batch_events[i]);
+  }
   if (ctx->nccl) ncclCommDestroy(ctx->nccl);
   if (ctx->cublas) cublasDestroy(ctx->cublas);
   if (ctx->solver_params) cusolverDnDestroyParams(ctx->solver_params);
@@ -228,6 +234,7 @@ int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value) {
   else if (n == "small_dense") ctx->small_dense = (int)value;
   else if (n == "i8_min_rows") ctx->i8_min_rows = value;
   else if (n == "z_pipeline") ctx->z_pipeline = (int)value;
+  else if (n == "batch_pipeline") ctx->batch_pipeline = (int)value;
   else if (n == "force_svd_fallback") ctx->force_svd_fallback = (int)value;
   else if (n == "fft_engine") ctx->fft_engine = (int)value;  // 0 = register two-pass where available, 1 = generic
   else throw Error(DFTK_B200_EINVAL, "set_option: unknown option " + n);

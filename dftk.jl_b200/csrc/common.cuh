@@ -121,6 +121,20 @@ struct dftk_b200_ctx {
   double* batch_gather_h = nullptr;
   dftk::DevBuf<signed char> i8_tmp_planes;   // gemm_backend 4: planes of an operand prepared inside a generic zgemm call
   dftk::DevBuf<int> i8_tmp_exps;
+  // second executor of the pipelined batched solves (two groups of k-blocks on two streams: while one group's round runs on
+  // the GPU, the host records and issues the other group's): its own descriptor ring, gather buffer, Gram workspace, counters
+  dftk::DevBuf<char> batch_ring2, batch_ws2;
+  dftk::DevBuf<double> batch_gather2;
+  dftk::DevBuf<int> small_counter2;
+  char* batch_ring_h2 = nullptr;
+  double* batch_gather_h2 = nullptr;
+  cudaStream_t batch_streams[2] = {nullptr, nullptr};
+  cudaEvent_t batch_events[2] = {nullptr, nullptr};
+  cudaStream_t batch_user_stream = nullptr;   // the context's own stream while a pipelined batch has swapped ctx->stream
+  bool batch_pipelined = false;
+  int batch_pipeline = 0;     // option: 1 = two pipelined groups for batches of >= 8 k-blocks, 0 (default) = one group (one sync per
+                              // round).  Measured equal within 1 % on C4 / C5 and 15 % slower on C2 (profiles/README.md): the rounds
+                              // are bound by the kernels, not by the host, so the doubled launch count buys nothing
   int64_t batch_rounds = 0;   // scheduler rounds (= host synchronisations) of the batched solves since creation / reset
 };
 

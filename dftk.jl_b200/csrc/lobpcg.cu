@@ -374,18 +374,39 @@ struct BatchExec {
   size_t gather_used = 0;
   int64_t rounds = 0;
 
-  explicit BatchExec(dftk_b200_ctx* c) : ctx(c) {
+  // the executor's device-side buffers: group 0 = the context's, group 1 = the second set (pipelined batches)
+  DevBuf<char>* ring_d = nullptr;
+  DevBuf<double>* gather_d = nullptr;
+  DevBuf<char>* ws_d = nullptr;
+  DevBuf<int>* counter_d = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool in_flight = false;
+
+  explicit BatchExec(dftk_b200_ctx* c, int group = 0) : ctx(c) {
     // pinned staging buffers are created once per context (cudaMallocHost costs about a millisecond)
     ring_cap = (size_t)4 << 20;
     gather_cap = (size_t)1 << 18;
-    if (!ctx->batch_ring_h) {
-      CUDA_CHECK(cudaMallocHost((void**)&ctx->batch_ring_h, ring_cap));
-      CUDA_CHECK(cudaMallocHost((void**)&ctx->batch_gather_h, gather_cap * sizeof(double)));
+    char** rh = group ? &ctx->batch_ring_h2 : &ctx->batch_ring_h;
+    double** gh = group ? &ctx->batch_gather_h2 : &ctx->batch_gather_h;
+    if (!*rh) {
+      CUDA_CHECK(cudaMallocHost((void**)rh, ring_cap));
+      CUDA_CHECK(cudaMallocHost((void**)gh, gather_cap * sizeof(double)));
     }
-    ring_h = ctx->batch_ring_h;
-    gather_h = ctx->batch_gather_h;
-    ctx->batch_ring.ensure(ring_cap);
-    ctx->batch_gather.ensure(gather_cap);
+    ring_h = *rh;
+    gather_h = *gh;
+    ring_d = group ? &ctx->batch_ring2 : &ctx->batch_ring;
+    gather_d = group ? &ctx->batch_gather2 : &ctx->batch_gather;
+    ws_d = group ? &ctx->batch_ws2 : &ctx->gemm_ws;
+    counter_d = group ? &ctx->small_counter2 : &ctx->small_counter;
+    ring_d->ensure(ring_cap);
+    gather_d->ensure(gather_cap);
+    if (!ctx->batch_events[group]) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->batch_events[group], cudaEventDisableTiming));
+    ev = ctx->batch_events[group];
+  }
+  // arrival counters of kb_gram, zeroed (also recovers from an aborted solve)
+  void reset_counters(size_t n) {
+    counter_d->ensure(std::max<size_t>(n, 256));
+    CUDA_CHECK(cudaMemsetAsync(counter_d->p, 0, counter_d->cap * sizeof(int), ctx->stream));
   }
   BatchExec(const BatchExec&) = delete;
   BatchExec& operator=(const BatchExec&) = delete;
@@ -400,7 +421,7 @@ struct BatchExec {
       REQUIRE(bytes <= ring_cap, "batched LOBPCG: descriptor ring too small");
     }
     memcpy(ring_h + ring_off, host, n_bytes);
-    char* d = ctx->batch_ring.p + ring_off;
+    char* d = ring_d->p + ring_off;
     CUDA_CHECK(cudaMemcpyAsync(d, ring_h + ring_off, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
     ring_off += bytes;
     return d;
@@ -432,16 +453,13 @@ struct BatchExec {
       max_ctas = std::max(max_ctas, it.n_ctas);
       smem = std::max(smem, (size_t)SMALL_TR * (nA + nB) * sizeof(cplx));
     }
-    cplx* ws = (cplx*)ctx->gemm_ws.ensure(ws_total * sizeof(cplx));
-    if (ctx->small_counter.cap < v.size()) {
-      unsigned* c = (unsigned*)ctx->small_counter.ensure(std::max<size_t>(v.size(), 256));
-      CUDA_CHECK(cudaMemsetAsync(c, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));
-    }
+    cplx* ws = (cplx*)ws_d->ensure(ws_total * sizeof(cplx));
+    if (counter_d->cap < v.size()) reset_counters(v.size());
     size_t off = 0;
     for (size_t i = 0; i < v.size(); ++i) {
       const int nA = v[i].A.start[v[i].A.n], nB = v[i].B.start[v[i].B.n];
       v[i].ws = ws + off;
-      v[i].counter = (unsigned*)ctx->small_counter.p + i;
+      v[i].counter = (unsigned*)counter_d->p + i;
       off += (size_t)v[i].n_ctas * nA * nB;
     }
     const GramItem* d = upload(v);
@@ -626,7 +644,7 @@ struct BatchExec {
           scatter.push_back({d.host_dst, {gather_used, d.n}});
           gather_used += d.n;
         }
-        LAUNCH(ctx, kb_gather, n, 64, 0, upload(v), ctx->batch_gather.p);
+        LAUNCH(ctx, kb_gather, n, 64, 0, upload(v), gather_d->p);
         break;
       }
       default: throw Error(DFTK_B200_EINVAL, "batched LOBPCG: unknown operation");
@@ -642,7 +660,12 @@ struct BatchExec {
   }
 
   // run everything recorded by the solves since the last round; one stream synchronisation at the end
-  void flush(std::vector<std::unique_ptr<Coro>>& coros) {
+  void flush(std::vector<Coro*>& coros) {
+    issue(coros);
+    complete(coros);
+  }
+  // enqueue everything recorded by the solves since the last round (launches + the round's result gather) on ctx->stream
+  void issue(std::vector<Coro*>& coros) {
     bool any = false;
     for (auto& c : coros) any = any || c->cursor < c->ops.size();
     if (!any) return;
@@ -664,8 +687,15 @@ struct BatchExec {
       launch(best, batch);
     }
     if (gather_used)
-      CUDA_CHECK(cudaMemcpyAsync(gather_h, ctx->batch_gather.p, gather_used * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      CUDA_CHECK(cudaMemcpyAsync(gather_h, gather_d->p, gather_used * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaEventRecord(ev, ctx->stream));
+    in_flight = true;
+  }
+  // wait for the issued round, hand the gathered values to the solves
+  void complete(std::vector<Coro*>& coros) {
+    if (!in_flight) return;
+    CUDA_CHECK(cudaEventSynchronize(ev));
+    in_flight = false;
     for (auto& s : scatter) memcpy(s.first, gather_h + s.second.first, s.second.second * sizeof(double));
     scatter.clear();
     gather_used = 0;
@@ -1211,6 +1241,14 @@ void Lobpcg::ortho_svd_fallback(Mat X, cplx* tmp, int64_t ldtmp) {
   // a rare recovery path, executed synchronously with the direct (immediate-launch) forms even inside a batched solve
   const bool was_small = small;
   small = false;
+  // inside a pipelined batch the other group may be in flight and ctx->stream is this group's stream: the direct forms use the
+  // context's workspaces and its cuBLAS / cuSOLVER handles (bound to the context's own stream), so everything is drained first
+  // and the recovery runs on the context's own stream
+  cudaStream_t group_stream = ctx->stream;
+  if (was_small && ctx->batch_pipelined) {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    ctx->stream = ctx->batch_user_stream;
+  }
   try {
     const cplx one = make_double2(1, 0), zero = make_double2(0, 0);
     gram({X}, {X}, Ochol, S3, true);
@@ -1247,9 +1285,11 @@ void Lobpcg::ortho_svd_fallback(Mat X, cplx* tmp, int64_t ldtmp) {
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   } catch (...) {
     small = was_small;
+    ctx->stream = group_stream;
     throw;
   }
   small = was_small;
+  ctx->stream = group_stream;
 }
 
 // H on a block of slab-distributed columns: rows <-> bands exchange, band-wise apply with the k-block's own kernels, and back.
@@ -1544,10 +1584,19 @@ void Lobpcg::body(SolveArgs& a) {
 // the recorded operations of all blocks into shared launches, one stream synchronisation per round.
 static void run_batched(dftk_b200_ctx* ctx, std::vector<Lobpcg>& L, std::vector<std::function<void()>>& bodies) {
   const int64_t n_blocks = (int64_t)L.size();
-  BatchExec exec(ctx);
-  if (ctx->small_counter.cap < (size_t)std::max<int64_t>(n_blocks, 256))
-    ctx->small_counter.ensure(std::max<size_t>((size_t)n_blocks, 256));
-  CUDA_CHECK(cudaMemsetAsync(ctx->small_counter.p, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));   // also recovers from an aborted solve
+  // Two pipelined groups when the batch is large enough: each group has its own stream and executor, and while the GPU runs
+  // one group's round the host resumes the other group's solves, records and issues their next round -- the host work and the
+  // synchronisation bubble of a round hide behind the other group's kernels (and small kernels of the two streams overlap).
+  bool pipelined = ctx->batch_pipeline != 0 && n_blocks >= 8;
+  for (auto& l : L)      // blocks whose nonlocal term would take the large (context-workspace) path stay in one group
+    pipelined = pipelined && (l.kb->n_proj == 0 || (l.kb->n_proj <= SMALL_MAX_COLS && l.kb->PD.p != nullptr));
+  const int G = pipelined ? 2 : 1;
+  cudaStream_t user = ctx->stream;
+  if (pipelined) {
+    for (int g = 0; g < 2; ++g)
+      if (!ctx->batch_streams[g]) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->batch_streams[g], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamSynchronize(user));     // the inputs are ready before the groups start on their own streams
+  }
   std::vector<std::unique_ptr<Coro>> coros;
   ucontext_t main_uc;
   ucontext_t* saved_main = g_main_uc;
@@ -1566,46 +1615,79 @@ static void run_batched(dftk_b200_ctx* ctx, std::vector<Lobpcg>& L, std::vector<
     c->uc.uc_link = nullptr;
     makecontext(&c->uc, (void (*)())coro_entry, 0);
   }
+  std::vector<Coro*> members[2];
+  for (int64_t i = 0; i < n_blocks; ++i) members[i % G].push_back(coros[i].get());   // interleaved: similar work per group
+  std::unique_ptr<BatchExec> exec[2];
+  for (int g = 0; g < G; ++g) exec[g].reset(new BatchExec(ctx, g));
+  auto stream_of = [&](int g) { return pipelined ? ctx->batch_streams[g] : user; };
   std::string first_err;
   int first_code = 0;
-  try {
-    while (true) {
-      bool all_done = true;
-      for (auto& c : coros) {
-        if (c->finished || c->waiting_align) continue;
-        g_coro = c.get();
-        swapcontext(&main_uc, &c->uc);
-        if (c->failed && first_err.empty()) {
-          first_err = c->err;
-          first_code = c->err_code;
-        }
-      }
-      if (!first_err.empty()) break;
-      exec.flush(coros);
-      bool all_waiting = true;
-      for (auto& c : coros) {
-        if (c->finished) continue;
-        all_done = false;
-        if (!c->waiting_align) all_waiting = false;
-      }
-      if (all_done) break;
-      if (all_waiting)
-        for (auto& c : coros) c->waiting_align = false;
-    }
-  } catch (...) {
+  auto restore = [&]() {
+    ctx->stream = user;
+    ctx->batch_pipelined = false;
     g_main_uc = saved_main;
     g_coro = saved_coro;
-    cudaStreamSynchronize(ctx->stream);
+  };
+  // resume the runnable solves of a group until each needs a value from the device, then enqueue what they recorded
+  auto advance = [&](int g) {
+    ctx->stream = stream_of(g);
+    for (Coro* c : members[g]) {
+      if (c->finished || c->waiting_align) continue;
+      g_coro = c;
+      swapcontext(&main_uc, &c->uc);
+      if (c->failed && first_err.empty()) {
+        first_err = c->err;
+        first_code = c->err_code;
+      }
+    }
+    if (first_err.empty()) exec[g]->issue(members[g]);
+    ctx->stream = user;
+  };
+  try {
+    ctx->batch_user_stream = user;
+    ctx->batch_pipelined = pipelined;
+    for (int g = 0; g < G; ++g) {
+      ctx->stream = stream_of(g);
+      exec[g]->reset_counters((size_t)members[g].size());
+      ctx->stream = user;
+    }
+    bool done[2] = {false, G == 1};
+    for (int g = 0; g < G && first_err.empty(); ++g) advance(g);
+    while (first_err.empty() && !(done[0] && done[1])) {
+      for (int g = 0; g < G && first_err.empty(); ++g) {
+        if (done[g]) continue;
+        ctx->stream = stream_of(g);
+        exec[g]->complete(members[g]);
+        ctx->stream = user;
+        bool all_done = true, all_waiting = true;
+        for (Coro* c : members[g]) {
+          if (c->finished) continue;
+          all_done = false;
+          if (!c->waiting_align) all_waiting = false;
+        }
+        if (all_done) {
+          done[g] = true;
+          continue;
+        }
+        if (all_waiting)
+          for (Coro* c : members[g]) c->waiting_align = false;
+        advance(g);
+      }
+    }
+  } catch (...) {
+    restore();
+    cudaDeviceSynchronize();
     throw;
   }
-  g_main_uc = saved_main;
-  g_coro = saved_coro;
+  restore();
   for (auto& l : L) l.co = nullptr;
+  for (int g = 0; g < G; ++g) ctx->batch_rounds += exec[g]->rounds;
   if (!first_err.empty()) {
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     throw Error(first_code, first_err);
   }
-  ctx->batch_rounds += exec.rounds;
+  if (pipelined)
+    for (int g = 0; g < 2; ++g) CUDA_CHECK(cudaStreamSynchronize(ctx->batch_streams[g]));
 }
 
 static void init_solver(Lobpcg& L, dftk_b200_kblock* kb, int64_t M, bool use_prec) {
@@ -1691,10 +1773,7 @@ void band_energies_multi(int64_t n, dftk_b200_kblock* const* kbs, const cplx* co
   if (n <= 0) return;
   dftk_b200_ctx* ctx = kbs[0]->grid->ctx;
   BatchExec exec(ctx);
-  if (ctx->small_counter.cap < (size_t)std::max<int64_t>(n, 256)) {
-    ctx->small_counter.ensure(std::max<size_t>((size_t)n, 256));
-    CUDA_CHECK(cudaMemsetAsync(ctx->small_counter.p, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));
-  }
+  if (ctx->small_counter.cap < (size_t)std::max<int64_t>(n, 256)) exec.reset_counters((size_t)n);
   std::vector<KinDotsItem> kd;
   std::vector<GramItem> gr;
   std::vector<NlEnergyItem> ne;
@@ -1760,10 +1839,7 @@ void tall_gram(dftk_b200_ctx* ctx, const cplx* A, int64_t lda, int nA, const cpl
                cplx* out_host) {
   REQUIRE(nA >= 1 && nB >= 1 && nA <= SMALL_MAX_COLS && nB <= SMALL_MAX_COLS, "tall_gram: 1 <= columns <= 96");
   BatchExec exec(ctx);
-  if (ctx->small_counter.cap < 256) {
-    ctx->small_counter.ensure(256);
-    CUDA_CHECK(cudaMemsetAsync(ctx->small_counter.p, 0, ctx->small_counter.cap * sizeof(int), ctx->stream));
-  }
+  if (ctx->small_counter.cap < 256) exec.reset_counters(256);
   cplx* C = (cplx*)ctx->batch_gather.p;       // >= 96 x 96 complex fit the gather buffer
   GramItem g{};
   g.A.n = g.B.n = 1;

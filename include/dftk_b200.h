@@ -63,6 +63,8 @@ int64_t dftk_b200_sync_count(dftk_b200_ctx* ctx, int reset);
  * launch, 0 = auto), "fft_engine" (0 = register two-pass engine where a factor pair exists, 1 = generic Stockham; applies to
  * grids created afterwards), "small_dense" (1 = batched small-matrix path for LOBPCG solves with <= 32 bands, 0 = the GEMM +
  * cuSOLVER sequence of the large path), "z_pipeline" (1 = persistent cp.async-pipelined fused z stage; default 0),
+ * "batch_pipeline" (1 = batched solves of >= 8 k-blocks run as two groups on two streams so that one group's host work hides
+ * behind the other's kernels; 0 = one group, one stream synchronisation per round; default 0: measured no faster),
  * "force_svd_fallback" (test hook) */
 int dftk_b200_set_option(dftk_b200_ctx* ctx, const char* name, int64_t value);
 

@@ -15,6 +15,7 @@ model, bk, desc = bench.baseline_model(dftk, name)
 basis = dftk.PlaneWaveBasis(model, **bk)
 mixing = dftk.KerkerMixing() if model.temperature > 0 else None
 ctx = basis.architecture.ctx
+ctx.set_option("batch_pipeline", int(os.environ.get("PIPE", "1")))
 dftk.self_consistent_field(basis, tol=1e-8, mixing=mixing, seed=3)
 torch.cuda.synchronize()
 ctx.launch_count(reset=True); ctx.sync_count(reset=True)
@@ -27,6 +28,6 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t
 torch.cuda.profiler.stop()
 n = res["n_iter"]
-print(f"{name}: {desc}: {dt:.3f} s, {n} SCF steps, {ctx.launch_count() / n:.0f} launches and {ctx.sync_count() / n:.0f} LOBPCG host syncs per step, "
+print(f"{name} batch_pipeline={os.environ.get('PIPE', '1')}: {desc}: {dt:.3f} s, {n} SCF steps, {ctx.launch_count() / n:.0f} launches and {ctx.sync_count() / n:.0f} LOBPCG host syncs per step, "
       f"blocks {len(basis.kpoints)}, bands {res['psi'][0].shape[0]}", flush=True)
 print("per step (s, summed LOBPCG iterations):", [(round(a, 4), b) for a, b in steps], flush=True)
