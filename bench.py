@@ -521,7 +521,25 @@ def run_gpu(args):
                                           max_dlambda_vs_one_gpu=dl,
                                           what="LOBPCG on ONE k-point (C3 Gamma block) by all ranks: plane-wave slabs, Gram "
                                                "products completed by ncclAllReduce, H applied band-wise after a rows<->bands exchange")
-            del X, X0, bs, hs, kbs
+            del X, X0
+            # real SCF iterations of the SAME single-k-point cell with all ranks on it (slab eigensolver, band-shared density,
+            # one density/energy allreduce per step): compare with the `scf` key of the N = 1 line
+            if args.scf_steps > 0 or args.slab_scf_steps > 0:
+                st, it = [], []
+
+                def cbs(info):
+                    st.append(info["time_step"])
+                    it.append(int(np.sum(info["diagonalization"]["n_iter"])))
+                c0 = comm.n_collectives
+                tq = time.perf_counter()
+                rs = dftk.self_consistent_field(bs, tol=1e-10, maxiter=max(args.scf_steps, args.slab_scf_steps), callback=cbs, seed=1)
+                torch.cuda.synchronize()
+                extra["single_k_slab"]["scf"] = dict(step_seconds=st, lobpcg_iters_per_step=it, total_s=time.perf_counter() - tq,
+                                                     energy_per_atom=rs["energies"].total / len(pos), last_drho=rs["history_drho"][-1],
+                                                     collectives_per_step=(comm.n_collectives - c0) / max(1, rs["n_iter"]),
+                                                     note="same cell, tolerances and seed as the `scf` key of the N = 1 line")
+                del rs
+            del bs, hs, kbs
             torch.cuda.empty_cache()
         except Exception as e:
             extra["single_k_slab"] = dict(error=repr(e))
@@ -701,6 +719,7 @@ def main():
                     help="skip the LOBPCG timing (eigensolver part of an SCF step, a few iterations)")
     ap.set_defaults(scf=True)
     ap.add_argument("--scf-steps", type=int, default=3, help="real SCF iterations to time (0 = skip)")
+    ap.add_argument("--slab-scf-steps", type=int, default=0, help="SCF iterations of the single-k slab section when --scf-steps is 0")
     ap.add_argument("--scf-tol", type=float, default=0.025)
     ap.add_argument("--scf-maxiter", type=int, default=6)
     args = ap.parse_args()
