@@ -492,6 +492,8 @@ def run_gpu(args):
     #      products + NCCL allreduce, rows <-> bands exchange around H) against one GPU solving it alone, same start vectors
     if world > 1 and args.scf and not args.no_slab:
         try:
+            kb.trim()        # the 503-band solve above left ~60 GB of solver scratch on this rank's k-block
+            torch.cuda.empty_cache()
             bs = dftk.PlaneWaveBasis(model, Ecut=w["Ecut"], kgrid=(1, 1, 1), architecture=arch, comm_slab=comm)
             hs = dftk.energy_hamiltonian(bs, None, None, rho=dftk.guess_density(bs))[1]
             kbs = hs[0].bind()
@@ -522,6 +524,8 @@ def run_gpu(args):
                                           what="LOBPCG on ONE k-point (C3 Gamma block) by all ranks: plane-wave slabs, Gram "
                                                "products completed by ncclAllReduce, H applied band-wise after a rows<->bands exchange")
             del X, X0
+            kbs.trim()       # scratch of the one-GPU comparison solve
+            torch.cuda.empty_cache()
             # real SCF iterations of the SAME single-k-point cell with all ranks on it (slab eigensolver, band-shared density,
             # one density/energy allreduce per step): compare with the `scf` key of the N = 1 line
             if args.scf_steps > 0 or args.slab_scf_steps > 0:

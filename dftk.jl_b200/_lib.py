@@ -36,6 +36,7 @@ SIGNATURES = {
     "dftk_b200_kblock_set_potential": (c_int, [c_vp, c_vp]),
     "dftk_b200_grid_set_potential": (c_int, [c_vp, c_int, c_vp]),
     "dftk_b200_kblock_use_grid_potential": (c_int, [c_vp, c_int]),
+    "dftk_b200_kblock_trim": (c_int, [c_vp]),
     "dftk_b200_fft_sphere_to_real": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int]),
     "dftk_b200_fft_real_to_sphere": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int]),
     "dftk_b200_apply_h": (c_int, [c_vp, c_vp, c_vp, c_i64]),

@@ -423,6 +423,27 @@ int dftk_b200_grid_set_potential(dftk_b200_grid* grid, int spin, const double* V
   API_END(ctx)
 }
 
+int dftk_b200_kblock_trim(dftk_b200_kblock* kb) {
+  dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
+  API_BEGIN
+  REQUIRE(kb, "kblock_trim: NULL k-block");
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  kb->lobpcg_ws.release();
+  kb->small_ws.release();
+  kb->slab_x.release();
+  kb->slab_stage.release();
+  kb->i8_psi_planes.release();
+  kb->i8_psi_exps.release();
+  for (int i = 0; i < 8; ++i) {
+    kb->i8_pool[i].release();
+    kb->i8_epool[i].release();
+  }
+  kb->W1.release();
+  kb->W2.release();
+  kb->proj.release();
+  API_END(ctx)
+}
+
 int dftk_b200_kblock_use_grid_potential(dftk_b200_kblock* kb, int spin) {
   dftk_b200_ctx* ctx = kb ? kb->grid->ctx : nullptr;
   API_BEGIN

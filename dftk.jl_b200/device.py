@@ -306,6 +306,11 @@ class KBlock:
         return dict(λ=lam, X=X, residual_norms=res, n_iter=nit.value, n_matvec=nmv.value,
                     converged=bool(conv.value))
 
+    def trim(self):
+        """dftk_b200_kblock_trim: free the scratch this block has grown (solver workspaces, residue-plane pools, FFT
+        intermediates); later calls re-grow what they need."""
+        check(self.ctx.L.dftk_b200_kblock_trim(self.h), self.ctx.h)
+
     def lobpcg_slab(self, X, tol=1e-6, miniter=1, maxiter=100, n_conv_check=None, prec=True):
         """dftk_b200_lobpcg_slab: this k-block solved by ALL ranks of the context together (plane-wave slabs; collective).
         X (n_bands, n_pw) must be identical on every rank; it holds the eigenvectors on every rank afterwards."""

@@ -97,6 +97,11 @@ int dftk_b200_kblock_set_potential(dftk_b200_kblock* kb, const double* V);
 int dftk_b200_grid_set_potential(dftk_b200_grid* grid, int spin, const double* V);
 int dftk_b200_kblock_use_grid_potential(dftk_b200_kblock* kb, int spin);
 
+/* Frees the scratch a k-block has grown (LOBPCG workspaces, INT8 residue-plane pools of the solver, FFT intermediates); the
+ * operator data (kinetic energies, projectors and their prepared planes, potential) stays, and every later call re-grows what
+ * it needs.  A 503-band solve at n_pw = 264 859 holds ≈ 60 GB of such scratch (no reference counterpart: Julia's GC does this). */
+int dftk_b200_kblock_trim(dftk_b200_kblock* kb);
+
 /* ---- sphere <-> real-space transforms (ifft!/fft! with Gvec_mapping, src/fft.jl:110-122,162-172) */
 int dftk_b200_fft_sphere_to_real(dftk_b200_kblock* kb, const void* psi /*n_pw×n_bands*/,
                                  void* out_real /*N_fft×n_bands complex*/, int64_t n_bands,

@@ -287,6 +287,25 @@ def test_lobpcg_svd_fallback_recovers_rank_deficient_block(si):
             ctx().set_option("force_svd_fallback", 0)
 
 
+def test_kblock_trim_frees_scratch_and_calls_regrow_it(si):
+    """dftk_b200_kblock_trim: the scratch of earlier calls (solver workspaces, FFT intermediates) is returned to the device;
+    the operator data stays, so the same calls give the same results afterwards."""
+    from gpu_common import to_dev
+    blk, kb = si["blk"], si["kb"]
+    rng = np.random.default_rng(11)
+    X0 = rng.standard_normal((blk.kpt.n_G, 6)) + 1j * rng.standard_normal((blk.kpt.n_G, 6))
+    psi = to_dev(X0.T)
+    h0 = kb.apply_h(psi).clone()
+    r0 = kb.lobpcg(to_dev(X0.T), tol=1e-9, maxiter=200)
+    free_before = kb.ctx.mem_info()[0]
+    kb.trim()
+    assert kb.ctx.mem_info()[0] >= free_before
+    assert (kb.apply_h(psi) - h0).abs().max().item() <= 1e-13 * h0.abs().max().item()
+    r1 = kb.lobpcg(to_dev(X0.T), tol=1e-9, maxiter=200)
+    assert r0["converged"] and r1["converged"]
+    np.testing.assert_allclose(r1["λ"], r0["λ"], atol=1e-9)
+
+
 @pytest.mark.parametrize("fft_size,Ecut", [((40, 45, 48), 30), ((32, 27, 36), 14), ((33, 40, 21), 10),
                                            ((75, 64, 60), 60)])
 def test_fft_engines_agree_with_oracle(fft_size, Ecut):
