@@ -480,12 +480,23 @@ def run_gpu(args):
         kb.lobpcg(X, tol=args.scf_tol, maxiter=1, n_conv_check=M - 3)   # untimed: cuSOLVER handles, 23 GB workspace
         X.copy_(psi)
         torch.cuda.synchronize()
+        try:
+            ctx.lobpcg_flops(reset=True)
+        except Exception:
+            pass
         t = time.perf_counter()
         res = kb.lobpcg(X, tol=args.scf_tol, maxiter=args.scf_maxiter, n_conv_check=M - 3)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t
         extra["lobpcg"] = dict(seconds=dt, n_iter=res["n_iter"], n_matvec=res["n_matvec"], converged=res["converged"],
                                tol=args.scf_tol, s_per_iter=dt / max(1, res["n_iter"]))
+        try:
+            fl = ctx.lobpcg_flops(reset=True)
+            extra["lobpcg"].update(gemm_flop=fl, gemm_TFLOPs_fp64_equivalent=fl / dt / 1e12,
+                                   note="GEMM flops executed (Gram, update, Cholesky-QR and nonlocal products, counted in the library) over "
+                                        "the WHOLE solve time, which also contains the FFT part of H, the eigensolver and host syncs")
+        except Exception as e:
+            extra["lobpcg"]["gemm_flop_error"] = repr(e)
         del X
 
     # ---- single-k multi-GPU: the SAME Gamma block solved by all ranks together (plane-wave slabs: local Gram

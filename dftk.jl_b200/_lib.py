@@ -27,6 +27,7 @@ SIGNATURES = {
     "dftk_b200_mem_info": (c_int, [c_vp, P(c_i64), P(c_i64)]),
     "dftk_b200_launch_count": (c_i64, [c_vp, c_int]),
     "dftk_b200_sync_count": (c_i64, [c_vp, c_int]),
+    "dftk_b200_lobpcg_flops": (c_dbl, [c_vp, c_int]),
     "dftk_b200_set_option": (c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "dftk_b200_grid_create": (c_int, [c_vp, c_int, c_int, c_int, c_dbl, P(c_vp)]),
     "dftk_b200_grid_destroy": (c_int, [c_vp]),

@@ -217,6 +217,13 @@ int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset) {
   return v;
 }
 
+double dftk_b200_lobpcg_flops(dftk_b200_ctx* ctx, int reset) {
+  if (!ctx) return -1.0;
+  const double v = ctx->lobpcg_flops;
+  if (reset) ctx->lobpcg_flops = 0.0;
+  return v;
+}
+
 int64_t dftk_b200_sync_count(dftk_b200_ctx* ctx, int reset) {
   if (!ctx) return -1;
   int64_t v = ctx->batch_rounds;

@@ -135,6 +135,7 @@ struct dftk_b200_ctx {
   int batch_pipeline = 0;     // option: 1 = two pipelined groups for batches of >= 8 k-blocks, 0 (default) = one group (one sync per
                               // round).  Measured equal within 1 % on C4 / C5 and 15 % slower on C2 (profiles/README.md): the rounds
                               // are bound by the kernels, not by the host, so the doubled launch count buys nothing
+  double lobpcg_flops = 0.0;  // FP64-equivalent GEMM flops executed by the large-path LOBPCG solves (Gram, update, Cholesky-QR, nonlocal) since reset
   int64_t batch_rounds = 0;   // scheduler rounds (= host synchronisations) of the batched solves since creation / reset
 };
 

@@ -777,6 +777,7 @@ struct Lobpcg {
   }
   void apply_h_slab(Mat in, Mat out);
 
+  double flops = 0.0;      // GEMM flops executed by this solve (large path), added to ctx->lobpcg_flops at the end
   bool use_i8(int64_t rows) const { return !small && ctx->gemm_backend == 4 && rows >= ctx->i8_min_rows; }
   I8Operand planes_for(const Mat& X) {
     for (auto& e : planes)
@@ -959,7 +960,10 @@ struct Lobpcg {
         for (size_t ib = 0; ib < B.size(); ++ib) {
           int64_t orow = 0;
           for (size_t ia = 0; ia < A.size(); ++ia) {
-            if (!(upper_only && ib < ia)) i8_gram(ctx, opA[ia], opB[ib], C + orow + ldc * oc, ldc, upper_only && ia == ib);
+            if (!(upper_only && ib < ia)) {
+              i8_gram(ctx, opA[ia], opB[ib], C + orow + ldc * oc, ldc, upper_only && ia == ib);
+              flops += 8.0 * (double)A[ia].rows * A[ia].cols * B[ib].cols * ((upper_only && ia == ib) ? 0.5 : 1.0);
+            }
             orow += A[ia].cols;
           }
           oc += B[ib].cols;
@@ -973,9 +977,11 @@ struct Lobpcg {
     for (size_t ib = 0; ib < B.size(); ++ib) {
       int64_t orow = 0;
       for (size_t ia = 0; ia < A.size(); ++ia) {
-        if (!(upper_only && ib < ia))
+        if (!(upper_only && ib < ia)) {
           zgemm(ctx, 2, A[ia].cols, B[ib].cols, A[ia].rows, one, A[ia].p, A[ia].ld, B[ib].p, B[ib].ld,
                 zero, C + orow + ldc * oc, ldc, /*upper tiles only on diagonal blocks*/ upper_only && ia == ib);
+          flops += 8.0 * (double)A[ia].rows * A[ia].cols * B[ib].cols * ((upper_only && ia == ib) ? 0.5 : 1.0);
+        }
         orow += A[ia].cols;
       }
       oc += B[ib].cols;
@@ -991,6 +997,7 @@ struct Lobpcg {
   void blocks_times(const std::vector<Mat>& Y, const cplx* c, int64_t ldc, int64_t ncols, Mat out,
                     double alpha, double beta) {
     if (small) return small_blocks_times(Y, c, ldc, ncols, out, alpha, beta);
+    for (auto& y : Y) flops += 8.0 * (double)out.rows * y.cols * ncols;
     if (!Y.empty() && use_i8(Y[0].rows) && Y.size() <= 3 && ncols >= 16) {
       bool ok = true;
       for (auto& y : Y) ok = ok && y.cols >= 32;
@@ -1092,6 +1099,7 @@ struct Lobpcg {
         continue;
       }
       // X <- X * invR   (rmul!(X, invR))
+      flops += 8.0 * (double)X.rows * n * n * 0.5;      // invR is upper triangular
       if (use_i8(X.rows) && n >= 32) {
         const I8Operand opX = planes_for(X);        // prepared for the Gram product above
         touch(tmp, ldtmp * n);
@@ -1400,6 +1408,7 @@ void Lobpcg::body(SolveArgs& a) {
       return;
     }
     touch(out);
+    flops += 16.0 * (double)(slab ? Nfull : N) * kb->n_proj * (slab ? (double)in.cols / ctx->nranks : (double)in.cols);
     if (slab) return apply_h_slab(in, out);
     kb_apply_local_kinetic(kb, in.p, out.p, in.cols, kb->has_V, kb->has_kin, false);
     kb_apply_nonlocal(kb, in.p, out.p, in.cols);
@@ -1577,7 +1586,10 @@ void Lobpcg::body(SolveArgs& a) {
   *a.n_iter = final_iter;
   *a.n_matvec = n_matvec;
   *a.converged = maxres < tol ? 1 : 0;
-  if (!small) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (!small) {
+    ctx->lobpcg_flops += flops;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  }
 }
 
 // Batched execution: one coroutine per k-block runs `bodies[i]` (which records operations on L[i].co); BatchExec merges

@@ -60,6 +60,10 @@ class Context:
     def launch_count(self, reset=False):
         return int(self.L.dftk_b200_launch_count(self.h, 1 if reset else 0))
 
+    def lobpcg_flops(self, reset=False):
+        """FP64-equivalent GEMM flops executed by the large-path LOBPCG solves since the last reset."""
+        return float(self.L.dftk_b200_lobpcg_flops(self.h, 1 if reset else 0))
+
     def sync_count(self, reset=False):
         """Scheduler rounds (host synchronisations) of the batched LOBPCG solves."""
         return int(self.L.dftk_b200_sync_count(self.h, 1 if reset else 0))

@@ -55,6 +55,10 @@ int dftk_b200_mem_info(dftk_b200_ctx* ctx, int64_t* free_bytes, int64_t* total_b
 int64_t dftk_b200_launch_count(dftk_b200_ctx* ctx, int reset);
 /* number of scheduler rounds (= host synchronisations) of the batched LOBPCG solves since creation / last reset */
 int64_t dftk_b200_sync_count(dftk_b200_ctx* ctx, int reset);
+/* FP64-equivalent GEMM flops the large-path LOBPCG solves of this context have executed since the last reset: Gram-type products
+ * (8 rows·m·n, half of it for the upper-triangle-only diagonal blocks), update-type products, the X R^-1 updates of ortho! and the
+ * two projector products of every H apply -- the "sum actually executed" of SURVEY §8d.  Batched small-block solves are not counted. */
+double dftk_b200_lobpcg_flops(dftk_b200_ctx* ctx, int reset);
 /* tuning knobs: "gemm_backend" (4 = default: the Gram-type and update-type products of contractions with at least
  * "i8_min_rows" (32768) rows run on the INT8 tensor cores -- tcgen05.mma.kind::i8 fed by TMA, FP64-equivalent results through
  * INT8 residues + CRT -- and everything smaller on the own FP64 DMMA kernels; 0 = DMMA kernels only; 1 = cuBLAS, for A/B
