@@ -54,17 +54,42 @@ HD void small_gram_cta(int cta, long long rows_per_cta, long long n_rows, const 
       Bs[r * nB + j] = r < nr ? small_col_ptr(B, j)[r0 + r] : make_double2(0.0, 0.0);
     }
     TSYNC();
-    TLOOP(o, total) {
-      const int i = o % nA, j = o / nA;
-      if (upper_only && small_block_of(B, j) < small_block_of(A, i)) continue;
-      double ax = 0.0, ay = 0.0;
-      for (int r = 0; r < nr; ++r) {
-        const cplx a = As[r * nA + i], b = Bs[r * nB + j];
-        ax += a.x * b.x + a.y * b.y;     // conj(a) * b
-        ay += a.x * b.y - a.y * b.x;
+    // register tile of 1 x 4 outputs per thread: one shared-memory read of a (consecutive threads, consecutive i) serves four
+    // columns of B (the same address for the whole warp: broadcast) -- the plain one-output form was bound by shared-memory
+    // reads at two 16-byte loads per four FMAs.  Each output still accumulates its rows in ascending order.
+    const int nJt = (nB + 3) / 4;
+    TLOOP(t, nA * nJt) {
+      const int i = t % nA, j0 = (t / nA) * 4;
+      const int bi = small_block_of(A, i);
+      int jq[4];
+      bool act[4];
+      bool any = false;
+      for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q;
+        act[q] = j < nB && !(upper_only && small_block_of(B, j) < bi);
+        jq[q] = j < nB ? j : nB - 1;          // inactive lanes read a valid element and drop the result
+        any = any || act[q];
       }
-      out[o].x += ax;
-      out[o].y += ay;
+      if (!any) continue;
+      double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int r = 0; r < nr; ++r) {
+        const cplx a = As[r * nA + i];
+        const cplx* brow = Bs + r * nB;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q) {
+          const cplx b = brow[jq[q]];
+          ax[q] += a.x * b.x + a.y * b.y;     // conj(a) * b
+          ay[q] += a.x * b.y - a.y * b.x;
+        }
+      }
+      for (int q = 0; q < 4; ++q)
+        if (act[q]) {
+          const int o = i + nA * (j0 + q);
+          out[o].x += ax[q];
+          out[o].y += ay[q];
+        }
     }
   }
 }
@@ -90,21 +115,41 @@ HD void small_gram_reduce(int n_ctas, const SmallMatList& A, const SmallMatList&
 }
 
 // ---- out[r, c] = alpha * sum_l Y[r, l] cm[l, c] + beta * out[r, c]  for one row r (cm: ny x ncols, leading dim ldcm)
-HD void small_blocks_times_row(long long r, const SmallMatList& Y, const cplx* __restrict__ cm, int ldcm, int ncols,
-                               cplx* __restrict__ out, long long ldo, double alpha, double beta) {
-  double ax[SMALL_MAX_N], ay[SMALL_MAX_N];
-  for (int c = 0; c < ncols; ++c) ax[c] = ay[c] = 0.0;
+// The accumulators of CT columns live in registers (fully unrolled, compile-time indices): a runtime-indexed array of
+// SMALL_MAX_N accumulators sits in local memory and makes every FMA a load + store.  Columns beyond the block's count
+// compute on a clamped column and are dropped; each output still sums l = 0 .. ny-1 in ascending order.
+template <int CT>
+HD void small_blocks_times_chunk(long long r, const SmallMatList& Y, const cplx* __restrict__ cm, int ldcm, int c0, int nc,
+                                 cplx* __restrict__ out, long long ldo, double alpha, double beta) {
+  double ax[CT], ay[CT];
+  int off[CT];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int q = 0; q < CT; ++q) {
+    ax[q] = ay[q] = 0.0;
+    off[q] = ldcm * (c0 + (q < nc ? q : nc - 1));
+  }
   const int ny = Y.start[Y.n];
   for (int l = 0; l < ny; ++l) {
     const cplx y = small_col_ptr(Y, l)[r];
-    for (int c = 0; c < ncols; ++c) {
-      const cplx m = cm[l + ldcm * c];
-      ax[c] += y.x * m.x - y.y * m.y;
-      ay[c] += y.x * m.y + y.y * m.x;
+    const cplx* mrow = cm + l;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < CT; ++q) {
+      const cplx m = mrow[off[q]];
+      ax[q] += y.x * m.x - y.y * m.y;
+      ay[q] += y.x * m.y + y.y * m.x;
     }
   }
-  for (int c = 0; c < ncols; ++c) {
-    cplx o = make_double2(alpha * ax[c], alpha * ay[c]);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int q = 0; q < CT; ++q) {
+    if (q >= nc) continue;
+    const int c = c0 + q;
+    cplx o = make_double2(alpha * ax[q], alpha * ay[q]);
     if (beta != 0.0) {
       const cplx p = out[r + ldo * c];
       o.x += beta * p.x;
@@ -112,6 +157,16 @@ HD void small_blocks_times_row(long long r, const SmallMatList& Y, const cplx* _
     }
     out[r + ldo * c] = o;
   }
+}
+HD void small_blocks_times_row(long long r, const SmallMatList& Y, const cplx* __restrict__ cm, int ldcm, int ncols,
+                               cplx* __restrict__ out, long long ldo, double alpha, double beta) {
+  int c0 = 0;
+  while (ncols - c0 > 8) {
+    const int nc = ncols - c0 < 16 ? ncols - c0 : 16;
+    small_blocks_times_chunk<16>(r, Y, cm, ldcm, c0, nc, out, ldo, alpha, beta);
+    c0 += nc;
+  }
+  if (ncols - c0 > 0) small_blocks_times_chunk<8>(r, Y, cm, ldcm, c0, ncols - c0, out, ldo, alpha, beta);
 }
 
 // ---- X[r, :] <- X[r, :] * invR (upper triangular n x n, column-major with leading dimension ldr), in place

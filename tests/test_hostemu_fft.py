@@ -240,15 +240,16 @@ def test_emulated_small_gram_and_updates(emu, rows, cols_a, cols_b):
             np.testing.assert_allclose(got[keep], ref[keep], rtol=1e-12, atol=1e-11)
             assert upper == 0 or np.all(np.isnan(got[~keep]))                             # skipped blocks stay untouched
     # out = alpha * [A blocks] cm + beta * out
-    ncols = min(7, ta)
-    cm = np.ascontiguousarray(rng.standard_normal((ncols, ta + 1)) + 1j * rng.standard_normal((ncols, ta + 1)))
-    out0 = np.ascontiguousarray(rng.standard_normal((ncols, rows)) + 1j * rng.standard_normal((ncols, rows)))
-    for alpha, beta in ((1.0, 0.0), (-1.0, 1.0)):
-        out = out0.copy()
-        assert emu.emu_small_blocks_times(*_lists(A), _p(cm), ta + 1, ncols, _p(out), ctypes.c_int64(rows),
-                                          ctypes.c_int64(rows), ctypes.c_double(alpha), ctypes.c_double(beta)) == 0
-        want = alpha * (Afull @ cm[:, :ta].T) + beta * out0.T
-        np.testing.assert_allclose(out.T, want, rtol=1e-12, atol=1e-11)
+    # (the column counts cover the 8-wide register chunk, the 16-wide one, a 16 + 8 split and the 32-column maximum)
+    for ncols in (min(7, ta), 1, 8, 9, 15, 16, 20, 32):
+        cm = np.ascontiguousarray(rng.standard_normal((ncols, ta + 1)) + 1j * rng.standard_normal((ncols, ta + 1)))
+        out0 = np.ascontiguousarray(rng.standard_normal((ncols, rows)) + 1j * rng.standard_normal((ncols, rows)))
+        for alpha, beta in ((1.0, 0.0), (-1.0, 1.0)):
+            out = out0.copy()
+            assert emu.emu_small_blocks_times(*_lists(A), _p(cm), ta + 1, ncols, _p(out), ctypes.c_int64(rows),
+                                              ctypes.c_int64(rows), ctypes.c_double(alpha), ctypes.c_double(beta)) == 0
+            want = alpha * (Afull @ cm[:, :ta].T) + beta * out0.T
+            np.testing.assert_allclose(out.T, want, rtol=1e-12, atol=1e-11)
 
 
 @pytest.mark.parametrize("n", [1, 7, 15, 32])
