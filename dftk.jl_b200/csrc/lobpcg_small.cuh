@@ -169,18 +169,40 @@ HD void small_blocks_times_row(long long r, const SmallMatList& Y, const cplx* _
   if (ncols - c0 > 0) small_blocks_times_chunk<8>(r, Y, cm, ldcm, c0, ncols - c0, out, ldo, alpha, beta);
 }
 
-// ---- X[r, :] <- X[r, :] * invR (upper triangular n x n, column-major with leading dimension ldr), in place
+// ---- X[r, :] <- X[r, :] * invR (upper triangular n x n, column-major with leading dimension ldr), in place.
+// Output columns are produced in chunks of 8 from the highest down, the accumulators of a chunk in registers: column j needs
+// the ORIGINAL x[l] for l <= j only, and a chunk is written after all its sums are complete, so lower chunks still read
+// originals.  Each output sums l = 0 .. j in ascending order (as the plain row-cached form did).
 HD void small_rmul_row(long long r, cplx* __restrict__ X, long long ld, int n, const cplx* __restrict__ Rinv, int ldr) {
-  cplx x[SMALL_MAX_N];
-  for (int l = 0; l < n; ++l) x[l] = X[r + ld * l];
-  for (int j = n - 1; j >= 0; --j) {
-    double sx = 0.0, sy = 0.0;
-    for (int l = 0; l <= j; ++l) {
-      const cplx m = Rinv[l + ldr * j];
-      sx += x[l].x * m.x - x[l].y * m.y;
-      sy += x[l].x * m.y + x[l].y * m.x;
+  for (int j0 = ((n - 1) / 8) * 8; j0 >= 0; j0 -= 8) {
+    double sx[8], sy[8];
+    int jq[8];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < 8; ++q) {
+      sx[q] = sy[q] = 0.0;
+      jq[q] = j0 + q < n ? j0 + q : n - 1;       // columns beyond n compute on a valid one and are dropped
     }
-    X[r + ld * j] = make_double2(sx, sy);
+    const int lmax = j0 + 7 < n - 1 ? j0 + 7 : n - 1;
+    for (int l = 0; l <= lmax; ++l) {
+      const cplx x = X[r + ld * l];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int q = 0; q < 8; ++q) {
+        if (l <= j0 + q) {                         // upper triangular: row l enters the columns j >= l
+          const cplx m = Rinv[l + ldr * jq[q]];
+          sx[q] += x.x * m.x - x.y * m.y;
+          sy[q] += x.x * m.y + x.y * m.x;
+        }
+      }
+    }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < 8; ++q)
+      if (j0 + q < n) X[r + ld * (j0 + q)] = make_double2(sx[q], sy[q]);
   }
 }
 
