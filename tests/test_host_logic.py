@@ -251,3 +251,40 @@ def test_smearing_functions_satisfy_reference_identities():
     for kind in ("FermiDirac", "Gaussian", "None"):
         np.testing.assert_allclose(pf(kind, x), of(kind, x), atol=1e-16)
         np.testing.assert_allclose(ps(kind, x), os_(kind, x), atol=1e-16)
+
+
+def test_occupation_metal_many_blocks_matches_blockwise_sum():
+    """The Fermi level is bisected over ONE flat array of all eigenvalues (the per-block Python loop was a third of a metal's
+    SCF step): the result must satisfy the electron-count equation of occupation.jl:30-50 evaluated block by block."""
+    import dftk_b200 as dftk
+    from dftk_b200.occupation import compute_occupation
+    from dftk_b200.terms import smearing_occupation
+    Si = dftk.ElementPsp("Si")
+    mm = dftk.model_DFT(LATTICE, [Si, Si], POSITIONS, functionals=dftk.LDA(), temperature=0.01)
+    rng = np.random.default_rng(7)
+    nk = 84
+    w = rng.random(nk)
+    w /= w.sum()
+    eig = [np.sort(rng.normal(0.2, 0.3, 9)) for _ in range(nk)]
+    b = _FakeBasis(mm, list(w), dftk.KpointComm())
+    occ, eF = compute_occupation(b, eig)
+    n_el = sum(wk * (2 * smearing_occupation("FermiDirac", (e - eF) / 0.01)).sum() for wk, e in zip(w, eig))
+    assert abs(n_el - 8) < 1e-9
+    assert all(np.allclose(o, 2 * smearing_occupation("FermiDirac", (e - eF) / 0.01), atol=1e-14) for o, e in zip(occ, eig))
+
+
+def test_slab_mode_decisions_and_band_shares():
+    """Single-k multi-GPU (comm_slab): which blocks take the slab eigensolver, and the band shares of compute_density."""
+    from types import SimpleNamespace
+    from dftk_b200.eigen import _use_slabs
+    comm = SimpleNamespace(nranks=4, rank=1)
+    A = SimpleNamespace(basis=SimpleNamespace(comm_slab=comm))
+    assert _use_slabs(A, torch.empty((503, 264859), device="meta"))
+    assert not _use_slabs(A, torch.empty((15, 5440), device="meta"))            # batched small-block regime
+    assert not _use_slabs(A, torch.empty((111, 1200), device="meta"))           # slabs of <= 3 n_bands rows: the solver refuses
+    assert not _use_slabs(SimpleNamespace(basis=SimpleNamespace(comm_slab=None)), torch.empty((503, 264859), device="meta"))
+    for nb in (0, 1, 7, 500, 503):
+        for R in (1, 2, 3, 4, 8):
+            shares = [range((nb * r) // R, (nb * (r + 1)) // R) for r in range(R)]
+            assert [i for s in shares for i in s] == list(range(nb))            # contiguous, disjoint, complete
+            assert max(len(s) for s in shares) - min(len(s) for s in shares) <= 1
